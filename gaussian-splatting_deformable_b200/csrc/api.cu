@@ -1,0 +1,320 @@
+// extern "C" entry points of libgsr_b200.so (declared in include/gsr_b200.h).
+// Host-side sequencing only: workspace carving and kernel launches on the
+// caller's stream.  Mirrors CudaRasterizer::Rasterizer::{forward,backward,
+// markVisible} (rasterizer_impl.cu:141-153,198-434) behind a C ABI.
+#include "../../include/gsr_b200.h"
+#include "kernels.cuh"
+#include <stdio.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+int gsr_set_error(cudaError_t e, const char* what, const char* file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    return (int)e;
+}
+int gsr_set_error_msg(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "gsr error %d: %s", code, msg);
+    return code;
+}
+
+namespace {
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct GeomLayout { size_t depths, tiles, recs, clamped, offsets, cov3d, block_sums, total, bytes; };
+GeomLayout geom_layout(int P) {
+    GeomLayout L{};
+    size_t o = 0;
+    const size_t p = (size_t)(P > 0 ? P : 0);
+    L.depths = o; o += al(4 * p);
+    L.tiles = o; o += al(4 * p);
+    L.recs = o; o += al(48 * p);
+    L.clamped = o; o += al(p);
+    L.offsets = o; o += al(4 * p);
+    L.cov3d = o; o += al(24 * p);
+    L.block_sums = o; o += al(4 * ((p + 255) / 256 + 1));
+    L.total = o; o += 256;
+    L.bytes = o;
+    return L;
+}
+struct ImageLayout { size_t final_T, n_contrib, ranges, bytes; };
+ImageLayout image_layout(int W, int H) {
+    ImageLayout L{};
+    const size_t n = (size_t)W * H;
+    const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
+    size_t o = 0;
+    L.final_T = o; o += al(4 * n);
+    L.n_contrib = o; o += al(4 * n);
+    L.ranges = o; o += al(8 * tiles);
+    L.bytes = o;
+    return L;
+}
+// Bits of the tile id, as the reference's getHigherMsb (rasterizer_impl.cu:35-50).
+int tile_bits(uint32_t n) {
+    int msb = 16, step = 16;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+struct BinLayout { size_t keys_a, keys_b, vals_a, vals_b, sort_temp, sort_temp_bytes, bytes; int end_bit; int passes; };
+BinLayout bin_layout(uint32_t R, int W, int H) {
+    BinLayout L{};
+    const uint32_t tiles = (uint32_t)((W + 15) / 16) * ((H + 15) / 16);
+    L.end_bit = 32 + tile_bits(tiles);
+    L.passes = (L.end_bit + 7) / 8;
+    size_t o = 0;
+    L.keys_a = o; o += al(8 * (size_t)R);
+    L.keys_b = o; o += al(8 * (size_t)R);
+    L.vals_a = o; o += al(4 * (size_t)R);
+    L.vals_b = o; o += al(4 * (size_t)R);
+    L.sort_temp = o; L.sort_temp_bytes = gsr_sort_temp_bytes(R, 0, L.end_bit); o += al(L.sort_temp_bytes);
+    L.bytes = o + 256;
+    return L;
+}
+
+int fill_view(const gsr_view* s, int M, GsrView& v) {
+    if (!s) return gsr_set_error_msg(-1, "view is NULL");
+    memcpy(v.view, s->viewmatrix, sizeof(v.view));
+    memcpy(v.proj, s->projmatrix, sizeof(v.proj));
+    memcpy(v.campos, s->campos, sizeof(v.campos));
+    v.tan_fovx = s->tanfovx; v.tan_fovy = s->tanfovy;
+    v.W = s->image_width; v.H = s->image_height;
+    // rasterizer_impl.cu:222-223
+    v.focal_y = v.H / (2.0f * v.tan_fovy);
+    v.focal_x = v.W / (2.0f * v.tan_fovx);
+    v.scale_modifier = s->scale_modifier;
+    v.grid_x = (v.W + GSR_TILE - 1) / GSR_TILE;
+    v.grid_y = (v.H + GSR_TILE - 1) / GSR_TILE;
+    v.sh_degree = s->sh_degree;
+    v.sh_coeffs = M;
+    if (v.W <= 0 || v.H <= 0) return gsr_set_error_msg(-1, "image size must be positive");
+    if (v.grid_x >= 65536 || v.grid_y >= 65536) return gsr_set_error_msg(-1, "image too large");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gsr_last_error_string(void) { return g_err; }
+int gsr_version(void) { return 100; }
+
+size_t gsr_geom_bytes(int P) { return geom_layout(P).bytes; }
+size_t gsr_image_bytes(int W, int H) { return image_layout(W, H).bytes; }
+size_t gsr_binning_bytes(uint32_t R, int W, int H) { return bin_layout(R, W, H).bytes; }
+size_t gsr_grad_bytes(int P) { return al(48 * (size_t)(P > 0 ? P : 0)) + 256; }
+
+void gsr_geom_layout(int P, size_t out[6]) {
+    const GeomLayout L = geom_layout(P);
+    out[0] = L.depths; out[1] = L.tiles; out[2] = L.recs; out[3] = L.clamped; out[4] = L.offsets; out[5] = L.cov3d;
+}
+void gsr_image_layout(int W, int H, size_t out[3]) {
+    const ImageLayout L = image_layout(W, H);
+    out[0] = L.final_T; out[1] = L.n_contrib; out[2] = L.ranges;
+}
+void gsr_binning_layout(uint32_t R, int W, int H, size_t out[4]) {
+    const BinLayout L = bin_layout(R, W, H);
+    const bool in_b = (L.passes & 1) != 0;
+    out[0] = in_b ? L.keys_b : L.keys_a;
+    out[1] = in_b ? L.vals_b : L.vals_a;
+    out[2] = in_b ? L.keys_a : L.keys_b;   // where the unsorted input was (overwritten by ping-pong if passes > 1)
+    out[3] = in_b ? L.vals_a : L.vals_b;
+}
+
+int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* means3D, const float* scales,
+                           const float* rotations, const float* opacities, const float* shs,
+                           const float* cov3D_precomp, const float* colors_precomp, const gsr_deform* deform,
+                           float* means_out, int32_t* radii, void* geom_ws, size_t geom_bytes,
+                           uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (host_num_rendered) *host_num_rendered = 0;
+    if (P < 0) return gsr_set_error_msg(-1, "P must be >= 0");
+    if (P == 0) return 0;
+    GsrView v;
+    if (int rc = fill_view(view, M, v)) return rc;
+    if (!means3D || !opacities || !radii || !geom_ws || !host_num_rendered)
+        return gsr_set_error_msg(-1, "forward_preprocess: required pointer is NULL");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+        return gsr_set_error_msg(-1, "provide exactly one of SHs or precomputed colors");
+    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+        return gsr_set_error_msg(-1, "provide exactly one of scale/rotation pair or precomputed 3D covariance");
+    if (shs && (M <= 0 || M > 16 || (v.sh_degree + 1) * (v.sh_degree + 1) > M || v.sh_degree > 3 || v.sh_degree < 0))
+        return gsr_set_error_msg(-1, "SH layout: need 0 <= degree <= 3 and (degree+1)^2 <= M <= 16");
+    const GeomLayout L = geom_layout(P);
+    if (geom_bytes < L.bytes) return gsr_set_error_msg(-3, "geometry workspace too small");
+    char* ws = reinterpret_cast<char*>(geom_ws);
+    PreprocessArgs a{};
+    a.P = P; a.means = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities; a.shs = shs;
+    a.cov3D_precomp = cov3D_precomp; a.colors_precomp = colors_precomp;
+    a.deform_mode = deform ? deform->mode : GSR_DEFORM_NONE;
+    if (a.deform_mode != GSR_DEFORM_NONE) {
+        if (!deform->S || !deform->theta || !means_out) return gsr_set_error_msg(-1, "deform: S, theta and means_out required");
+        if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && !deform->body_id) return gsr_set_error_msg(-1, "deform: body_id required");
+        a.twist_S = deform->S; a.twist_theta = deform->theta; a.body_id = deform->body_id;
+    }
+    a.means_out = means_out;
+    a.radii = radii;
+    a.depths = reinterpret_cast<float*>(ws + L.depths);
+    a.tiles_touched = reinterpret_cast<uint32_t*>(ws + L.tiles);
+    a.recs = reinterpret_cast<float4*>(ws + L.recs);
+    a.clamped = reinterpret_cast<uint8_t*>(ws + L.clamped);
+    a.cov3D_out = debug_dump_cov3D ? reinterpret_cast<float*>(ws + L.cov3d) : nullptr;
+    a.block_sums = reinterpret_cast<uint32_t*>(ws + L.block_sums);
+    if (int rc = gsr_launch_preprocess_fwd(a, v, stream)) return rc;
+    uint32_t* d_total = reinterpret_cast<uint32_t*>(ws + L.total);
+    if (int rc = gsr_launch_scan_block_sums(a.block_sums, gsr_div_up(P, 256), d_total, stream)) return rc;
+    GSR_CHECK(cudaMemcpyAsync(host_num_rendered, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GSR_CHECK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* radii, void* geom_ws, void* binning_ws,
+                       size_t binning_bytes, void* image_ws, float* out_color, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GsrView v;
+    if (int rc = fill_view(view, 0, v)) return rc;
+    if (!image_ws || !out_color) return gsr_set_error_msg(-1, "forward_render: required pointer is NULL");
+    const ImageLayout IL = image_layout(v.W, v.H);
+    char* iw = reinterpret_cast<char*>(image_ws);
+    uint2* ranges = reinterpret_cast<uint2*>(iw + IL.ranges);
+    const int num_tiles = v.grid_x * v.grid_y;
+    const uint32_t* point_list = nullptr;
+    const float4* recs = nullptr;
+    if (P > 0 && R > 0) {
+        if (!geom_ws || !binning_ws || !radii) return gsr_set_error_msg(-1, "forward_render: workspace is NULL");
+        if (R >= (1u << 30)) return gsr_set_error_msg(-2, "num_rendered must be < 2^30");
+        const GeomLayout L = geom_layout(P);
+        const BinLayout BL = bin_layout(R, v.W, v.H);
+        if (binning_bytes < BL.bytes) return gsr_set_error_msg(-3, "binning workspace too small");
+        char* gw = reinterpret_cast<char*>(geom_ws);
+        char* bw = reinterpret_cast<char*>(binning_ws);
+        recs = reinterpret_cast<const float4*>(gw + L.recs);
+        uint64_t* keys_a = reinterpret_cast<uint64_t*>(bw + BL.keys_a);
+        uint64_t* keys_b = reinterpret_cast<uint64_t*>(bw + BL.keys_b);
+        uint32_t* vals_a = reinterpret_cast<uint32_t*>(bw + BL.vals_a);
+        uint32_t* vals_b = reinterpret_cast<uint32_t*>(bw + BL.vals_b);
+        if (int rc = gsr_launch_duplicate(P, radii, reinterpret_cast<const float*>(gw + L.depths),
+                                          reinterpret_cast<const uint32_t*>(gw + L.tiles), recs,
+                                          reinterpret_cast<const uint32_t*>(gw + L.block_sums),
+                                          reinterpret_cast<uint32_t*>(gw + L.offsets), keys_a, vals_a, v.grid_x, v.grid_y,
+                                          stream))
+            return rc;
+        int in_b = 0;
+        if (int rc = gsr_launch_sort_pairs(keys_a, keys_b, vals_a, vals_b, R, 0, BL.end_bit, bw + BL.sort_temp,
+                                           BL.sort_temp_bytes, &in_b, stream))
+            return rc;
+        const uint64_t* sorted_keys = in_b ? keys_b : keys_a;
+        point_list = in_b ? vals_b : vals_a;
+        if (int rc = gsr_launch_tile_ranges(R, sorted_keys, ranges, num_tiles, stream)) return rc;
+    } else {
+        GSR_CHECK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
+    }
+    BlendFwdArgs b{};
+    b.ranges = ranges; b.point_list = point_list; b.recs = recs;
+    b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
+    b.bg[0] = view->bg[0]; b.bg[1] = view->bg[1]; b.bg[2] = view->bg[2];
+    b.out_color = out_color;
+    b.final_T = reinterpret_cast<float*>(iw + IL.final_T);
+    b.n_contrib = reinterpret_cast<uint32_t*>(iw + IL.n_contrib);
+    return gsr_launch_blend_fwd(b, stream);
+}
+
+int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* means3D, const float* means_deformed,
+                 const float* scales, const float* rotations, const float* shs, const float* cov3D_precomp,
+                 const float* colors_precomp, const gsr_deform* deform, const int32_t* radii, const void* geom_ws,
+                 const void* binning_ws, const void* image_ws, void* grad_ws, const float* dL_dout_color,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dopacity, float* dL_dcolors, float* dL_dcov3D,
+                 float* dL_dsh, float* dL_dscales, float* dL_drots, float* dL_dtwist_S, float* dL_dtwist_theta,
+                 void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P <= 0) return 0;
+    GsrView v;
+    if (int rc = fill_view(view, M, v)) return rc;
+    if (!means3D || !radii || !geom_ws || !image_ws || !grad_ws || !dL_dout_color || !dL_dmeans3D || !dL_dmeans2D ||
+        !dL_dopacity || !dL_dcolors || !dL_dcov3D)
+        return gsr_set_error_msg(-1, "backward: required pointer is NULL");
+    if (shs && !dL_dsh) return gsr_set_error_msg(-1, "backward: dL_dsh required when shs given");
+    const GeomLayout L = geom_layout(P);
+    const ImageLayout IL = image_layout(v.W, v.H);
+    const char* gw = reinterpret_cast<const char*>(geom_ws);
+    const char* iw = reinterpret_cast<const char*>(image_ws);
+    float4* grad_recs = reinterpret_cast<float4*>(grad_ws);
+    GSR_CHECK(cudaMemsetAsync(grad_recs, 0, 48 * (size_t)P, stream));
+    if (R > 0) {
+        if (!binning_ws) return gsr_set_error_msg(-1, "backward: binning workspace is NULL");
+        const BinLayout BL = bin_layout(R, v.W, v.H);
+        const char* bw = reinterpret_cast<const char*>(binning_ws);
+        const bool in_b = (BL.passes & 1) != 0;
+        BlendBwdArgs b{};
+        b.ranges = reinterpret_cast<const uint2*>(iw + IL.ranges);
+        b.point_list = reinterpret_cast<const uint32_t*>(bw + (in_b ? BL.vals_b : BL.vals_a));
+        b.recs = reinterpret_cast<const float4*>(gw + L.recs);
+        b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
+        b.bg[0] = view->bg[0]; b.bg[1] = view->bg[1]; b.bg[2] = view->bg[2];
+        b.final_T = reinterpret_cast<const float*>(iw + IL.final_T);
+        b.n_contrib = reinterpret_cast<const uint32_t*>(iw + IL.n_contrib);
+        b.dL_dpix = dL_dout_color;
+        b.grad_recs = grad_recs;
+        if (int rc = gsr_launch_blend_bwd(b, stream)) return rc;
+    }
+    PreprocessBwdArgs a{};
+    a.P = P; a.means = means3D;
+    a.deform_mode = deform ? deform->mode : GSR_DEFORM_NONE;
+    a.means_deformed = (a.deform_mode != GSR_DEFORM_NONE) ? means_deformed : nullptr;
+    if (a.deform_mode != GSR_DEFORM_NONE) {
+        if (!means_deformed || !deform->S || !deform->theta) return gsr_set_error_msg(-1, "backward: deform inputs missing");
+        a.twist_S = deform->S; a.twist_theta = deform->theta; a.body_id = deform->body_id; a.num_bodies = deform->num_bodies;
+        if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && (!deform->body_id || deform->num_bodies <= 0))
+            return gsr_set_error_msg(-1, "backward: body_id / num_bodies required");
+        if ((dL_dtwist_S == nullptr) != (dL_dtwist_theta == nullptr))
+            return gsr_set_error_msg(-1, "backward: give both twist gradients or neither");
+    }
+    a.scales = scales; a.rotations = rotations; a.shs = shs; a.cov3D_precomp = cov3D_precomp; a.colors_precomp = colors_precomp;
+    a.radii = radii; a.clamped = reinterpret_cast<const uint8_t*>(gw + L.clamped); a.grad_recs = grad_recs;
+    a.dL_dmeans3D = dL_dmeans3D; a.dL_dmeans2D = dL_dmeans2D; a.dL_dopacity = dL_dopacity; a.dL_dcolors = dL_dcolors;
+    a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = scales ? dL_dscales : nullptr;
+    a.dL_drots = scales ? dL_drots : nullptr;
+    a.dL_dtwist_S = dL_dtwist_S; a.dL_dtwist_theta = dL_dtwist_theta;
+    return gsr_launch_preprocess_bwd(a, v, stream);
+}
+
+int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t* present, void* stream_) {
+    if (P <= 0) return 0;
+    GsrView v;
+    gsr_view tmp = *view;
+    if (tmp.image_width <= 0) tmp.image_width = 16;      // markVisible only needs the view matrix
+    if (tmp.image_height <= 0) tmp.image_height = 16;
+    if (int rc = fill_view(&tmp, 0, v)) return rc;
+    if (!means3D || !present) return gsr_set_error_msg(-1, "mark_visible: NULL pointer");
+    return gsr_launch_mark_visible(P, means3D, v, present, (cudaStream_t)stream_);
+}
+
+size_t gsr_knn_bytes(int P) { return gsr_knn_temp_bytes(P); }
+int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream_) {
+    if (P > 0 && (!points || !mean_dist2 || !temp)) return gsr_set_error_msg(-1, "knn: NULL pointer");
+    return gsr_launch_knn_dist2(P, points, mean_dist2, temp, temp_bytes, (cudaStream_t)stream_);
+}
+
+int gsr_exp_se3(int N, const float* S, const float* theta, float* T44, void* stream_) {
+    if (N > 0 && (!S || !theta || !T44)) return gsr_set_error_msg(-1, "exp_se3: NULL pointer");
+    return gsr_launch_se3_matrices(N, S, theta, T44, (cudaStream_t)stream_);
+}
+int gsr_exp_se3_backward(int N, const float* S, const float* theta, const float* dT44, float* dS, float* dtheta,
+                         void* stream_) {
+    if (N > 0 && (!S || !theta || !dT44 || !dS || !dtheta)) return gsr_set_error_msg(-1, "exp_se3_backward: NULL pointer");
+    return gsr_launch_se3_matrices_bwd(N, S, theta, dT44, dS, dtheta, (cudaStream_t)stream_);
+}
+
+size_t gsr_sort_bytes(uint32_t n, int begin_bit, int end_bit) { return gsr_sort_temp_bytes(n, begin_bit, end_bit); }
+int gsr_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n, int begin_bit,
+                   int end_bit, void* temp, size_t temp_bytes, int* result_in_b, void* stream_) {
+    int dummy = 0;
+    return gsr_launch_sort_pairs(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
+                                 result_in_b ? result_in_b : &dummy, (cudaStream_t)stream_);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Shared declarations for the sm_100a deformable-Gaussian rasterizer kernels.
+//
+// Everything here is device-side plumbing for the C-ABI in include/gsr_b200.h.
+// No torch, no glm, no CUB: the library links against the CUDA runtime only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GSR_TILE 16              // reference: BLOCK_X = BLOCK_Y = 16 (cuda_rasterizer/config.h:16-17)
+#define GSR_TILE_PIX 256
+#define GSR_NEAR 0.2f            // reference near plane (auxiliary.h:154)
+
+// ---------------------------------------------------------------------------
+// Camera / view constants, passed by value (lives in the constant bank, so the
+// 35 matrix words are LDC broadcasts instead of global loads).
+// Matrices keep the reference's memory convention: 16 floats, true row i is
+// (m[i], m[i+4], m[i+8], m[i+12])  (auxiliary.h:58-76).
+// ---------------------------------------------------------------------------
+struct GsrView {
+    float view[16];
+    float proj[16];
+    float campos[3];
+    float tan_fovx, tan_fovy;
+    float focal_x, focal_y;      // W / (2 tan_fovx), H / (2 tan_fovy)  (rasterizer_impl.cu:222-223)
+    float scale_modifier;
+    int W, H;
+    int grid_x, grid_y;          // ceil(W/16), ceil(H/16)
+    int sh_degree;               // active degree D
+    int sh_coeffs;               // M = coefficients stored per Gaussian (0 => no SH)
+};
+
+// Per-Gaussian "splat record" consumed by the blend kernels: 3 x float4 = 48 B,
+// contiguous so one list entry is one 48-byte gather (one TMA bulk copy).
+//   q0 = (x, y, conic.x, conic.y)   q1 = (conic.z, opacity, r, g)
+//   q2 = (b, power_cut, 0, 0)
+// power_cut: a pixel whose power is below it can never reach alpha >= 1/255
+// (log(1/(255*opacity)) minus a safety margin) -- lets the blend loops reject
+// without evaluating expf, with decisions identical to the reference's.
+#define GSR_REC_F4 3
+
+// 12-float gradient record accumulated by blend backward, consumed by the
+// fused per-Gaussian backward:
+//   g0 = (dL_dmean2D.x, dL_dmean2D.y, dL_dconic.x, dL_dconic.y)
+//   g1 = (dL_dconic.w(zz), dL_dopacity, dL_dcolor.r, dL_dcolor.g)
+//   g2 = (dL_dcolor.b, 0, 0, 0)
+#define GSR_GRAD_F4 3
+
+// Deformation modes fused into preprocess (scene/rigid_body.py:86-93 + the
+// apply recipe gaussian_renderer/__init__.py:92-95).
+#define GSR_DEFORM_NONE 0
+#define GSR_DEFORM_PER_GAUSSIAN 1   // S[P,6], theta[P]
+#define GSR_DEFORM_RIGID_BODIES 2   // body_id[P], S[B,6], theta[B]
+
+#define GSR_CHECK(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return gsr_set_error(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define GSR_CHECK_LAUNCH() GSR_CHECK(cudaGetLastError())
+
+int gsr_set_error(cudaError_t e, const char* what, const char* file, int line);
+int gsr_set_error_msg(int code, const char* msg);
+
+static inline int gsr_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// SE3 exponential map applied to a point (closed form of rigid_body.exp_se3
+// followed by y = (T [x;1])[:3]):
+//   R = I + sin(th) W + (1-cos(th)) W^2
+//   p = (th I + (1-cos(th)) W + (th - sin(th)) W^2) v
+//   y = R x + p,  with  W u = w x u  and  W^2 u = w (w.u) - (w.w) u
+// ---------------------------------------------------------------------------
+struct Se3Coef { float a, b, c; };  // sin(th), 1-cos(th), th-sin(th)
+
+__device__ __forceinline__ Se3Coef se3_coef(float th) {
+    float s, c;
+    sincosf(th, &s, &c);
+    Se3Coef k; k.a = s; k.b = 1.0f - c; k.c = th - s; return k;
+}
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// W^2 u
+__device__ __forceinline__ float3 skew2(float3 w, float3 u) {
+    float wu = dot3(w, u), ww = dot3(w, w);
+    return make_float3(w.x * wu - ww * u.x, w.y * wu - ww * u.y, w.z * wu - ww * u.z);
+}
+__device__ __forceinline__ float3 se3_apply(float3 x, float3 w, float3 v, float th) {
+    Se3Coef k = se3_coef(th);
+    float3 wx = cross3(w, x), wwx = skew2(w, x);
+    float3 wv = cross3(w, v), wwv = skew2(w, v);
+    float3 y;
+    y.x = x.x + k.a * wx.x + k.b * wwx.x + th * v.x + k.b * wv.x + k.c * wwv.x;
+    y.y = x.y + k.a * wx.y + k.b * wwx.y + th * v.y + k.b * wv.y + k.c * wwv.y;
+    y.z = x.z + k.a * wx.z + k.b * wwx.z + th * v.z + k.b * wv.z + k.c * wwv.z;
+    return y;
+}

@@ -1,0 +1,103 @@
+// Kernel argument blocks and host-side launchers shared between the .cu files
+// and the C-ABI (api.cu).  All pointers are device pointers unless noted.
+#pragma once
+#include "common.cuh"
+
+struct PreprocessArgs {
+    int P;
+    const float* means;          // [P,3] un-deformed
+    const float* scales;         // [P,3] or null
+    const float* rotations;      // [P,4] or null
+    const float* opacities;      // [P]
+    const float* shs;            // [P,M,3] or null
+    const float* cov3D_precomp;  // [P,6] or null
+    const float* colors_precomp; // [P,3] or null
+    int deform_mode;
+    const float* twist_S;        // [P,6] or [B,6]
+    const float* twist_theta;    // [P] or [B]
+    const int* body_id;          // [P] (rigid-body mode)
+    float* means_out;            // [P,3] deformed means (required when deform_mode != 0)
+    int* radii;                  // [P]
+    float* depths;               // [P]
+    uint32_t* tiles_touched;     // [P]
+    float4* recs;                // [P,3] splat records
+    uint8_t* clamped;            // [P] bit c set when colour channel c was clamped at 0
+    float* cov3D_out;            // [P,6] or null (parity dumps)
+    uint32_t* block_sums;        // [ceil(P/256)] sum of tiles_touched per 256-Gaussian block
+};
+
+int gsr_launch_preprocess_fwd(const PreprocessArgs& a, const GsrView& v, cudaStream_t stream);
+int gsr_launch_mark_visible(int P, const float* means, const GsrView& v, uint8_t* present, cudaStream_t stream);
+
+// ---- binning -------------------------------------------------------------
+// Exclusive scan of the per-block sums in place; total -> *d_total.
+int gsr_launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* d_total, cudaStream_t stream);
+// rasterizer_impl.cu:70-111 duplicateWithKeys (block-cooperative, balanced).
+int gsr_launch_duplicate(int P, const int* radii, const float* depths, const uint32_t* tiles_touched,
+                         const float4* recs, const uint32_t* block_offsets, uint32_t* point_offsets /*or null*/,
+                         uint64_t* keys, uint32_t* vals, int grid_x, int grid_y, cudaStream_t stream);
+// rasterizer_impl.cu:116-138 identifyTileRanges (+ the memset of :310).
+int gsr_launch_tile_ranges(uint32_t R, const uint64_t* sorted_keys, uint2* ranges, int num_tiles, cudaStream_t stream);
+
+// ---- onesweep radix sort of (u64 key, u32 value) pairs --------------------
+size_t gsr_sort_temp_bytes(uint32_t n, int begin_bit, int end_bit);
+// Sorts on bits [begin_bit, end_bit).  Ping-pongs between the a/b buffers and
+// returns (through *result_in_b) where the sorted data ended up.
+int gsr_launch_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n,
+                          int begin_bit, int end_bit, void* temp, size_t temp_bytes, int* result_in_b,
+                          cudaStream_t stream);
+
+// ---- blending -------------------------------------------------------------
+struct BlendFwdArgs {
+    const uint2* ranges; const uint32_t* point_list; const float4* recs;
+    int W, H, grid_x, grid_y;
+    float bg[3];
+    float* out_color;        // [3,H,W]
+    float* final_T;          // [H*W]
+    uint32_t* n_contrib;     // [H*W]
+};
+int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream);
+
+struct BlendBwdArgs {
+    const uint2* ranges; const uint32_t* point_list; const float4* recs;
+    int W, H, grid_x, grid_y;
+    float bg[3];
+    const float* final_T; const uint32_t* n_contrib;
+    const float* dL_dpix;    // [3,H,W]
+    float4* grad_recs;       // [P,3], zero-initialised by the caller
+};
+int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream);
+
+// ---- fused per-Gaussian backward ------------------------------------------
+struct PreprocessBwdArgs {
+    int P;
+    const float* means;          // [P,3] un-deformed input means
+    const float* means_deformed; // [P,3] or null when deform_mode == NONE (then == means)
+    const float* scales; const float* rotations; const float* shs;
+    const float* cov3D_precomp; const float* colors_precomp;
+    int deform_mode; const float* twist_S; const float* twist_theta; const int* body_id; int num_bodies;
+    const int* radii; const uint8_t* clamped;
+    const float4* grad_recs;     // [P,3] from blend backward
+    // outputs (every element written, zeros for culled Gaussians)
+    float* dL_dmeans3D;          // [P,3]  w.r.t. the un-deformed means
+    float* dL_dmeans2D;          // [P,3]
+    float* dL_dopacity;          // [P]
+    float* dL_dcolors;           // [P,3]  (meaningful when colors_precomp given)
+    float* dL_dcov3D;            // [P,6]
+    float* dL_dsh;               // [P,M,3] or null
+    float* dL_dscales;           // [P,3] or null
+    float* dL_drots;             // [P,4] or null
+    float* dL_dtwist_S;          // [P,6] direct, or [B,6] accumulated (pre-zeroed), or null
+    float* dL_dtwist_theta;      // [P] or [B] (pre-zeroed), or null
+};
+int gsr_launch_preprocess_bwd(const PreprocessBwdArgs& a, const GsrView& v, cudaStream_t stream);
+
+// ---- standalone SE3 (rigid_body drop-in) ------------------------------------
+int gsr_launch_se3_matrices(int N, const float* S, const float* theta, float* T44, cudaStream_t stream);
+int gsr_launch_se3_matrices_bwd(int N, const float* S, const float* theta, const float* dT44, float* dS,
+                                float* dtheta, cudaStream_t stream);
+
+// ---- kNN -------------------------------------------------------------------
+size_t gsr_knn_temp_bytes(int P);
+int gsr_launch_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes,
+                         cudaStream_t stream);

@@ -1,0 +1,170 @@
+// Fused SE3-deform + preprocess forward, and the frustum test (markVisible).
+//
+// Replaces, in one pass over the Gaussians:
+//   scene/rigid_body.py:86-93  exp_se3  +  gaussian_renderer/__init__.py:92-95 apply
+//   cuda_rasterizer/forward.cu:155-256  preprocessCUDA<3>
+//   the per-block partial sums of cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:277)
+//
+// HBM-bound kernel: 236 B in (+28 B twist) and ~84 B out per Gaussian.  One thread
+// per Gaussian; the 192-byte SH record and the 48-byte splat record are moved as
+// 128-bit vectors; SH is only touched for Gaussians that survive culling.
+#include "geom_exact.cuh"
+#include "kernels.cuh"
+
+// Spherical-harmonics constants (same values as auxiliary.h:22-38 / utils/sh_utils.py).
+__device__ __constant__ float kSH_C0 = 0.28209479177387814f;
+__device__ __constant__ float kSH_C1 = 0.4886025119029199f;
+__device__ __constant__ float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                           -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                           0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                           -0.5900435899266435f};
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 operator*(float s, V3 v) { return {s * v.x, s * v.y, s * v.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+
+// forward.cu:20-71.  `sh` points at this Gaussian's M x 3 coefficients already in
+// registers/local (48 floats for M = 16).  Returns the un-clamped colour + 0.5.
+template <typename ShFetch>
+__device__ __forceinline__ V3 sh_to_rgb(int deg, float3 pos, const float* campos, ShFetch sh) {
+    V3 dir = {pos.x - campos[0], pos.y - campos[1], pos.z - campos[2]};
+    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
+    V3 result = kSH_C0 * sh(0);
+    if (deg > 0) {
+        const float x = dir.x, y = dir.y, z = dir.z;
+        result = result - kSH_C1 * y * sh(1) + kSH_C1 * z * sh(2) - kSH_C1 * x * sh(3);
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z;
+            const float xy = x * y, yz = y * z, xz = x * z;
+            result = result + kSH_C2[0] * xy * sh(4) + kSH_C2[1] * yz * sh(5) +
+                     kSH_C2[2] * (2.0f * zz - xx - yy) * sh(6) + kSH_C2[3] * xz * sh(7) +
+                     kSH_C2[4] * (xx - yy) * sh(8);
+            if (deg > 2) {
+                result = result + kSH_C3[0] * y * (3.0f * xx - yy) * sh(9) + kSH_C3[1] * xy * z * sh(10) +
+                         kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh(11) +
+                         kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh(12) +
+                         kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh(13) + kSH_C3[5] * z * (xx - yy) * sh(14) +
+                         kSH_C3[6] * x * (xx - 3.0f * yy) * sh(15);
+            }
+        }
+    }
+    result.x += 0.5f; result.y += 0.5f; result.z += 0.5f;
+    return result;
+}
+
+
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a, GsrView v) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    uint32_t tiles = 0;
+    if (idx < a.P) {
+        float3 p = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
+        if (a.deform_mode != GSR_DEFORM_NONE) {
+            const int t = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) ? a.body_id[idx] : idx;
+            const float* S = a.twist_S + 6 * (size_t)t;
+            const float3 w = make_float3(S[0], S[1], S[2]), tv = make_float3(S[3], S[4], S[5]);
+            p = se3_apply(p, w, tv, a.twist_theta[t]);
+            a.means_out[3 * idx] = p.x; a.means_out[3 * idx + 1] = p.y; a.means_out[3 * idx + 2] = p.z;
+        }
+        int radius = 0;
+        // Near-cull first so culled Gaussians cost 12 B of reads.
+        const float depth = xform_row(v.view, 2, p);
+        if (depth > GSR_NEAR) {
+            float cov6[6];
+            if (a.cov3D_precomp) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_precomp[6 * (size_t)idx + k];
+            } else {
+                const float3 s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+                const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+                cov3d_exact(s, v.scale_modifier, q, cov6);
+                if (a.cov3D_out) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) a.cov3D_out[6 * (size_t)idx + k] = cov6[k];
+                }
+            }
+            const SplatGeom g = splat_geometry_exact(p, cov6, v);
+            if (g.ok) {
+                V3 rgb;
+                uint8_t cl = 0;
+                if (a.colors_precomp) {
+                    rgb = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
+                } else {
+                    // 192-byte SH record as 12 x LDG.128 (M == 16), scalar otherwise.
+                    float shv[48];
+                    const int M = v.sh_coeffs;
+                    const int need = (v.sh_degree + 1) * (v.sh_degree + 1) * 3;
+                    const float* base = a.shs + (size_t)idx * M * 3;
+                    if (M == 16) {
+                        const float4* b4 = reinterpret_cast<const float4*>(base);
+#pragma unroll
+                        for (int k = 0; k < 12; k++) {
+                            if (4 * k < need) {
+                                const float4 t4 = __ldg(b4 + k);
+                                shv[4 * k] = t4.x; shv[4 * k + 1] = t4.y; shv[4 * k + 2] = t4.z; shv[4 * k + 3] = t4.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 48; k++) shv[k] = (k < need) ? base[k] : 0.0f;
+                    }
+                    auto fetch = [&](int k) -> V3 { return {shv[3 * k], shv[3 * k + 1], shv[3 * k + 2]}; };
+                    rgb = sh_to_rgb(v.sh_degree, p, v.campos, fetch);
+                    cl = (rgb.x < 0 ? 1 : 0) | (rgb.y < 0 ? 2 : 0) | (rgb.z < 0 ? 4 : 0);
+                    rgb.x = fmaxf(rgb.x, 0.0f); rgb.y = fmaxf(rgb.y, 0.0f); rgb.z = fmaxf(rgb.z, 0.0f);
+                }
+                const float op = a.opacities[idx];
+                // alpha = min(.99, op*exp(power)) >= 1/255 needs power >= log(1/(255 op)).
+                // Margin 1e-3 dwarfs the rounding of expf and of this log.
+                float cut = (op > 0.0f) ? (__logf(1.0f / (255.0f * op)) - 1e-3f) : 1.0f;
+                radius = g.radius;
+                tiles = (g.rmax.y - g.rmin.y) * (g.rmax.x - g.rmin.x);
+                a.depths[idx] = g.depth;
+                float4* r = a.recs + 3 * (size_t)idx;
+                r[0] = make_float4(g.pix.x, g.pix.y, g.conic.x, g.conic.y);
+                r[1] = make_float4(g.conic.z, op, rgb.x, rgb.y);
+                r[2] = make_float4(rgb.z, cut, 0.0f, 0.0f);
+                a.clamped[idx] = cl;
+            }
+        }
+        a.radii[idx] = radius;
+        a.tiles_touched[idx] = tiles;
+    }
+    // Per-block partial sum for the offsets scan (fused: saves re-reading tiles_touched).
+    __shared__ uint32_t wsum[8];
+    uint32_t s = tiles;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += wsum[k];
+        a.block_sums[blockIdx.x] = t;
+    }
+}
+
+// rasterizer_impl.cu:54-66 checkFrustum: present = (view-space z > 0.2).
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* means, GsrView v, uint8_t* present) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = make_float3(means[3 * idx], means[3 * idx + 1], means[3 * idx + 2]);
+    present[idx] = xform_row(v.view, 2, p) > GSR_NEAR ? 1 : 0;
+}
+
+int gsr_launch_preprocess_fwd(const PreprocessArgs& a, const GsrView& v, cudaStream_t stream) {
+    if (a.P <= 0) return 0;
+    preprocess_fwd_kernel<<<gsr_div_up(a.P, 256), 256, 0, stream>>>(a, v);
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+
+int gsr_launch_mark_visible(int P, const float* means, const GsrView& v, uint8_t* present, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, means, v, present);
+    GSR_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,294 @@
+"""Drop-in replacement for the reference's `diff_gaussian_rasterization` package.
+
+Same names, argument meaning, return values and error behaviour as
+submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py
+(GaussianRasterizationSettings :157-169, GaussianRasterizer :171-220,
+rasterize_gaussians :21-42, _RasterizeGaussians :44-155), backed by
+libgsr_b200.so (hand-written sm_100a kernels) through ctypes instead of the
+reference's pybind `_C` module.
+
+Additions that do not disturb reference call sites (keyword-only, default None):
+`GaussianRasterizer.forward(..., se3_S=, se3_theta=, body_id=)` fuses the SE3
+exponential-map deformation of scene/rigid_body.py into the preprocess kernel,
+forward and backward.  The deformed means of the last call are available as
+`rasterizer.deformed_means`.
+"""
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+import gsr_runtime as _rt
+
+
+def _c(t):
+    """Contiguous fp32 view of an optional tensor (None for absent/empty)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _empty_like_arg(t):
+    return torch.Tensor([]) if t is None else t
+
+
+class _Deform:
+    """Optional fused SE3 deformation (see gsr_deform in include/gsr_b200.h)."""
+    __slots__ = ("mode", "S", "theta", "body_id", "num_bodies")
+
+    def __init__(self, S, theta, body_id):
+        self.S, self.theta, self.body_id = S, theta, body_id
+        if S is None:
+            self.mode, self.num_bodies = _rt.DEFORM_NONE, 0
+        elif body_id is None:
+            self.mode, self.num_bodies = _rt.DEFORM_PER_GAUSSIAN, 0
+        else:
+            self.mode, self.num_bodies = _rt.DEFORM_RIGID_BODIES, int(S.shape[0])
+
+    def c_struct(self):
+        d = _rt.gsr_deform()
+        d.mode = self.mode
+        d.num_bodies = self.num_bodies
+        d.S = self.S.data_ptr() if self.S is not None else None
+        d.theta = self.theta.data_ptr() if self.theta is not None else None
+        d.body_id = self.body_id.data_ptr() if self.body_id is not None else None
+        return d
+
+
+def rasterize_gaussians(
+    means3D,
+    means2D,
+    sh,
+    colors_precomp,
+    opacities,
+    scales,
+    rotations,
+    cov3Ds_precomp,
+    raster_settings,
+    se3_S=None,
+    se3_theta=None,
+    body_id=None,
+):
+    return _RasterizeGaussians.apply(
+        means3D,
+        means2D,
+        sh,
+        colors_precomp,
+        opacities,
+        scales,
+        rotations,
+        cov3Ds_precomp,
+        raster_settings,
+        se3_S,
+        se3_theta,
+        body_id,
+    )
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(
+        ctx,
+        means3D,
+        means2D,
+        sh,
+        colors_precomp,
+        opacities,
+        scales,
+        rotations,
+        cov3Ds_precomp,
+        raster_settings,
+        se3_S=None,
+        se3_theta=None,
+        body_id=None,
+    ):
+        lib = _rt.load()
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            # rasterize_points.cu:57-59
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        if not means3D.is_cuda:
+            raise _rt.GsrError("libgsr_b200 runs on CUDA tensors only (no CPU fallback)")
+        dev = means3D.device
+        P = int(means3D.shape[0])
+        H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+
+        means3D_c = _c(means3D) if P else means3D
+        sh_c, colors_c, opac_c = _c(sh), _c(colors_precomp), _c(opacities)
+        scales_c, rots_c, cov_c = _c(scales), _c(rotations), _c(cov3Ds_precomp)
+        M = int(sh_c.shape[1]) if sh_c is not None else 0
+        deform = _Deform(_c(se3_S), _c(se3_theta),
+                         body_id.to(torch.int32).contiguous() if body_id is not None else None)
+
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        means_def = torch.empty((P, 3), dtype=torch.float32, device=dev) if deform.mode else None
+        view = _rt.make_view(raster_settings)
+        with torch.cuda.device(dev):
+            stream = _rt.stream_ptr(dev)
+            geom = torch.empty(lib.gsr_geom_bytes(P), dtype=torch.uint8, device=dev)
+            img = torch.empty(lib.gsr_image_bytes(W, H), dtype=torch.uint8, device=dev)
+            mailbox = _rt.pinned_u32(dev)
+            num_rendered = 0
+            dstruct = deform.c_struct()
+            if P != 0:
+                _rt.check(lib.gsr_forward_preprocess(
+                    view, P, M, _rt.ptr(means3D_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c),
+                    _rt.ptr(sh_c), _rt.ptr(cov_c), _rt.ptr(colors_c), dstruct, _rt.ptr(means_def),
+                    _rt.ptr(radii), _rt.ptr(geom), geom.numel(), mailbox.data_ptr(),
+                    1 if raster_settings.debug else 0, stream))
+                num_rendered = int(mailbox.item()) & 0xFFFFFFFF
+            binning = torch.empty(lib.gsr_binning_bytes(num_rendered, W, H), dtype=torch.uint8, device=dev)
+            _rt.check(lib.gsr_forward_render(view, P, num_rendered, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
+                                             binning.numel(), _rt.ptr(img), _rt.ptr(color), stream))
+
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        ctx.M = M
+        ctx.deform_mode = deform.mode
+        ctx.num_bodies = deform.num_bodies
+        ctx.view = view
+        ctx.flags = (sh is not None and sh.numel() > 0, colors_precomp is not None and colors_precomp.numel() > 0,
+                     scales is not None and scales.numel() > 0, cov3Ds_precomp is not None and cov3Ds_precomp.numel() > 0)
+        none = torch.empty(0, device=dev)
+        ctx.save_for_backward(
+            colors_c if colors_c is not None else none, means3D_c, scales_c if scales_c is not None else none,
+            rots_c if rots_c is not None else none, cov_c if cov_c is not None else none, radii,
+            sh_c if sh_c is not None else none, geom, binning, img,
+            means_def if means_def is not None else none,
+            deform.S if deform.S is not None else none, deform.theta if deform.theta is not None else none,
+            deform.body_id if deform.body_id is not None else none)
+        ctx.mark_non_differentiable(radii)
+        _RasterizeGaussians.last_deformed_means = means_def
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        lib = _rt.load()
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img,
+         means_def, tw_S, tw_theta, body_id) = ctx.saved_tensors
+        dev = means3D.device
+        P = int(means3D.shape[0])
+        M = ctx.M
+        has_sh, has_colors, has_scales, has_cov = ctx.flags
+        f32 = dict(dtype=torch.float32, device=dev)
+        grad_means3D = torch.empty((P, 3), **f32)
+        grad_means2D = torch.empty((P, 3), **f32)
+        grad_opacities = torch.empty((P, 1), **f32)
+        grad_colors = torch.empty((P, 3), **f32)
+        grad_cov3D = torch.empty((P, 6), **f32)
+        grad_sh = torch.empty((P, M, 3), **f32) if has_sh else None
+        grad_scales = torch.empty((P, 3), **f32) if has_scales else None
+        grad_rots = torch.empty((P, 4), **f32) if has_scales else None
+        grad_S = grad_theta = None
+        deform = _Deform(tw_S if ctx.deform_mode else None, tw_theta if ctx.deform_mode else None,
+                         body_id if ctx.deform_mode == _rt.DEFORM_RIGID_BODIES else None)
+        if ctx.deform_mode == _rt.DEFORM_PER_GAUSSIAN:
+            grad_S = torch.empty((P, 6), **f32)
+            grad_theta = torch.empty((P,), **f32)
+        elif ctx.deform_mode == _rt.DEFORM_RIGID_BODIES:
+            grad_S = torch.zeros((ctx.num_bodies, 6), **f32)
+            grad_theta = torch.zeros((ctx.num_bodies,), **f32)
+        if P != 0:
+            g = grad_out_color
+            if g.dtype != torch.float32:
+                g = g.float()
+            g = g.contiguous()
+            with torch.cuda.device(dev):
+                grad_ws = torch.empty(lib.gsr_grad_bytes(P), dtype=torch.uint8, device=dev)
+                _rt.check(lib.gsr_backward(
+                    ctx.view, P, M, ctx.num_rendered, _rt.ptr(means3D), _rt.ptr(means_def),
+                    _rt.ptr(scales), _rt.ptr(rotations), _rt.ptr(sh), _rt.ptr(cov3Ds_precomp), _rt.ptr(colors_precomp),
+                    deform.c_struct(), _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning), _rt.ptr(img), _rt.ptr(grad_ws),
+                    _rt.ptr(g), _rt.ptr(grad_means3D), _rt.ptr(grad_means2D), _rt.ptr(grad_opacities),
+                    _rt.ptr(grad_colors), _rt.ptr(grad_cov3D), _rt.ptr(grad_sh), _rt.ptr(grad_scales),
+                    _rt.ptr(grad_rots), _rt.ptr(grad_S), _rt.ptr(grad_theta), _rt.stream_ptr(dev)))
+        # Same order as the reference (__init__.py:143-153), then the SE3 extras.
+        grads = (
+            grad_means3D,
+            grad_means2D,
+            grad_sh,
+            grad_colors if has_colors else None,
+            grad_opacities,
+            grad_scales,
+            grad_rots,
+            grad_cov3D if has_cov else None,
+            None,
+            grad_S,
+            grad_theta,
+            None,
+        )
+        return grads
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.deformed_means = None
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            lib = _rt.load()
+            raster_settings = self.raster_settings
+            P = int(positions.shape[0])
+            pos = positions.float().contiguous()
+            visible = torch.zeros((P,), dtype=torch.bool, device=positions.device)
+            if P != 0:
+                view = _rt.make_view(raster_settings._replace(
+                    bg=raster_settings.bg if raster_settings.bg is not None else torch.zeros(3),
+                    campos=raster_settings.campos if raster_settings.campos is not None else torch.zeros(3)))
+                with torch.cuda.device(positions.device):
+                    _rt.check(lib.gsr_mark_visible(view, P, _rt.ptr(pos), _rt.ptr(visible),
+                                                   _rt.stream_ptr(positions.device)))
+        return visible
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, *, se3_S=None, se3_theta=None, body_id=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        if (se3_S is None) != (se3_theta is None):
+            raise Exception('Please provide both se3_S and se3_theta, or neither!')
+        if body_id is not None and se3_S is None:
+            raise Exception('body_id needs se3_S/se3_theta (one twist per rigid body)!')
+
+        out = rasterize_gaussians(
+            means3D,
+            means2D,
+            _empty_like_arg(shs),
+            _empty_like_arg(colors_precomp),
+            opacities,
+            _empty_like_arg(scales),
+            _empty_like_arg(rotations),
+            _empty_like_arg(cov3D_precomp),
+            raster_settings,
+            se3_S,
+            se3_theta,
+            body_id,
+        )
+        self.deformed_means = _RasterizeGaussians.last_deformed_means
+        return out

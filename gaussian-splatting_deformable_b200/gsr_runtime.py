@@ -1,0 +1,196 @@
+"""ctypes binding of libgsr_b200.so (C ABI in include/gsr_b200.h) + small host helpers.
+
+PyTorch is used for device memory, streams and autograd plumbing only; all compute
+goes through the hand-written sm_100a kernels in csrc/.  There is NO CPU or eager
+fallback: if the library is missing or a call fails this module raises.
+"""
+import ctypes
+import os
+import weakref
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgsr_b200.so")
+_lib = None
+
+
+class GsrError(RuntimeError):
+    pass
+
+
+class gsr_view(ctypes.Structure):
+    """Mirror of `struct gsr_view` (include/gsr_b200.h)."""
+    _fields_ = [
+        ("image_height", ctypes.c_int32),
+        ("image_width", ctypes.c_int32),
+        ("tanfovx", ctypes.c_float),
+        ("tanfovy", ctypes.c_float),
+        ("bg", ctypes.c_float * 3),
+        ("scale_modifier", ctypes.c_float),
+        ("viewmatrix", ctypes.c_float * 16),
+        ("projmatrix", ctypes.c_float * 16),
+        ("sh_degree", ctypes.c_int32),
+        ("campos", ctypes.c_float * 3),
+        ("prefiltered", ctypes.c_int32),
+        ("debug", ctypes.c_int32),
+    ]
+
+
+class gsr_deform(ctypes.Structure):
+    """Mirror of `struct gsr_deform` (include/gsr_b200.h)."""
+    _fields_ = [
+        ("mode", ctypes.c_int32),
+        ("num_bodies", ctypes.c_int32),
+        ("S", ctypes.c_void_p),
+        ("theta", ctypes.c_void_p),
+        ("body_id", ctypes.c_void_p),
+    ]
+
+
+DEFORM_NONE, DEFORM_PER_GAUSSIAN, DEFORM_RIGID_BODIES = 0, 1, 2
+
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    "gsr_last_error_string": (ctypes.c_char_p, []),
+    "gsr_version": (ctypes.c_int, []),
+    "gsr_geom_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "gsr_image_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "gsr_binning_bytes": (ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),
+    "gsr_grad_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "gsr_geom_layout": (None, [ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "gsr_image_layout": (None, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "gsr_binning_layout": (None, [ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "gsr_forward_preprocess": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_int,
+                                              _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
+                                              _P, _P, ctypes.c_size_t, _P, ctypes.c_int, _P]),
+    "gsr_forward_render": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P,
+                                          ctypes.c_size_t, _P, _P, _P]),
+    "gsr_backward": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                    _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
+                                    _P, _P, _P, _P, _P,
+                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gsr_mark_visible": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, _P, _P, _P]),
+    "gsr_knn_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "gsr_knn_dist2": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_size_t, _P]),
+    "gsr_exp_se3": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P]),
+    "gsr_exp_se3_backward": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P, _P, _P]),
+    "gsr_sort_bytes": (ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),
+    "gsr_sort_pairs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, _P,
+                                      ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load libgsr_b200.so (raises GsrError if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise GsrError("libgsr_b200.so is not built: run `python gaussian-splatting_deformable_b200/build.py` "
+                       "(or __graft_entry__.build()).  There is no fallback path.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GsrError("libgsr_b200: %s" % load().gsr_last_error_string().decode())
+
+
+def ptr(t):
+    """Device pointer of a tensor, or NULL for None / empty tensors (the reference passes
+    empty CPU tensors for absent optionals, diff_gaussian_rasterization/__init__.py:197-207)."""
+    if t is None or t.numel() == 0:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# ---------------------------------------------------------------------------
+# Host copies of the (tiny) camera tensors.  The kernels take the matrices in
+# the constant bank, so the host needs their values; Camera objects keep the same
+# tensors for the whole run, so this is a one-time D2H per camera, not per step.
+# Keyed on object identity (validated through a weakref) and the in-place
+# version counter, never on data_ptr (addresses are recycled by the allocator).
+# ---------------------------------------------------------------------------
+_host_cache = {}
+
+
+def host_values(t, n):
+    key = id(t)
+    hit = _host_cache.get(key)
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    vals = t.detach().to(dtype=torch.float32, device="cpu").contiguous().reshape(-1).tolist()
+    if len(vals) != n:
+        raise GsrError("expected a tensor with %d elements, got %d" % (n, len(vals)))
+    if len(_host_cache) > 8192:
+        _host_cache.clear()
+    try:
+        _host_cache[key] = (weakref.ref(t), t._version, vals)
+    except TypeError:
+        pass
+    return vals
+
+
+def make_view(rs, sh_degree=None):
+    """Build the host-side gsr_view from a GaussianRasterizationSettings tuple."""
+    v = gsr_view()
+    v.image_height = int(rs.image_height)
+    v.image_width = int(rs.image_width)
+    v.tanfovx = float(rs.tanfovx)
+    v.tanfovy = float(rs.tanfovy)
+    v.bg[:] = host_values(rs.bg, 3)
+    v.scale_modifier = float(rs.scale_modifier)
+    v.viewmatrix[:] = host_values(rs.viewmatrix, 16)
+    v.projmatrix[:] = host_values(rs.projmatrix, 16)
+    v.sh_degree = int(rs.sh_degree if sh_degree is None else sh_degree)
+    v.campos[:] = host_values(rs.campos, 3)
+    v.prefiltered = int(bool(rs.prefiltered))
+    v.debug = int(bool(rs.debug))
+    return v
+
+
+_pinned = {}
+
+
+def pinned_u32(device):
+    """One pinned 4-byte mailbox per device for the num_rendered read-back."""
+    key = str(device)
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _pinned[key] = buf
+    return buf
+
+
+def geom_layout(P):
+    out = (ctypes.c_size_t * 6)()
+    load().gsr_geom_layout(int(P), out)
+    return dict(zip(("depths", "tiles_touched", "recs", "clamped", "point_offsets", "cov3D"), list(out)))
+
+
+def image_layout(W, H):
+    out = (ctypes.c_size_t * 3)()
+    load().gsr_image_layout(int(W), int(H), out)
+    return dict(zip(("final_T", "n_contrib", "ranges"), list(out)))
+
+
+def binning_layout(R, W, H):
+    out = (ctypes.c_size_t * 4)()
+    load().gsr_binning_layout(int(R), int(W), int(H), out)
+    return dict(zip(("keys_sorted", "point_list", "keys_other", "vals_other"), list(out)))

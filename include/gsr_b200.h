@@ -1,0 +1,149 @@
+/* gsr_b200.h - C ABI of libgsr_b200.so: the sm_100a (B200) deformable
+ * Gaussian-splatting hot path.
+ *
+ * This is the drop-in boundary.  Every entry point below takes plain pointers and
+ * sizes (device pointers unless the name says host), a cudaStream_t passed as
+ * void*, and returns 0 on success or a non-zero code (cudaError_t value, or a
+ * negative library code) with a message available from gsr_last_error_string().
+ * The library never allocates or frees device memory: the caller owns inputs,
+ * outputs and the workspaces whose sizes the *_bytes() queries report.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   gsr_forward_preprocess + gsr_forward_render
+ *       <- CudaRasterizer::Rasterizer::forward
+ *          submodules/diff-gaussian-rasterization/cuda_rasterizer/rasterizer.h:33-56,
+ *          rasterizer_impl.cu:198-336 (bound to Python by rasterize_points.cu:35-115,
+ *          ext.cpp:16 "rasterize_gaussians")
+ *       <- scene/rigid_body.py:86-93 exp_se3 + gaussian_renderer/__init__.py:92-95
+ *          (the SE3 deformation is fused into the preprocess stage)
+ *   gsr_backward
+ *       <- CudaRasterizer::Rasterizer::backward  rasterizer.h:58-84,
+ *          rasterizer_impl.cu:340-434 (rasterize_points.cu:117-196,
+ *          ext.cpp:17 "rasterize_gaussians_backward") + autograd of rigid_body.py
+ *   gsr_mark_visible
+ *       <- CudaRasterizer::Rasterizer::markVisible rasterizer.h:26-31,
+ *          rasterizer_impl.cu:141-153 (rasterize_points.cu:198-217, ext.cpp:18)
+ *   gsr_knn_dist2
+ *       <- distCUDA2  submodules/simple-knn/spatial.cu:15-26, simple_knn.cu:185-221
+ *   gsr_exp_se3 / gsr_exp_se3_backward
+ *       <- scene/rigid_body.py:86-93 exp_se3 (materialised [N,4,4] transforms)
+ *   gsr_sort_pairs
+ *       <- cub::DeviceRadixSort::SortPairs as called at rasterizer_impl.cu:303-308
+ *          (exported so the sort can be tested and profiled on its own)
+ */
+#ifndef GSR_B200_H
+#define GSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Host-side description of one view.  Field meaning follows
+ * GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:157-169);
+ * matrices use the reference's memory convention (16 floats, true row i =
+ * m[i], m[i+4], m[i+8], m[i+12]).  All arrays here are HOST values. */
+typedef struct gsr_view {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float bg[3];
+    float scale_modifier;
+    float viewmatrix[16];
+    float projmatrix[16];
+    int32_t sh_degree;     /* active degree D */
+    float campos[3];
+    int32_t prefiltered;
+    int32_t debug;
+} gsr_view;
+
+/* Optional SE3 deformation fused into preprocess.  mode: 0 none,
+ * 1 per-Gaussian twists (S[P,6], theta[P]), 2 rigid bodies (body_id[P] int32,
+ * S[B,6], theta[B]).  S = (w, v) as in rigid_body.exp_se3. */
+typedef struct gsr_deform {
+    int32_t mode;
+    int32_t num_bodies;
+    const float* S;
+    const float* theta;
+    const int32_t* body_id;
+} gsr_deform;
+
+const char* gsr_last_error_string(void);
+int gsr_version(void);
+
+/* ---- workspace sizes ---------------------------------------------------- */
+size_t gsr_geom_bytes(int P);                       /* per-Gaussian state of one view        */
+size_t gsr_image_bytes(int width, int height);      /* final_T, n_contrib, tile ranges       */
+size_t gsr_binning_bytes(uint32_t num_rendered, int width, int height); /* keys/values x2 + sort temp */
+size_t gsr_grad_bytes(int P);                       /* blend-backward gradient records       */
+/* Byte offsets of the geometry-workspace sub-arrays, for tests and tools:
+ * out[0]=depths f32[P], out[1]=tiles_touched u32[P], out[2]=splat records float4[3P]
+ * (x,y,conic.x,conic.y | conic.z,opacity,r,g | b,cut,0,0), out[3]=clamped u8[P],
+ * out[4]=point_offsets u32[P] (inclusive scan), out[5]=cov3D f32[6P] (debug only) */
+void gsr_geom_layout(int P, size_t out[6]);
+/* out[0]=final_T f32[WH], out[1]=n_contrib u32[WH], out[2]=ranges uint2[tiles] */
+void gsr_image_layout(int width, int height, size_t out[3]);
+/* out[0]=sorted keys u64[R], out[1]=sorted values (point_list) u32[R],
+ * out[2]=unsorted keys, out[3]=unsorted values */
+void gsr_binning_layout(uint32_t num_rendered, int width, int height, size_t out[4]);
+
+/* ---- forward -------------------------------------------------------------
+ * Stage 1: deform + project + covariance + SH, offsets scan.  Writes radii[P]
+ * (int32), optional means_out[P,3] (required when deform->mode != 0), fills the
+ * geometry workspace, copies num_rendered to *host_num_rendered (pinned host
+ * memory recommended) and synchronises the stream - the one host round trip of
+ * the forward, as in the reference (rasterizer_impl.cu:281).
+ * Optional inputs are NULL when absent (exactly one of shs/colors_precomp and one
+ * of (scales,rotations)/cov3D_precomp must be given).  M = SH coefficients stored
+ * per Gaussian. */
+int gsr_forward_preprocess(const gsr_view* view, int P, int M,
+                           const float* means3D, const float* scales, const float* rotations,
+                           const float* opacities, const float* shs,
+                           const float* cov3D_precomp, const float* colors_precomp,
+                           const gsr_deform* deform, float* means_out,
+                           int32_t* radii, void* geom_ws, size_t geom_bytes,
+                           uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream);
+
+/* Stage 2: duplicate keys, onesweep sort, tile ranges, blend.  out_color[3,H,W]. */
+int gsr_forward_render(const gsr_view* view, int P, uint32_t num_rendered,
+                       const int32_t* radii, void* geom_ws, void* binning_ws, size_t binning_bytes,
+                       void* image_ws, float* out_color, void* stream);
+
+/* ---- backward -------------------------------------------------------------
+ * dL_dout_color[3,H,W] -> gradients.  Every output element is written (no
+ * pre-zeroing needed) except dL_dtwist_* in rigid-body mode, which are
+ * ACCUMULATED into and must be zeroed by the caller.  Outputs may be NULL when
+ * the corresponding input was absent (dL_dsh, dL_dscales, dL_drots, dL_dtwist_*). */
+int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
+                 const float* means3D, const float* means_deformed,
+                 const float* scales, const float* rotations, const float* shs,
+                 const float* cov3D_precomp, const float* colors_precomp,
+                 const gsr_deform* deform, const int32_t* radii,
+                 const void* geom_ws, const void* binning_ws, const void* image_ws,
+                 void* grad_ws, const float* dL_dout_color,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dopacity, float* dL_dcolors,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
+                 float* dL_dtwist_S, float* dL_dtwist_theta, void* stream);
+
+/* ---- the rest of the reference's operator surface -------------------------- */
+int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t* present, void* stream);
+
+size_t gsr_knn_bytes(int P);
+int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream);
+
+int gsr_exp_se3(int N, const float* S, const float* theta, float* T44, void* stream);
+int gsr_exp_se3_backward(int N, const float* S, const float* theta, const float* dT44,
+                         float* dS, float* dtheta, void* stream);
+
+size_t gsr_sort_bytes(uint32_t n, int begin_bit, int end_bit);
+int gsr_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                   uint32_t n, int begin_bit, int end_bit, void* temp, size_t temp_bytes,
+                   int* result_in_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H */
