@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the deformable Gaussian-splatting hot path (BASELINE.json metric:
+fwd+bwd ms/view and Gaussian-views/s, 1 M Gaussians @ 1080p, 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one training-style pass over a batch of V views (default 8 per GPU, so
+8 GPUs render the 64 cameras of config C5): for every view, SE3 exp-map deformation
+of all Gaussians + rasterize forward + dL/dimage injection + backward down to the
+leaf parameters and twists; per-Gaussian gradients are summed over the views of the
+GPU and (N > 1) all-reduced over NCCL.  Synthetic scene/cameras.
+
+Arms
+  ours       GaussianRasterizer (drop-in API) -> libgsr_b200.so, SE3 fused in-kernel.
+  reference  the reference's own CUDA rasterizer rebuilt unmodified (oracle/_ref) +
+             its torch rigid_body op graph (oracle/rigid_body_port.py) on the same
+             GPU: the comparator BASELINE.json's north_star names.  The reference has
+             no CPU rasterizer; its torch-CPU deformation stage is reported as
+             `cpu_baseline`.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_deformable_b200"))
+
+PARAM_KEYS = ("means3D", "scales", "rotations", "opacities", "shs")
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+def build_workload(args, rank, world, dev):
+    import synthetic
+    sc = synthetic.make_scene(args.P, seed=0, device="cpu")
+    S, theta = synthetic.make_twists(args.P, seed=2, device="cpu")
+    host = {k: sc[k].pin_memory() for k in PARAM_KEYS}
+    host["S"], host["theta"] = S.pin_memory(), theta.pin_memory()
+    total_views = args.views * world
+    K = max(total_views, 64)
+    cams = [synthetic.make_camera(rank * args.views + v, K, args.W, args.H, device=dev) for v in range(args.views)]
+    bg = torch.zeros(3, device=dev)
+    grad = synthetic.make_image_grad(args.W, args.H, seed=1, device=dev)
+    return host, cams, bg, grad
+
+
+def to_device(host, dev):
+    return {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host.items()}
+
+
+def zero_grads(leaves):
+    for t in leaves.values():
+        t.grad = None
+
+
+def step_ours(leaves, cams, bg, grad, args):
+    import synthetic
+    from diff_gaussian_rasterization import GaussianRasterizer
+    loss_total = None
+    for cam in cams:
+        rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+        ras = GaussianRasterizer(rs)
+        means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                           shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                           se3_S=leaves["S"], se3_theta=leaves["theta"])
+        loss = (color * grad).sum()
+        loss.backward()
+        loss_total = loss.detach() if loss_total is None else loss_total + loss.detach()
+    return loss_total
+
+
+def step_reference(leaves, cams, bg, grad, args):
+    """Reference arm: torch rigid_body op graph (autograd) + the reference's CUDA
+    rasterizer driven the way its own autograd.Function drives `_C`."""
+    import synthetic
+    from oracle import ref_driver, rigid_body_port
+    loss_total = None
+    for cam in cams:
+        rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+        y = rigid_body_port.deform_points(leaves["means3D"], leaves["S"], leaves["theta"])
+        yd = y.detach()
+        f = ref_driver.forward(rs, yd, leaves["opacities"].detach(), shs=leaves["shs"].detach(),
+                               scales=leaves["scales"].detach(), rotations=leaves["rotations"].detach())
+        loss = (f["color"] * grad).sum()
+        g = ref_driver.backward(rs, f, grad, yd, shs=leaves["shs"].detach(), scales=leaves["scales"].detach(),
+                                rotations=leaves["rotations"].detach())
+        y.backward(g["means3D"])
+        for k, gk in (("opacities", "opacities"), ("shs", "shs"), ("scales", "scales"), ("rotations", "rotations")):
+            t = leaves[k]
+            t.grad = g[gk].view_as(t) if t.grad is None else t.grad + g[gk].view_as(t)
+        loss_total = loss.detach() if loss_total is None else loss_total + loss.detach()
+    return loss_total
+
+
+def allreduce_grads(leaves, world):
+    if world == 1:
+        return
+    import torch.distributed as dist
+    works = [dist.all_reduce(t.grad, async_op=True) for t in leaves.values() if t.grad is not None]
+    for w in works:
+        w.wait()
+
+
+def cpu_baseline(n=100000, iters=30):
+    """Reference torch-CPU deformation stage (config C1): exp_se3 + apply, fwd+bwd."""
+    import synthetic
+    from oracle import rigid_body_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    x0 = synthetic.make_scene(n, seed=0)["means3D"]
+    S0, th0 = synthetic.make_twists(n, seed=2)
+    gy = torch.randn_like(x0)
+    ts = []
+    for it in range(5 + iters):
+        x, S, th = x0.clone().requires_grad_(True), S0.clone().requires_grad_(True), th0.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        y = rigid_body_port.deform_points(x, S, th)
+        (y * gy).sum().backward()
+        dt = time.perf_counter() - t0
+        if it >= 5:
+            ts.append(dt)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": n / med, "unit": "Gaussian-views/s (SE3 deformation stage only; the reference has no CPU rasterizer)",
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "C1: rigid_body exp_se3+apply fwd+bwd, N=%d, fp32 torch-CPU, median of %d (%.1f ms/iter)" % (n, iters, med * 1e3)}
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--views", type=int, default=8, help="views per GPU per step")
+    ap.add_argument("--P", type=int, default=1000000)
+    ap.add_argument("--W", type=int, default=1920)
+    ap.add_argument("--H", type=int, default=1080)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    if args.impl == "reference":
+        from oracle import ref_driver
+        if not ref_driver.available():
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_dgr_C.so not built (needs /root/reference)"}))
+            return
+        step_fn = step_reference
+    else:
+        import gsr_runtime as rt
+        rt.load()
+        step_fn = step_ours
+
+    host, cams, bg, grad = build_workload(args, rank, world, dev)
+    leaves = to_device(host, dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def run_step():
+        zero_grads(leaves)
+        loss = step_fn(leaves, cams, bg, grad, args)
+        allreduce_grads(leaves, world)
+        return loss
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        run_step()
+    launches = 0
+    if args.impl == "ours":
+        rt.launch_count(reset=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    if args.impl == "ours":
+        launches = rt.launch_count(reset=True)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    views_total = args.views * world
+    value = args.P * views_total / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end: host buffers in, loss out ----------------
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    for _ in range(2):
+        leaves = to_device(host, dev)
+        float(run_step().item())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        leaves = to_device(host, dev)                 # pinned host -> device, every step
+        loss = run_step()
+        _ = float(loss.item())                        # device -> host read of the step's result
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    e2e_val = args.P * views_total / (float(e2e_s.item()) / args.steps)
+
+    # ---------------- per-kernel profile (ours) -> roofline ----------------
+    roofline, kernels, counters = None, None, None
+    if args.impl == "ours" and rank == 0:
+        from diff_gaussian_rasterization import _RasterizeGaussians
+        rt.profile_enable(True)
+        run_step()
+        torch.cuda.synchronize()
+        prof = rt.profile_dump()
+        rt.profile_enable(False)
+        R = getattr(_RasterizeGaussians, "last_num_rendered", 0)
+        tiles = ((args.W + 15) // 16) * ((args.H + 15) // 16)
+        passes = (32 + max(tiles, 1).bit_length() + 7) // 8
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        alg = {  # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x units per launch; R = last view's)
+            "preprocess_fwd": 316.0 * args.P,
+            "preprocess_bwd": 572.0 * args.P,
+            "duplicate_with_keys": 12.0 * R + 20.0 * args.P,
+            "sort_histogram": 8.0 * R,
+            "sort_onesweep_pass": 24.0 * R,
+            "tile_ranges": 8.0 * R + 8.0 * tiles,
+        }
+        kernels = {}
+        for name, (cnt, tot) in prof.items():
+            avg = tot / max(cnt, 1)
+            k = {"launches": cnt, "avg_ms": round(avg, 5), "total_ms": round(tot, 4)}
+            if name in alg and avg > 0:
+                k["alg_GBps"] = round(alg[name] / avg / 1e6, 1)
+                k["frac_of_hbm_peak"] = round(alg[name] / avg / 1e6 / peak, 4)
+            kernels[name] = k
+        hbm_kernels = [n for n in kernels if n in alg]
+        dom = max(hbm_kernels, key=lambda n: kernels[n]["total_ms"]) if hbm_kernels else None
+        if dom:
+            a = alg[dom] / kernels[dom]["avg_ms"] / 1e6
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(a / peak, 4), "traffic": None, "peak_source": peak_src,
+                        "note": "dominant HBM-bound kernel; the blend kernels (largest time share) are FP32-issue/"
+                                "shared-memory bound, see `kernels` and profiles/"}
+        counters = {"num_rendered_last_view": R, "sort_passes": passes, "tiles": tiles}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    out = {
+        "metric": "gaussian_views_per_s_fwd_bwd",
+        "value": value,
+        "unit": "Gaussian-views/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "ms_per_view": ms_per_step / args.views,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "impl": args.impl,
+        "config": {"workload": "C2: %d Gaussians, SH degree 3, %dx%d, SE3 exp-map deform + rasterize fwd+bwd; "
+                               "%d views/GPU/step on a camera circle (C5's 64 cameras at 8 GPUs)" % (args.P, args.W, args.H, args.views),
+                   "P": args.P, "width": args.W, "height": args.H, "views_per_gpu_per_step": args.views,
+                   "parallelism": "view-parallel x%d, per-Gaussian grad all-reduce (NCCL)" % world if world > 1 else "single GPU",
+                   "l2": "inputs (264 MB params+twists, 85 MB geometry state, 190 MB keys) exceed the 126 MB L2 every view"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "Gaussian-views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches if args.impl == "ours" else 0,
+    }
+    if args.impl == "ours":
+        out["roofline"] = roofline
+        out["kernels"] = kernels
+        out["counters"] = counters
+    if not args.no_cpu_baseline and world >= 1:
+        try:
+            out["cpu_baseline"] = cpu_baseline()
+        except Exception as ex:  # pragma: no cover
+            out["cpu_baseline"] = {"error": repr(ex)}
+    if args.impl == "reference":
+        out["reference_arm"] = ("reference CUDA rasterizer (oracle/_ref, sm_100, unmodified sources) + torch-CUDA "
+                                "rigid_body op graph; the reference's torch-CPU deformation is `cpu_baseline`")
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,53 @@ int gsr_set_error_msg(int code, const char* msg) {
     return code;
 }
 
+// ---- launch accounting / profiler -------------------------------------------
+namespace {
+struct ProfEntry { const char* name; unsigned long long count; double ms; };
+struct ProfPending { int slot; cudaEvent_t e0, e1; };
+bool g_prof_on = false;
+unsigned long long g_launches = 0;
+ProfEntry g_prof[64];
+int g_prof_n = 0;
+ProfPending g_pending[4096];
+int g_pending_n = 0;
+int prof_slot(const char* name) {
+    for (int i = 0; i < g_prof_n; i++) if (g_prof[i].name == name || !strcmp(g_prof[i].name, name)) return i;
+    if (g_prof_n >= 64) return 63;
+    g_prof[g_prof_n] = ProfEntry{name, 0ull, 0.0};
+    return g_prof_n++;
+}
+void prof_collect() {
+    for (int i = 0; i < g_pending_n; i++) {
+        float ms = 0.f;
+        cudaEventSynchronize(g_pending[i].e1);
+        cudaEventElapsedTime(&ms, g_pending[i].e0, g_pending[i].e1);
+        g_prof[g_pending[i].slot].ms += ms;
+        cudaEventDestroy(g_pending[i].e0);
+        cudaEventDestroy(g_pending[i].e1);
+    }
+    g_pending_n = 0;
+}
+}  // namespace
+
+GsrProfScope::GsrProfScope(const char* name, cudaStream_t s) : slot(-1), stream(s) {
+    g_launches++;
+    if (!g_prof_on) return;
+    if (g_pending_n >= 4096) prof_collect();
+    slot = prof_slot(name);
+    g_prof[slot].count++;
+    ProfPending& p = g_pending[g_pending_n];
+    p.slot = slot;
+    cudaEventCreate(&p.e0);
+    cudaEventCreate(&p.e1);
+    cudaEventRecord(p.e0, stream);
+}
+GsrProfScope::~GsrProfScope() {
+    if (slot < 0) return;
+    cudaEventRecord(g_pending[g_pending_n].e1, stream);
+    g_pending_n++;
+}
+
 namespace {
 
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -101,6 +148,28 @@ int fill_view(const gsr_view* s, int M, GsrView& v) {
 extern "C" {
 
 const char* gsr_last_error_string(void) { return g_err; }
+
+void gsr_profile_enable(int on) {
+    prof_collect();
+    g_prof_on = on != 0;
+    if (on) { g_prof_n = 0; }
+}
+unsigned long long gsr_launch_count(int reset) {
+    const unsigned long long n = g_launches;
+    if (reset) g_launches = 0;
+    return n;
+}
+int gsr_profile_dump(char* out, size_t cap) {
+    prof_collect();
+    size_t o = 0;
+    if (cap) out[0] = 0;
+    for (int i = 0; i < g_prof_n; i++) {
+        const int w = snprintf(out + o, cap > o ? cap - o : 0, "%s %llu %.6f\n", g_prof[i].name, g_prof[i].count, g_prof[i].ms);
+        if (w < 0 || (size_t)w >= (cap > o ? cap - o : 0)) break;
+        o += (size_t)w;
+    }
+    return g_prof_n;
+}
 int gsr_version(void) { return 100; }
 
 size_t gsr_geom_bytes(int P) { return geom_layout(P).bytes; }

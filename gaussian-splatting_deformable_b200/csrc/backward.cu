@@ -432,14 +432,16 @@ int gsr_launch_preprocess_bwd(const PreprocessBwdArgs& a, const GsrView& v, cuda
     size_t smem = 0;
     if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && a.dL_dtwist_S && a.num_bodies * 7 * 4 <= 32768)
         smem = (size_t)a.num_bodies * 7 * 4;
-    preprocess_bwd_kernel<<<gsr_div_up(a.P, 256), 256, smem, stream>>>(a, v);
+    { GsrProfScope prof_("preprocess_bwd", stream);
+    preprocess_bwd_kernel<<<gsr_div_up(a.P, 256), 256, smem, stream>>>(a, v); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
 
 int gsr_launch_se3_matrices(int N, const float* S, const float* theta, float* T44, cudaStream_t stream) {
     if (N <= 0) return 0;
-    se3_matrices_kernel<<<gsr_div_up(N, 256), 256, 0, stream>>>(N, S, theta, T44);
+    { GsrProfScope prof_("se3_matrices", stream);
+    se3_matrices_kernel<<<gsr_div_up(N, 256), 256, 0, stream>>>(N, S, theta, T44); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -447,7 +449,8 @@ int gsr_launch_se3_matrices(int N, const float* S, const float* theta, float* T4
 int gsr_launch_se3_matrices_bwd(int N, const float* S, const float* theta, const float* dT44, float* dS,
                                 float* dtheta, cudaStream_t stream) {
     if (N <= 0) return 0;
-    se3_matrices_bwd_kernel<<<gsr_div_up(N, 256), 256, 0, stream>>>(N, S, theta, dT44, dS, dtheta);
+    { GsrProfScope prof_("se3_matrices_bwd", stream);
+    se3_matrices_bwd_kernel<<<gsr_div_up(N, 256), 256, 0, stream>>>(N, S, theta, dT44, dS, dtheta); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* sums, i
 }
 
 int gsr_launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* d_total, cudaStream_t stream) {
-    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, num_blocks, d_total);
+    { GsrProfScope prof_("scan_block_sums", stream);
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, num_blocks, d_total); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -135,8 +136,9 @@ int gsr_launch_duplicate(int P, const int* radii, const float* depths, const uin
                          const float4* recs, const uint32_t* block_offsets, uint32_t* point_offsets,
                          uint64_t* keys, uint32_t* vals, int grid_x, int grid_y, cudaStream_t stream) {
     if (P <= 0) return 0;
+    { GsrProfScope prof_("duplicate_with_keys", stream);
     duplicate_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, radii, depths, tiles_touched, recs, block_offsets,
-                                                             point_offsets, keys, vals, grid_x, grid_y);
+                                                             point_offsets, keys, vals, grid_x, grid_y); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -166,7 +168,8 @@ int gsr_launch_tile_ranges(uint32_t R, const uint64_t* sorted_keys, uint2* range
                            cudaStream_t stream) {
     GSR_CHECK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
     if (R == 0) return 0;
-    tile_ranges_kernel<<<gsr_div_up(R, 256), 256, 0, stream>>>(R, sorted_keys, ranges);
+    { GsrProfScope prof_("tile_ranges", stream);
+    tile_ranges_kernel<<<gsr_div_up(R, 256), 256, 0, stream>>>(R, sorted_keys, ranges); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

@@ -356,14 +356,16 @@ __global__ void __launch_bounds__(BLK) blend_bwd_kernel(BlendBwdArgs a) {
 
 int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
-    blend_fwd_kernel<<<grid, BLK, 0, stream>>>(a);
+    { GsrProfScope prof_("blend_fwd", stream);
+    blend_fwd_kernel<<<grid, BLK, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
 
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
-    blend_bwd_kernel<<<grid, BLK, 0, stream>>>(a);
+    { GsrProfScope prof_("blend_bwd", stream);
+    blend_bwd_kernel<<<grid, BLK, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

@@ -61,6 +61,14 @@ struct GsrView {
 int gsr_set_error(cudaError_t e, const char* what, const char* file, int line);
 int gsr_set_error_msg(int code, const char* msg);
 
+// Launch accounting + optional per-kernel timing with CUDA events on the launching
+// stream (gsr_profile_enable / gsr_profile_dump in include/gsr_b200.h).
+struct GsrProfScope {
+    GsrProfScope(const char* name, cudaStream_t stream);
+    ~GsrProfScope();
+    int slot; cudaStream_t stream;
+};
+
 static inline int gsr_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------

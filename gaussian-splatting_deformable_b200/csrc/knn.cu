@@ -203,11 +203,15 @@ int gsr_launch_knn_dist2(int P, const float* points, float* mean_dist2, void* te
     int bits = 1;
     while ((1ull << bits) < (unsigned long long)cells) bits++;
 
-    knn_init_kernel<<<1, 32, 0, stream>>>(bbox);
+    { GsrProfScope prof_("knn_init", stream);
+    knn_init_kernel<<<1, 32, 0, stream>>>(bbox); }
     int bb = gsr_div_up(P, 256); if (bb > 148 * 8) bb = 148 * 8;
-    knn_bbox_kernel<<<bb, 256, 0, stream>>>(P, points, bbox);
-    knn_grid_kernel<<<1, 32, 0, stream>>>(bbox, G, grid);
-    knn_keys_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, points, grid, keys_a, vals_a);
+    { GsrProfScope prof_("knn_bbox", stream);
+    knn_bbox_kernel<<<bb, 256, 0, stream>>>(P, points, bbox); }
+    { GsrProfScope prof_("knn_grid", stream);
+    knn_grid_kernel<<<1, 32, 0, stream>>>(bbox, G, grid); }
+    { GsrProfScope prof_("knn_keys", stream);
+    knn_keys_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, points, grid, keys_a, vals_a); }
     GSR_CHECK_LAUNCH();
     int in_b = 0;
     int rc = gsr_launch_sort_pairs(keys_a, keys_b, vals_a, vals_b, (uint32_t)P, 0, bits,
@@ -215,8 +219,10 @@ int gsr_launch_knn_dist2(int P, const float* points, float* mean_dist2, void* te
     if (rc) return rc;
     const uint64_t* sk = in_b ? keys_b : keys_a;
     const uint32_t* sv = in_b ? vals_b : vals_a;
-    knn_cells_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, sk, sv, points, cell_start, cells, sorted_pts);
-    knn_query_kernel<<<gsr_div_up(P, 128), 128, 0, stream>>>(P, sorted_pts, cell_start, grid, mean_dist2);
+    { GsrProfScope prof_("knn_cells", stream);
+    knn_cells_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, sk, sv, points, cell_start, cells, sorted_pts); }
+    { GsrProfScope prof_("knn_query", stream);
+    knn_query_kernel<<<gsr_div_up(P, 128), 128, 0, stream>>>(P, sorted_pts, cell_start, grid, mean_dist2); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

@@ -157,14 +157,16 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* m
 
 int gsr_launch_preprocess_fwd(const PreprocessArgs& a, const GsrView& v, cudaStream_t stream) {
     if (a.P <= 0) return 0;
-    preprocess_fwd_kernel<<<gsr_div_up(a.P, 256), 256, 0, stream>>>(a, v);
+    { GsrProfScope prof_("preprocess_fwd", stream);
+    preprocess_fwd_kernel<<<gsr_div_up(a.P, 256), 256, 0, stream>>>(a, v); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
 
 int gsr_launch_mark_visible(int P, const float* means, const GsrView& v, uint8_t* present, cudaStream_t stream) {
     if (P <= 0) return 0;
-    mark_visible_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, means, v, present);
+    { GsrProfScope prof_("mark_visible", stream);
+    mark_visible_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, means, v, present); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

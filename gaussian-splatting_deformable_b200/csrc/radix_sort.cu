@@ -263,16 +263,19 @@ int gsr_launch_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, 
     GSR_CHECK(cudaMemsetAsync(temp, 0, need, stream));
     int hist_blocks = (int)((n + 256u * 16u - 1) / (256u * 16u));
     if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-    histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys_a, n, plan, hist);
+    { GsrProfScope prof_("sort_histogram", stream);
+    histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys_a, n, plan, hist); }
     GSR_CHECK_LAUNCH();
-    scan_hist_kernel<<<plan.passes, RADIX, 0, stream>>>(hist);
+    { GsrProfScope prof_("sort_scan_hist", stream);
+    scan_hist_kernel<<<plan.passes, RADIX, 0, stream>>>(hist); }
     GSR_CHECK_LAUNCH();
     uint64_t* kin = keys_a; uint64_t* kout = keys_b;
     uint32_t* vin = vals_a; uint32_t* vout = vals_b;
     for (int p = 0; p < plan.passes; p++) {
-        onesweep_kernel<<<tiles, SORT_THREADS, sizeof(SortSmem), stream>>>(
+        { GsrProfScope prof_("sort_onesweep_pass", stream);
+    onesweep_kernel<<<tiles, SORT_THREADS, sizeof(SortSmem), stream>>>(
             kin, kout, vin, vout, n, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p,
-            tickets + 63, plan.shift[p], plan.mask[p]);
+            tickets + 63, plan.shift[p], plan.mask[p]); }
         GSR_CHECK_LAUNCH();
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;

@@ -161,6 +161,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             deform.body_id if deform.body_id is not None else none)
         ctx.mark_non_differentiable(radii)
         _RasterizeGaussians.last_deformed_means = means_def
+        _RasterizeGaussians.last_num_rendered = num_rendered
         return color, radii
 
     @staticmethod

@@ -54,6 +54,9 @@ _P = ctypes.c_void_p
 _SIGNATURES = {
     "gsr_last_error_string": (ctypes.c_char_p, []),
     "gsr_version": (ctypes.c_int, []),
+    "gsr_profile_enable": (None, [ctypes.c_int]),
+    "gsr_launch_count": (ctypes.c_ulonglong, [ctypes.c_int]),
+    "gsr_profile_dump": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t]),
     "gsr_geom_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_image_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "gsr_binning_bytes": (ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),
@@ -194,3 +197,22 @@ def binning_layout(R, W, H):
     out = (ctypes.c_size_t * 4)()
     load().gsr_binning_layout(int(R), int(W), int(H), out)
     return dict(zip(("keys_sorted", "point_list", "keys_other", "vals_other"), list(out)))
+
+
+def profile_enable(on=True):
+    load().gsr_profile_enable(1 if on else 0)
+
+
+def launch_count(reset=False):
+    return int(load().gsr_launch_count(1 if reset else 0))
+
+
+def profile_dump():
+    """{kernel name: (launches, total_ms)} measured with CUDA events on the launching stream."""
+    buf = ctypes.create_string_buffer(8192)
+    load().gsr_profile_dump(buf, 8192)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -74,6 +74,15 @@ typedef struct gsr_deform {
 const char* gsr_last_error_string(void);
 int gsr_version(void);
 
+/* Launch accounting and per-kernel timing.  gsr_launch_count: kernels launched by
+ * this library since the last reset.  With profiling enabled every kernel launch is
+ * bracketed by CUDA events on its stream; gsr_profile_dump synchronises those events
+ * and writes one "name launches total_ms" line per kernel into out (returns the
+ * number of kernels).  Single-threaded use. */
+void gsr_profile_enable(int on);
+unsigned long long gsr_launch_count(int reset);
+int gsr_profile_dump(char* out, size_t cap);
+
 /* ---- workspace sizes ---------------------------------------------------- */
 size_t gsr_geom_bytes(int P);                       /* per-Gaussian state of one view        */
 size_t gsr_image_bytes(int width, int height);      /* final_T, n_contrib, tile ranges       */
