@@ -292,6 +292,26 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
     return gsr_launch_blend_fwd(b, stream);
 }
 
+// Debug: workload counters of the blend stage for a finished forward (see blend.cu).
+int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t R, const void* geom_ws, const void* binning_ws,
+                          const void* image_ws, unsigned long long* out8, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GsrView v;
+    if (int rc = fill_view(view, 0, v)) return rc;
+    if (P <= 0 || R == 0 || !geom_ws || !binning_ws || !image_ws || !out8) return gsr_set_error_msg(-1, "blend_stats: bad arguments");
+    const GeomLayout L = geom_layout(P);
+    const ImageLayout IL = image_layout(v.W, v.H);
+    const BinLayout BL = bin_layout(R, v.W, v.H);
+    const bool in_b = (BL.passes & 1) != 0;
+    BlendFwdArgs b{};
+    b.ranges = reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(image_ws) + IL.ranges);
+    b.point_list = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(binning_ws) + (in_b ? BL.vals_b : BL.vals_a));
+    b.recs = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(geom_ws) + L.recs);
+    b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
+    GSR_CHECK(cudaMemsetAsync(out8, 0, 8 * sizeof(unsigned long long), stream));
+    return gsr_launch_blend_stats(b, out8, stream);
+}
+
 int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* means3D, const float* means_deformed,
                  const float* scales, const float* rotations, const float* shs, const float* cov3D_precomp,
                  const float* colors_precomp, const gsr_deform* deform, const int32_t* radii, const void* geom_ws,

@@ -26,6 +26,7 @@
 //     9 scalar atomics per (pixel, Gaussian).
 #include "geom_exact.cuh"
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -70,6 +71,7 @@ __device__ __forceinline__ bool tile_may_contribute(float mx, float my, float a,
 
 // Stable compaction of one flag per thread across the CTA.  Returns this
 // thread's output slot (valid when keep) and the CTA total in `total`.
+template <int NT = BLK>
 __device__ __forceinline__ int block_compact(bool keep, uint32_t* s_wcount, int& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(FULL, keep);
@@ -77,7 +79,7 @@ __device__ __forceinline__ int block_compact(bool keep, uint32_t* s_wcount, int&
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < BLK / 32; w++) {
+    for (int w = 0; w < NT / 32; w++) {
         const int c = (int)s_wcount[w];
         base += (w < warp) ? c : 0;
         tot += c;
@@ -87,37 +89,55 @@ __device__ __forceinline__ int block_compact(bool keep, uint32_t* s_wcount, int&
 }
 
 // ---------------------------------------------------------------------------
-// Forward
+// Forward.  PPT pixels per thread: a CTA has 256/PPT threads; warp w owns the PPT
+// consecutive 8x4 patches w*PPT .. w*PPT+PPT-1 (patch p at ((p&1)*8, (p>>1)*4)) and
+// lane l owns the same in-patch pixel of each.  Staged records, loop control and the
+// contributor bookkeeping are then paid once per PPT pixels.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLK) blend_fwd_kernel(BlendFwdArgs a) {
-    __shared__ float4 s_q0[BLK];     // x, y, conic.x, conic.y
-    __shared__ float4 s_q1[BLK];     // conic.z, opacity, cut, (contributor number as bits)
-    __shared__ float4 s_q2[BLK];     // r, g, b, -
+template <int PPT>
+__device__ __forceinline__ void patch_pixel(int tid, int slot, int& lx, int& ly) {
+    const int w = tid >> 5, l = tid & 31;
+    const int p = w * PPT + slot;
+    lx = ((p & 1) << 3) + (l & 7);
+    ly = ((p >> 1) << 2) + (l >> 3);
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(BLK / PPT) blend_fwd_kernel(BlendFwdArgs a) {
+    constexpr int NT = BLK / PPT;
+    __shared__ float4 s_q0[NT];     // x, y, conic.x, conic.y
+    __shared__ float4 s_q1[NT];     // conic.z, opacity, cut, (contributor number as bits)
+    __shared__ float4 s_q2[NT];     // r, g, b, -
     __shared__ uint32_t s_wcount[BLK / 32];
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.y * a.grid_x + blockIdx.x;
-    int lx, ly;
-    tile_pixel(tid, lx, ly);
-    const int px = blockIdx.x * GSR_TILE + lx, py = blockIdx.y * GSR_TILE + ly;
-    const bool inside = px < a.W && py < a.H;
-    const float pxf = (float)px, pyf = (float)py;
+    float pxf[PPT], pyf[PPT], T[PPT], C0[PPT], C1[PPT], C2[PPT];
+    uint32_t last_contributor[PPT];
+    bool done[PPT], inside[PPT];
+    int pxi[PPT], pyi[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+        int lx, ly;
+        patch_pixel<PPT>(tid, s, lx, ly);
+        pxi[s] = blockIdx.x * GSR_TILE + lx; pyi[s] = blockIdx.y * GSR_TILE + ly;
+        inside[s] = pxi[s] < a.W && pyi[s] < a.H;
+        pxf[s] = (float)pxi[s]; pyf[s] = (float)pyi[s];
+        done[s] = !inside[s];
+        T[s] = 1.0f; C0[s] = C1[s] = C2[s] = 0.0f; last_contributor[s] = 0;
+    }
     const float tx0 = (float)(blockIdx.x * GSR_TILE), ty0 = (float)(blockIdx.y * GSR_TILE);
     const float tx1 = fminf(tx0 + 15.0f, (float)(a.W - 1)), ty1 = fminf(ty0 + 15.0f, (float)(a.H - 1));
 
     const uint2 range = a.ranges[tile];
     const int todo = (int)(range.y - range.x);
-    const int rounds = (todo + BLK - 1) / BLK;
-
-    bool done = !inside;
-    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
-    uint32_t last_contributor = 0;
+    const int rounds = (todo + NT - 1) / NT;
 
     // Software pipeline: gathers of batch i+1 are in flight while batch i is blended.
     float4 n0, n1, n2;
     bool nvalid = false;
     auto fetch = [&](int round) {
-        const int pos = round * BLK + tid;
+        const int pos = round * NT + tid;
         nvalid = pos < todo;
         if (nvalid) {
             const uint32_t id = a.point_list[range.x + pos];
@@ -128,46 +148,57 @@ __global__ void __launch_bounds__(BLK) blend_fwd_kernel(BlendFwdArgs a) {
     if (rounds > 0) fetch(0);
 
     for (int i = 0; i < rounds; i++) {
+        bool all_done = true;
+#pragma unroll
+        for (int s = 0; s < PPT; s++) all_done = all_done && done[s];
         // Whole CTA done?  (also the barrier that protects the staging buffers)
-        if (__syncthreads_count(done) == BLK) break;
+        if (__syncthreads_count(all_done) == NT) break;
         const float4 q0 = n0, q1 = n1, q2 = n2;
         const bool keep = nvalid && tile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q2.y, tx0, ty0, tx1, ty1);
-        const int pos = i * BLK + tid;
+        const int pos = i * NT + tid;
         if (i + 1 < rounds) fetch(i + 1);
         int n;
-        const int slot = block_compact(keep, s_wcount, n);
+        const int slot = block_compact<NT>(keep, s_wcount, n);
         if (keep) {
             s_q0[slot] = q0;
             s_q1[slot] = make_float4(q1.x, q1.y, q2.y, __uint_as_float((uint32_t)pos + 1u));
             s_q2[slot] = make_float4(q1.z, q1.w, q2.x, 0.0f);
         }
         __syncthreads();
-        for (int j = 0; !done && j < n; j++) {
+        for (int j = 0; j < n; j++) {
+            if (PPT == 1) { if (done[0]) break; }
             const float4 g0 = s_q0[j];
             const float4 g1 = s_q1[j];
-            const float dx = g0.x - pxf, dy = g0.y - pyf;
-            const float power = blend_power_exact(dx, dy, g0.z, g0.w, g1.x);
-            if (power > 0.0f || power < g1.z) continue;
-            const float alpha = fminf(0.99f, g1.y * expf(power));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = T * (1.0f - alpha);
-            if (test_T < 0.0001f) { done = true; continue; }
-            const float4 col = s_q2[j];
-            C0 = fmaf(T, alpha * col.x, C0);
-            C1 = fmaf(T, alpha * col.y, C1);
-            C2 = fmaf(T, alpha * col.z, C2);
-            T = test_T;
-            last_contributor = __float_as_uint(g1.w);
+#pragma unroll
+            for (int s = 0; s < PPT; s++) {
+                if (done[s]) continue;
+                const float dx = g0.x - pxf[s], dy = g0.y - pyf[s];
+                const float power = blend_power_exact(dx, dy, g0.z, g0.w, g1.x);
+                if (power > 0.0f || power < g1.z) continue;
+                const float alpha = fminf(0.99f, g1.y * expf(power));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float test_T = T[s] * (1.0f - alpha);
+                if (test_T < 0.0001f) { done[s] = true; continue; }
+                const float4 col = s_q2[j];
+                C0[s] = fmaf(T[s], alpha * col.x, C0[s]);
+                C1[s] = fmaf(T[s], alpha * col.y, C1[s]);
+                C2[s] = fmaf(T[s], alpha * col.z, C2[s]);
+                T[s] = test_T;
+                last_contributor[s] = __float_as_uint(g1.w);
+            }
         }
     }
-    if (inside) {
-        const size_t pix = (size_t)py * a.W + px;
-        const size_t HW = (size_t)a.H * a.W;
-        a.final_T[pix] = T;
-        a.n_contrib[pix] = last_contributor;
-        a.out_color[pix] = fmaf(T, a.bg[0], C0);
-        a.out_color[HW + pix] = fmaf(T, a.bg[1], C1);
-        a.out_color[2 * HW + pix] = fmaf(T, a.bg[2], C2);
+    const size_t HW = (size_t)a.H * a.W;
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+        if (inside[s]) {
+            const size_t pix = (size_t)pyi[s] * a.W + pxi[s];
+            a.final_T[pix] = T[s];
+            a.n_contrib[pix] = last_contributor[s];
+            a.out_color[pix] = fmaf(T[s], a.bg[0], C0[s]);
+            a.out_color[HW + pix] = fmaf(T[s], a.bg[1], C1[s]);
+            a.out_color[2 * HW + pix] = fmaf(T[s], a.bg[2], C2[s]);
+        }
     }
 }
 
@@ -207,50 +238,61 @@ __device__ __forceinline__ void warp_reduce9(float (&v)[9], int lane) {
     for (int o = 16; o > 0; o >>= 1) v[8] += __shfl_xor_sync(FULL, v[8], o);
 }
 
-__global__ void __launch_bounds__(BLK) blend_bwd_kernel(BlendBwdArgs a) {
-    __shared__ float4 s_q0[BLK];
-    __shared__ float4 s_q1[BLK];     // conic.z, opacity, cut, list position as bits
-    __shared__ float4 s_q2[BLK];     // r, g, b, -
-    __shared__ uint32_t s_id[BLK];
-    __shared__ float s_grad[BLK][9];
-    __shared__ uint32_t s_touched[BLK];
+// 1/x to ~1 ulp for x in [0.01, 1]: MUFU.RCP + one Newton step (the reference's IEEE
+// division T/(1-alpha) costs ~10 instructions; gradients tolerate 1e-4 relative).
+__device__ __forceinline__ float rcp_nr(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(BLK / PPT) blend_bwd_kernel(BlendBwdArgs a) {
+    constexpr int NT = BLK / PPT;
+    __shared__ float4 s_q0[NT];
+    __shared__ float4 s_q1[NT];     // conic.z, opacity, cut, list position as bits
+    __shared__ float4 s_q2[NT];     // r, g, b, Gaussian id as bits
     __shared__ uint32_t s_wcount[BLK / 32];
     __shared__ uint32_t s_wmax[BLK / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * a.grid_x + blockIdx.x;
-    int lx, ly;
-    tile_pixel(tid, lx, ly);
-    const int px = blockIdx.x * GSR_TILE + lx, py = blockIdx.y * GSR_TILE + ly;
-    const bool inside = px < a.W && py < a.H;
-    const float pxf = (float)px, pyf = (float)py;
     const float tx0 = (float)(blockIdx.x * GSR_TILE), ty0 = (float)(blockIdx.y * GSR_TILE);
     const float tx1 = fminf(tx0 + 15.0f, (float)(a.W - 1)), ty1 = fminf(ty0 + 15.0f, (float)(a.H - 1));
     const uint2 range = a.ranges[tile];
-
-    const size_t pix = (size_t)py * a.W + px;
     const size_t HW = (size_t)a.H * a.W;
-    const float T_final = inside ? a.final_T[pix] : 0.0f;
-    const uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
-    float dpx0 = 0.0f, dpx1 = 0.0f, dpx2 = 0.0f;
-    if (inside) { dpx0 = a.dL_dpix[pix]; dpx1 = a.dL_dpix[HW + pix]; dpx2 = a.dL_dpix[2 * HW + pix]; }
-    const float bg_dot = a.bg[0] * dpx0 + a.bg[1] * dpx1 + a.bg[2] * dpx2;
     const bool has_bg = (a.bg[0] != 0.0f) || (a.bg[1] != 0.0f) || (a.bg[2] != 0.0f);
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
 
+    float pxf[PPT], pyf[PPT], T[PPT], T_final[PPT], dpx0[PPT], dpx1[PPT], dpx2[PPT], bg_dot[PPT];
+    float acc0[PPT], acc1[PPT], acc2[PPT], lc0[PPT], lc1[PPT], lc2[PPT], last_alpha[PPT];
+    uint32_t last_contributor[PPT];
+    uint32_t m = 0;
+#pragma unroll
+    for (int s = 0; s < PPT; s++) {
+        int lx, ly;
+        patch_pixel<PPT>(tid, s, lx, ly);
+        const int px = blockIdx.x * GSR_TILE + lx, py = blockIdx.y * GSR_TILE + ly;
+        const bool inside = px < a.W && py < a.H;
+        pxf[s] = (float)px; pyf[s] = (float)py;
+        const size_t pix = (size_t)py * a.W + px;
+        T_final[s] = inside ? a.final_T[pix] : 0.0f;
+        last_contributor[s] = inside ? a.n_contrib[pix] : 0u;
+        dpx0[s] = dpx1[s] = dpx2[s] = 0.0f;
+        if (inside) { dpx0[s] = a.dL_dpix[pix]; dpx1[s] = a.dL_dpix[HW + pix]; dpx2[s] = a.dL_dpix[2 * HW + pix]; }
+        bg_dot[s] = a.bg[0] * dpx0[s] + a.bg[1] * dpx1[s] + a.bg[2] * dpx2[s];
+        T[s] = T_final[s];
+        acc0[s] = acc1[s] = acc2[s] = lc0[s] = lc1[s] = lc2[s] = last_alpha[s] = 0.0f;
+        m = max(m, last_contributor[s]);
+    }
     // Nothing behind the tile's deepest contributor matters to any pixel.
-    uint32_t m = last_contributor;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
     if (lane == 0) s_wmax[warp] = m;
     __syncthreads();
     uint32_t tile_last = 0;
 #pragma unroll
-    for (int w = 0; w < BLK / 32; w++) tile_last = max(tile_last, s_wmax[w]);
-
-    float T = T_final;
-    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
-    float last_alpha = 0.0f, lc0 = 0.0f, lc1 = 0.0f, lc2 = 0.0f;
+    for (int w = 0; w < NT / 32; w++) tile_last = max(tile_last, s_wmax[w]);
 
     float4 n0, n1, n2;
     uint32_t nid = 0;
@@ -265,107 +307,205 @@ __global__ void __launch_bounds__(BLK) blend_bwd_kernel(BlendBwdArgs a) {
         }
     };
     if (tile_last > 0) fetch((int)tile_last);
+    float* const grad_base = reinterpret_cast<float*>(a.grad_recs);
 
-    for (int start = (int)tile_last; start > 0; start -= BLK) {
+    for (int start = (int)tile_last; start > 0; start -= NT) {
         const float4 q0 = n0, q1 = n1, q2 = n2;
         const uint32_t id = nid;
         const int pos = start - 1 - tid;
         const bool keep = nvalid && tile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q2.y, tx0, ty0, tx1, ty1);
-        if (start - BLK > 0) fetch(start - BLK);
+        if (start - NT > 0) fetch(start - NT);
         int n;
-        const int slot = block_compact(keep, s_wcount, n);   // contains a barrier: previous flush is complete
+        const int slot = block_compact<NT>(keep, s_wcount, n);   // barrier: previous batch fully consumed
         if (keep) {
             s_q0[slot] = q0;
             s_q1[slot] = make_float4(q1.x, q1.y, q2.y, __uint_as_float((uint32_t)pos));
-            s_q2[slot] = make_float4(q1.z, q1.w, q2.x, 0.0f);
-            s_id[slot] = id;
+            s_q2[slot] = make_float4(q1.z, q1.w, q2.x, __uint_as_float(id));
         }
-        for (int k = tid; k < n * 9; k += BLK) (&s_grad[0][0])[k] = 0.0f;
-        if (tid < n) s_touched[tid] = 0;
         __syncthreads();
 
         for (int j = 0; j < n; j++) {
             const float4 g0 = s_q0[j];
             const float4 g1 = s_q1[j];
             const uint32_t pos_j = __float_as_uint(g1.w);
-            float v[9];
-            bool active = false;
-            float dx = 0.f, dy = 0.f, power = 0.f;
-            if (pos_j < last_contributor) {
-                dx = g0.x - pxf; dy = g0.y - pyf;
-                power = blend_power_exact(dx, dy, g0.z, g0.w, g1.x);
-                active = !(power > 0.0f || power < g1.z);
-            }
-            float G = 0.f, alpha = 0.f;
-            if (active) {
-                G = expf(power);
-                alpha = fminf(0.99f, g1.y * G);
-                active = !(alpha < 1.0f / 255.0f);
-            }
-            if (!__any_sync(FULL, active)) continue;
-            if (active) {
-                const float4 col = s_q2[j];
-                const float one_m_alpha = 1.0f - alpha;
-                T = T / one_m_alpha;
-                const float dchannel_dcolor = alpha * T;
-                float dL_dalpha = 0.0f;
-                acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0; lc0 = col.x;
-                dL_dalpha += (col.x - acc0) * dpx0;
-                acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1; lc1 = col.y;
-                dL_dalpha += (col.y - acc1) * dpx1;
-                acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2; lc2 = col.z;
-                dL_dalpha += (col.z - acc2) * dpx2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                if (has_bg) dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
-                const float dL_dG = g1.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-                const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
-                v[6] = dchannel_dcolor * dpx0;
-                v[7] = dchannel_dcolor * dpx1;
-                v[8] = dchannel_dcolor * dpx2;
-            } else {
+            bool act[PPT];
+            float dx[PPT], dy[PPT], G[PPT], alpha[PPT];
+            bool any_lane = false;
 #pragma unroll
-                for (int k = 0; k < 9; k++) v[k] = 0.0f;
+            for (int s = 0; s < PPT; s++) {
+                act[s] = false;
+                if (pos_j < last_contributor[s]) {
+                    dx[s] = g0.x - pxf[s]; dy[s] = g0.y - pyf[s];
+                    const float power = blend_power_exact(dx[s], dy[s], g0.z, g0.w, g1.x);
+                    if (!(power > 0.0f || power < g1.z)) {
+                        G[s] = expf(power);
+                        alpha[s] = fminf(0.99f, g1.y * G[s]);
+                        act[s] = !(alpha[s] < 1.0f / 255.0f);
+                    }
+                }
+                any_lane = any_lane || act[s];
+            }
+            if (!__any_sync(FULL, any_lane)) continue;
+            const float4 col = s_q2[j];
+            float v[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) v[k] = 0.0f;
+#pragma unroll
+            for (int s = 0; s < PPT; s++) {
+                if (act[s]) {
+                    const float one_m_alpha = 1.0f - alpha[s];
+                    const float inv = rcp_nr(one_m_alpha);
+                    T[s] = T[s] * inv;
+                    const float dchannel_dcolor = alpha[s] * T[s];
+                    const float la = last_alpha[s], one_m_la = 1.0f - la;
+                    acc0[s] = la * lc0[s] + one_m_la * acc0[s]; lc0[s] = col.x;
+                    acc1[s] = la * lc1[s] + one_m_la * acc1[s]; lc1[s] = col.y;
+                    acc2[s] = la * lc2[s] + one_m_la * acc2[s]; lc2[s] = col.z;
+                    float dL_dalpha = ((col.x - acc0[s]) * dpx0[s] + (col.y - acc1[s]) * dpx1[s] +
+                                       (col.z - acc2[s]) * dpx2[s]) * T[s];
+                    last_alpha[s] = alpha[s];
+                    if (has_bg) dL_dalpha += (-T_final[s] * inv) * bg_dot[s];
+                    const float dL_dG = g1.y * dL_dalpha;
+                    const float gdx = G[s] * dx[s], gdy = G[s] * dy[s];
+                    const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+                    const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+                    const float h = -0.5f * dL_dG;
+                    v[0] += dL_dG * dG_ddelx;
+                    v[1] += dL_dG * dG_ddely;
+                    v[2] += h * gdx * dx[s];
+                    v[3] += h * gdx * dy[s];
+                    v[4] += h * gdy * dy[s];
+                    v[5] += G[s] * dL_dalpha;
+                    v[6] += dchannel_dcolor * dpx0[s];
+                    v[7] += dchannel_dcolor * dpx1[s];
+                    v[8] += dchannel_dcolor * dpx2[s];
+                }
             }
             warp_reduce9(v, lane);
-            if ((lane & 3) == 0) atomicAdd(&s_grad[j][lane >> 2], v[0]);
-            if (lane == 1) { atomicAdd(&s_grad[j][8], v[8]); s_touched[j] = 1; }
+            // Native float reductions straight to the per-Gaussian gradient record.
+            float* dst = grad_base + 12 * (size_t)__float_as_uint(col.w);
+            if ((lane & 3) == 0) {
+                const int k = lane >> 2;
+                float val = v[0];
+                if (k == 0) val *= ddelx_dx;
+                if (k == 1) val *= ddely_dy;
+                atomicAdd(dst + k, val);
+            } else if (lane == 1) {
+                atomicAdd(dst + 8, v[8]);
+            }
         }
-        __syncthreads();
-        // Flush the CTA's per-Gaussian sums: two 128-bit vector reductions + one scalar.
-        if (tid < n && s_touched[tid]) {
-            const float* g = s_grad[tid];
-            float4* dst = a.grad_recs + 3 * (size_t)s_id[tid];
-            atomicAdd(dst, make_float4(g[0], g[1], g[2], g[3]));
-            atomicAdd(dst + 1, make_float4(g[4], g[5], g[6], g[7]));
-            atomicAdd(reinterpret_cast<float*>(dst + 2), g[8]);
-        }
-        // next iteration's block_compact barrier orders this flush before re-staging
     }
+}
+
+// ---------------------------------------------------------------------------
+// Debug: replay the forward loop and count what the blend kernels have to do.
+// out[0] staged list entries   out[1] survivors of the tile cull
+// out[2] (warp, survivor) iterations   out[3] ... with >= 1 lane passing the power/cut test
+// out[4] ... with >= 1 lane blending   out[5] (pixel, entry) pairs evaluated
+// out[6] (pixel, entry) pairs blended  out[7] list entries in all tile ranges
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLK) blend_stats_kernel(BlendFwdArgs a, unsigned long long* out) {
+    __shared__ float4 s_q0[BLK];
+    __shared__ float4 s_q1[BLK];
+    __shared__ uint32_t s_wcount[BLK / 32];
+    __shared__ unsigned long long s_cnt[8];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 8) s_cnt[tid] = 0;
+    const int tile = blockIdx.y * a.grid_x + blockIdx.x;
+    int lx, ly;
+    tile_pixel(tid, lx, ly);
+    const int px = blockIdx.x * GSR_TILE + lx, py = blockIdx.y * GSR_TILE + ly;
+    const bool inside = px < a.W && py < a.H;
+    const float pxf = (float)px, pyf = (float)py;
+    const float tx0 = (float)(blockIdx.x * GSR_TILE), ty0 = (float)(blockIdx.y * GSR_TILE);
+    const float tx1 = fminf(tx0 + 15.0f, (float)(a.W - 1)), ty1 = fminf(ty0 + 15.0f, (float)(a.H - 1));
+    const uint2 range = a.ranges[tile];
+    const int todo = (int)(range.y - range.x);
+    const int rounds = (todo + BLK - 1) / BLK;
+    bool done = !inside;
+    float T = 1.0f;
+    unsigned long long c_staged = 0, c_surv = 0, c_wit = 0, c_wpow = 0, c_wblend = 0, c_peval = 0, c_pblend = 0;
+    for (int i = 0; i < rounds; i++) {
+        if (__syncthreads_count(done) == BLK) break;
+        const int pos = i * BLK + tid;
+        bool keep = false;
+        float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+        if (pos < todo) {
+            const uint32_t id = a.point_list[range.x + pos];
+            const float4* r = a.recs + 3 * (size_t)id;
+            q0 = r[0]; q1 = r[1]; q2 = r[2];
+            keep = tile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q2.y, tx0, ty0, tx1, ty1);
+            c_staged++;
+        }
+        int n;
+        const int slot = block_compact(keep, s_wcount, n);
+        if (keep) { s_q0[slot] = q0; s_q1[slot] = make_float4(q1.x, q1.y, q2.y, 0.f); c_surv++; }
+        __syncthreads();
+        for (int j = 0; j < n; j++) {
+            if (__all_sync(FULL, done)) break;
+            if (lane == 0) c_wit++;
+            const float4 g0 = s_q0[j];
+            const float4 g1 = s_q1[j];
+            bool pw = false, bl = false;
+            if (!done) {
+                c_peval++;
+                const float dx = g0.x - pxf, dy = g0.y - pyf;
+                const float power = blend_power_exact(dx, dy, g0.z, g0.w, g1.x);
+                if (!(power > 0.0f || power < g1.z)) {
+                    pw = true;
+                    const float alpha = fminf(0.99f, g1.y * expf(power));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = T * (1.0f - alpha);
+                        if (test_T < 0.0001f) done = true;
+                        else { T = test_T; bl = true; c_pblend++; }
+                    }
+                }
+            }
+            const bool anyp = __any_sync(FULL, pw), anyb = __any_sync(FULL, bl);
+            if (lane == 0) { c_wpow += anyp; c_wblend += anyb; }
+        }
+    }
+    atomicAdd(&s_cnt[0], c_staged); atomicAdd(&s_cnt[1], c_surv); atomicAdd(&s_cnt[2], c_wit);
+    atomicAdd(&s_cnt[3], c_wpow); atomicAdd(&s_cnt[4], c_wblend); atomicAdd(&s_cnt[5], c_peval);
+    atomicAdd(&s_cnt[6], c_pblend);
+    __syncthreads();
+    if (tid < 7) atomicAdd(&out[tid], s_cnt[tid]);
+    if (tid == 7) atomicAdd(&out[7], (unsigned long long)todo);
 }
 
 }  // namespace
 
+int gsr_launch_blend_stats(const BlendFwdArgs& a, unsigned long long* out, cudaStream_t stream) {
+    dim3 grid(a.grid_x, a.grid_y, 1);
+    blend_stats_kernel<<<grid, BLK, 0, stream>>>(a, out);
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// Pixels per thread of the blend kernels (1, 2 or 4): GSR_FWD_PPT / GSR_BWD_PPT.
 int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
+    static const int ppt = env_int("GSR_FWD_PPT", 2);
     { GsrProfScope prof_("blend_fwd", stream);
-    blend_fwd_kernel<<<grid, BLK, 0, stream>>>(a); }
+    if (ppt == 4) blend_fwd_kernel<4><<<grid, BLK / 4, 0, stream>>>(a);
+    else if (ppt == 2) blend_fwd_kernel<2><<<grid, BLK / 2, 0, stream>>>(a);
+    else blend_fwd_kernel<1><<<grid, BLK, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
 
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
+    static const int ppt = env_int("GSR_BWD_PPT", 4);
     { GsrProfScope prof_("blend_bwd", stream);
-    blend_bwd_kernel<<<grid, BLK, 0, stream>>>(a); }
+    if (ppt == 4) blend_bwd_kernel<4><<<grid, BLK / 4, 0, stream>>>(a);
+    else if (ppt == 2) blend_bwd_kernel<2><<<grid, BLK / 2, 0, stream>>>(a);
+    else blend_bwd_kernel<1><<<grid, BLK, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

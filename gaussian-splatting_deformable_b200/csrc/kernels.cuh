@@ -57,6 +57,7 @@ struct BlendFwdArgs {
     uint32_t* n_contrib;     // [H*W]
 };
 int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream);
+int gsr_launch_blend_stats(const BlendFwdArgs& a, unsigned long long* out8, cudaStream_t stream);
 
 struct BlendBwdArgs {
     const uint2* ranges; const uint32_t* point_list; const float4* recs;

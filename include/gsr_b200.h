@@ -137,6 +137,13 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
                  float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
                  float* dL_dtwist_S, float* dL_dtwist_theta, void* stream);
 
+/* Debug/measurement aid: replays the blend loop of a finished forward and writes 8
+ * workload counters (device u64[8]): staged entries, tile-cull survivors,
+ * (warp,entry) iterations, ... with a lane passing the power test, ... with a lane
+ * blending, (pixel,entry) pairs evaluated, pairs blended, total list entries. */
+int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t num_rendered, const void* geom_ws,
+                          const void* binning_ws, const void* image_ws, unsigned long long* out8, void* stream);
+
 /* ---- the rest of the reference's operator surface -------------------------- */
 int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t* present, void* stream);
 
