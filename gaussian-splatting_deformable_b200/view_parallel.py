@@ -1,0 +1,84 @@
+"""View-parallel (data-parallel over cameras) training support.
+
+The reference is single-process / single-GPU (utils/general_utils.py:133 pins cuda:0)
+and has no distributed code at all.  The render of each (camera, time) is independent
+given the full parameter set and gradients are additive, so the hot path shards by
+VIEW: every rank keeps a full replica of the Gaussian parameters (and twists), renders
+cameras {rank, rank+G, ...} of the step's batch, sums their per-Gaussian gradients
+locally, and ONE all-reduce of a single flat fp32 buffer makes the replicas agree
+(59 floats = 236 B per Gaussian for xyz/f_dc/f_rest/opacity/scaling/rotation,
+scene/gaussian_model.py:825-831, + 7 per twist).  There is no other exchange step -
+no collective on the data path - so nothing else is communicated.
+
+One process per GPU, `torch.distributed` (NCCL on GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def partition_views(num_views, world_size, rank):
+    """Indices of the views rank `rank` renders: a round-robin split, so that
+    neighbouring (similar-cost) cameras land on different ranks."""
+    return list(range(rank, num_views, world_size))
+
+
+class FlatGradBuffer:
+    """Gradients of a set of leaf tensors laid out in ONE contiguous fp32 buffer.
+
+    Each parameter's `.grad` is a view into the buffer, so autograd accumulates the
+    views' gradients in place across the views a rank renders and the all-reduce runs
+    on the buffer itself - no pack/unpack kernels around the collective."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        total = sum(p.numel() for p in self.params)
+        first = self.params[0]
+        self.flat = torch.zeros(total, dtype=torch.float32, device=first.device)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero_(self):
+        self.flat.zero_()
+        off = 0
+        for p in self.params:          # re-attach: callers may have replaced .grad
+            n = p.numel()
+            g = self.flat[off:off + n].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g
+            off += n
+
+    def all_reduce(self, group=None, average=False):
+        """Sum (or average) the flat buffer over all ranks.  Returns bytes reduced."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                self.flat.div_(dist.get_world_size(group))
+        return self.flat.numel() * 4
+
+
+def reduce_densification_stats(xyz_gradient_accum, denom, max_radii2D, group=None):
+    """Make the densification statistics identical on all ranks (SUM for the
+    accumulated view-space gradient norms and their counts, MAX for the radii;
+    scene/gaussian_model.py:1252-1257, train.py:613), so every replica takes the
+    same clone/split/prune decisions."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(denom, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+def render_step(render_view, views, buffer, group=None):
+    """One view-parallel step: `render_view(i)` must run forward+backward for local view
+    i (accumulating into the parameters' .grad, i.e. into `buffer`) and return the loss.
+    Returns the summed loss of the local views (a tensor)."""
+    buffer.zero_()
+    total = None
+    for i in views:
+        loss = render_view(i)
+        total = loss.detach() if total is None else total + loss.detach()
+    buffer.all_reduce(group=group)
+    return total

@@ -1,0 +1,126 @@
+"""Helpers shared by the GPU parity tests (all calls go through the C ABI)."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+import gsr_runtime as rt
+import synthetic
+from diff_gaussian_rasterization import GaussianRasterizer
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KEYS = ("means3D", "scales", "rotations", "opacities", "shs")
+
+
+def bits_equal(a, b):
+    a, b = a.detach().contiguous(), b.detach().contiguous()
+    if a.dtype.is_floating_point:
+        return bool((a.float().view(torch.int32) == b.float().view(torch.int32)).all())
+    return bool((a == b).all())
+
+
+def rel_to_max(a, b):
+    a, b = a.detach().double(), b.detach().double().reshape(a.shape)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def make_view_settings(P, W, H, k=0, K=1, bg=(0.1, 0.2, 0.3), seed=0, scale_mult=1.0, sh_degree=3, scale_modifier=1.0):
+    dev = "cuda"
+    sc = synthetic.make_scene(P, seed=seed, device=dev, scale_mult=scale_mult)
+    cam = synthetic.make_camera(k, K, W, H, device=dev)
+    rs = synthetic.raster_settings(cam, torch.tensor(bg, device=dev), sh_degree=sh_degree, scale_modifier=scale_modifier)
+    return sc, cam, rs
+
+
+def run_ours(rs, sc, grad, twists=None, body_id=None, colors_precomp=None, cov3D_precomp=None):
+    """Forward+backward through the public drop-in API.  Returns dict of results."""
+    ras = GaussianRasterizer(rs)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    kw = {}
+    extra = {}
+    if twists is not None:
+        extra["S"] = twists[0].clone().requires_grad_(True)
+        extra["theta"] = twists[1].clone().requires_grad_(True)
+        kw.update(se3_S=extra["S"], se3_theta=extra["theta"])
+        if body_id is not None:
+            kw["body_id"] = body_id
+    if colors_precomp is not None:
+        extra["colors"] = colors_precomp.clone().requires_grad_(True)
+        kw["colors_precomp"] = extra["colors"]
+    else:
+        kw["shs"] = leaves["shs"]
+    if cov3D_precomp is not None:
+        extra["cov3D"] = cov3D_precomp.clone().requires_grad_(True)
+        kw["cov3D_precomp"] = extra["cov3D"]
+    else:
+        kw.update(scales=leaves["scales"], rotations=leaves["rotations"])
+    color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], **kw)
+    if grad is not None:
+        (color * grad).sum().backward()
+    out = dict(color=color.detach(), radii=radii, means2D_grad=means2D.grad,
+               grads={k: v.grad for k, v in leaves.items()}, deformed=ras.deformed_means,
+               extra_grads={k: v.grad for k, v in extra.items()})
+    return out
+
+
+def intermediates(rs, sc, M=16, deform=None):
+    """Forward through the raw C ABI keeping the workspaces; returns sliced intermediates."""
+    lib = rt.load()
+    P = sc["means3D"].shape[0]
+    W, H = rs.image_width, rs.image_height
+    dev = sc["means3D"].device
+    view = rt.make_view(rs)
+    geom = torch.zeros(lib.gsr_geom_bytes(P), dtype=torch.uint8, device=dev)
+    img = torch.zeros(lib.gsr_image_bytes(W, H), dtype=torch.uint8, device=dev)
+    radii = torch.zeros(P, dtype=torch.int32, device=dev)
+    color = torch.zeros((3, H, W), device=dev)
+    mb = rt.pinned_u32(dev)
+    st = rt.stream_ptr(dev)
+    rt.check(lib.gsr_forward_preprocess(view, P, M, rt.ptr(sc["means3D"]), rt.ptr(sc["scales"]), rt.ptr(sc["rotations"]),
+                                        rt.ptr(sc["opacities"]), rt.ptr(sc["shs"]), None, None, rt.gsr_deform(), None,
+                                        rt.ptr(radii), rt.ptr(geom), geom.numel(), mb.data_ptr(), 1, st))
+    R = int(mb.item())
+    binning = torch.zeros(lib.gsr_binning_bytes(R, W, H), dtype=torch.uint8, device=dev)
+    rt.check(lib.gsr_forward_render(view, P, R, rt.ptr(radii), rt.ptr(geom), rt.ptr(binning), binning.numel(),
+                                    rt.ptr(img), rt.ptr(color), st))
+    torch.cuda.synchronize()
+    gl, il, bl = rt.geom_layout(P), rt.image_layout(W, H), rt.binning_layout(R, W, H)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+
+    def sl(buf, off, n, dt):
+        es = torch.empty((), dtype=dt).element_size()
+        return buf[off:off + n * es].view(dt)
+    recs = sl(geom, gl["recs"], 12 * P, torch.float32).view(P, 12)
+    cl = sl(geom, gl["clamped"], P, torch.uint8)
+    return dict(R=R, radii=radii, color=color,
+                depths=sl(geom, gl["depths"], P, torch.float32),
+                tiles_touched=sl(geom, gl["tiles_touched"], P, torch.int32),
+                point_offsets=sl(geom, gl["point_offsets"], P, torch.int32),
+                cov3D=sl(geom, gl["cov3D"], 6 * P, torch.float32).view(P, 6),
+                clamped=torch.stack([(cl & 1) > 0, (cl & 2) > 0, (cl & 4) > 0], 1),
+                means2D=recs[:, 0:2], conic_opacity=recs[:, 2:6], rgb=recs[:, 6:9],
+                keys_sorted=sl(binning, bl["keys_sorted"], R, torch.int64),
+                point_list=sl(binning, bl["point_list"], R, torch.int32),
+                final_T=sl(img, il["final_T"], W * H, torch.float32),
+                n_contrib=sl(img, il["n_contrib"], W * H, torch.int32),
+                ranges=sl(img, il["ranges"], 2 * tiles, torch.int32).view(tiles, 2))
+
+
+def sort_pairs(keys, vals, begin_bit, end_bit):
+    lib = rt.load()
+    n = keys.numel()
+    ka, kb = keys.clone(), torch.zeros_like(keys)
+    va, vb = vals.clone(), torch.zeros_like(vals)
+    nbytes = lib.gsr_sort_bytes(n, begin_bit, end_bit)
+    temp = torch.zeros(max(nbytes, 4), dtype=torch.uint8, device=keys.device)
+    in_b = ctypes.c_int(0)
+    rt.check(lib.gsr_sort_pairs(rt.ptr(ka), rt.ptr(kb), rt.ptr(va), rt.ptr(vb), n, begin_bit, end_bit,
+                                rt.ptr(temp), nbytes, ctypes.byref(in_b), rt.stream_ptr()))
+    torch.cuda.synchronize()
+    return (kb, vb) if in_b.value else (ka, va)
+
+
+def load_golden():
+    return np.load(os.path.join(GOLD, "raster_golden.npz"))

@@ -1,0 +1,158 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every
+symbol include/gsr_b200.h declares, workspace layouts are sane, and the Python
+operator mirrors the reference's interface (names, field order, error behaviour).
+No compute call is made (there is no GPU here and no CPU fallback)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import gsr_runtime as rt
+import diff_gaussian_rasterization as dgr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    txt = open(os.path.join(ROOT, "include", "gsr_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsr_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(rt.lib_path())
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libgsr_b200.so does not export %s" % n
+    # and the Python binding knows every one of them
+    assert set(names) == set(rt.EXPORTED_SYMBOLS)
+    assert rt.load().gsr_version() >= 100
+
+
+def test_struct_mirrors_match_header():
+    txt = open(os.path.join(ROOT, "include", "gsr_b200.h")).read()
+    body = re.search(r"typedef struct gsr_view \{(.*?)\} gsr_view;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [re.sub(r"\[.*", "", f.split()[-1]) for f in body.split(";") if f.strip()]
+    assert fields == [f[0] for f in rt.gsr_view._fields_]
+    assert ctypes.sizeof(rt.gsr_view) == 4 * (2 + 2 + 3 + 1 + 16 + 16 + 1 + 3 + 2)
+    assert [f[0] for f in rt.gsr_deform._fields_] == ["mode", "num_bodies", "S", "theta", "body_id"]
+
+
+def test_workspace_sizes_and_layouts():
+    lib = rt.load()
+    P, W, H, R = 1000000, 1920, 1080, 7600000
+    gl = rt.geom_layout(P)
+    offs = sorted(gl.values())
+    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and len(set(offs)) == len(offs)
+    assert gl["recs"] - gl["tiles_touched"] >= 4 * P and gl["clamped"] - gl["recs"] >= 48 * P
+    assert lib.gsr_geom_bytes(P) > max(offs)
+    assert lib.gsr_geom_bytes(2 * P) > lib.gsr_geom_bytes(P)
+    il = rt.image_layout(W, H)
+    assert il["n_contrib"] - il["final_T"] >= 4 * W * H and lib.gsr_image_bytes(W, H) >= il["ranges"] + 8 * 8160
+    bl = rt.binning_layout(R, W, H)
+    assert len(set(bl.values())) == 4
+    # 2 key arrays + 2 value arrays + onesweep state: between 24 B and 40 B per duplicate
+    assert 24 * R <= lib.gsr_binning_bytes(R, W, H) <= 40 * R
+    assert lib.gsr_binning_bytes(0, W, H) < 1 << 20
+    assert lib.gsr_grad_bytes(P) >= 48 * P
+    # 45 key bits at 1080p -> 6 digit passes (even): the sorted data ends in the first buffer pair
+    assert lib.gsr_sort_bytes(R, 0, 45) > 6 * ((R + 4095) // 4096) * 256 * 4
+    assert lib.gsr_knn_bytes(100000) > 100000 * (2 * 8 + 2 * 4 + 16)
+
+
+def test_settings_tuple_is_the_reference_one():
+    # diff_gaussian_rasterization/__init__.py:157-169
+    assert dgr.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+    sig = inspect.signature(dgr.GaussianRasterizer.forward)
+    assert list(sig.parameters)[:9] == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                        "rotations", "cov3D_precomp"]
+    for extra in ("se3_S", "se3_theta", "body_id"):         # additions are keyword-only, default None
+        p = sig.parameters[extra]
+        assert p.kind is inspect.Parameter.KEYWORD_ONLY and p.default is None
+    assert list(inspect.signature(dgr.rasterize_gaussians).parameters)[:9] == [
+        "means3D", "means2D", "sh", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp",
+        "raster_settings"]
+    assert hasattr(dgr.GaussianRasterizer, "markVisible") and hasattr(dgr, "_RasterizeGaussians")
+
+
+def _settings():
+    z = torch.zeros(3)
+    return dgr.GaussianRasterizationSettings(32, 32, 0.5, 0.5, z, 1.0, torch.eye(4), torch.eye(4), 3, z, False, False)
+
+
+def test_argument_validation_matches_reference_messages():
+    ras = dgr.GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3)
+    o = torch.zeros(4, 1)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        ras(m, m, o, scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        ras(m, m, o, shs=torch.zeros(4, 16, 3), colors_precomp=torch.zeros(4, 3), scales=torch.ones(4, 3),
+            rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        ras(m, m, o, shs=torch.zeros(4, 16, 3))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        ras(m, m, o, shs=torch.zeros(4, 16, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4),
+            cov3D_precomp=torch.zeros(4, 6))
+    with pytest.raises(Exception, match="both se3_S and se3_theta"):
+        ras(m, m, o, shs=torch.zeros(4, 16, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4),
+            se3_S=torch.zeros(4, 6))
+    with pytest.raises(RuntimeError, match=r"means3D must have dimensions \(num_points, 3\)"):
+        ras(torch.zeros(4, 4), m, o, shs=torch.zeros(4, 16, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must fail loudly: the product has no eager/CPU path."""
+    import rigid_body
+    from simple_knn._C import distCUDA2
+    ras = dgr.GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3)
+    with pytest.raises(rt.GsrError, match="no CPU fallback"):
+        ras(m, m, torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(rt.GsrError, match="no CPU fallback"):
+        distCUDA2(torch.zeros(8, 3))
+    with pytest.raises(rt.GsrError, match="no CPU fallback"):
+        rigid_body.exp_se3(torch.zeros(2, 6), torch.ones(2))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "gaussian-splatting_deformable_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), "%s mentions the oracle" % f
+
+
+def test_host_view_cache_tracks_identity_and_version():
+    t = torch.arange(3, dtype=torch.float32)
+    assert rt.host_values(t, 3) == [0.0, 1.0, 2.0]
+    t.add_(1)                                   # in-place edit bumps _version -> must be re-read
+    assert rt.host_values(t, 3) == [1.0, 2.0, 3.0]
+    u = torch.tensor([9.0, 9.0, 9.0])
+    assert rt.host_values(u, 3) == [9.0, 9.0, 9.0]
+    v = rt.make_view(_settings())
+    assert v.image_width == 32 and list(v.viewmatrix)[:5] == [1.0, 0.0, 0.0, 0.0, 0.0]
+
+
+def test_rigid_body_helpers_match_port():
+    import rigid_body
+    from oracle import rigid_body_port as port
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(5, 3, generator=g)
+    th = torch.rand(5, generator=g) + 0.1
+    p = torch.randn(5, 3, generator=g)
+    assert torch.equal(rigid_body.skew(w), port.skew(w))
+    torch.testing.assert_close(rigid_body.exp_so3(w, th), port.exp_so3(w, th))
+    R = port.exp_so3(w, th)
+    assert torch.equal(rigid_body.rp_to_se3(R, p), port.rp_to_se3(R, p))
+    assert torch.equal(rigid_body.to_homogenous(p), port.to_homogenous(p))
+    h = port.to_homogenous(p) * 2.0
+    assert torch.equal(rigid_body.from_homogenous(h), port.from_homogenous(h))

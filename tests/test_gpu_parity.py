@@ -1,0 +1,348 @@
+"""Parity of the sm_100a kernels (through the C ABI / drop-in API) with
+  (1) the reference's own CUDA rasterizer + simple-knn, rebuilt unmodified (oracle/_ref),
+  (2) golden vectors that reference produced (tests/golden/raster_golden.npz),
+  (3) the CPU oracle (oracle/gsr_oracle.c) and the rigid_body port.
+Bars (BASELINE.json north_star): tile keys, sort order and tile ranges bit-exact;
+images within 1e-5 max-abs; gradients within 1e-4 relative (atomics are unordered)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _ref():
+    from oracle import ref_driver
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return ref_driver
+
+
+def _ref_fb(rd, rs, sc, grad, means=None, **over):
+    kw = dict(shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+    kw.update(over)
+    kw = {k: v for k, v in kw.items() if v is not None}
+    m = sc["means3D"] if means is None else means
+    f = rd.forward(rs, m, sc["opacities"], **kw)
+    b = rd.backward(rs, f, grad, m, **kw) if grad is not None else None
+    torch.cuda.synchronize()
+    return f, b
+
+
+@pytest.mark.parametrize("P,W,H,smult", [(20000, 320, 200, 1.0), (200000, 800, 600, 1.0), (40000, 333, 177, 4.0),
+                                           (1000000, 1920, 1080, 1.0), (1500000, 3840, 2160, 1.0)])
+def test_forward_stages_bit_exact_vs_reference(P, W, H, smult):
+    import synthetic
+    from _gpu_util import bits_equal, intermediates, make_view_settings
+    rd = _ref()
+    sc, cam, rs = make_view_settings(P, W, H, scale_mult=smult)
+    f, _ = _ref_fb(rd, rs, sc, None)
+    R = f["num_rendered"]
+    g = rd.slice_geom(f["geom"], P)
+    b = rd.slice_binning(f["binning"], R)
+    im = rd.slice_img(f["img"], W, H)
+    m = intermediates(rs, sc)
+    vis = f["radii"] > 0
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    assert m["R"] == R and R > 0
+    assert torch.equal(m["radii"], f["radii"])
+    assert torch.equal(m["tiles_touched"], g["tiles_touched"])
+    assert torch.equal(m["point_offsets"], torch.cumsum(g["tiles_touched"], 0).int())
+    for k in ("depths", "means2D", "conic_opacity", "cov3D", "rgb"):
+        assert bits_equal(m[k][vis], g[k][vis]), k
+    assert torch.equal(m["clamped"][vis], g["clamped"][vis])
+    # tile keys, sort order, tile ranges: bit-exact
+    assert torch.equal(m["keys_sorted"], b["point_list_keys"])
+    assert torch.equal(m["point_list"], b["point_list"])
+    assert torch.equal(m["ranges"], im["ranges"][:tiles])
+    assert torch.equal(m["n_contrib"], im["n_contrib"])
+    assert float((m["final_T"] - im["accum_alpha"]).abs().max()) <= 1e-6
+    assert float((m["color"] - f["color"]).abs().max()) <= IMG_TOL
+
+
+@pytest.mark.parametrize("P,W,H,smult,bg", [(20000, 320, 200, 1.0, (0.1, 0.2, 0.3)), (200000, 800, 600, 1.0, (0, 0, 0)),
+                                              (30000, 250, 130, 5.0, (1, 1, 1)), (1000000, 1920, 1080, 1.0, (0, 0, 0))])
+def test_forward_backward_vs_reference(P, W, H, smult, bg):
+    import synthetic
+    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    rd = _ref()
+    sc, cam, rs = make_view_settings(P, W, H, scale_mult=smult, bg=bg)
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    f, b = _ref_fb(rd, rs, sc, grad)
+    o = run_ours(rs, sc, grad)
+    assert torch.equal(o["radii"], f["radii"])
+    assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
+    for k in ("means3D", "opacities", "shs", "scales", "rotations"):
+        assert rel_to_max(o["grads"][k], b[k]) <= GRAD_TOL, k
+    assert rel_to_max(o["means2D_grad"], b["means2D"]) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("case", ["sh3", "sh1", "precomp"])
+def test_golden_vectors(case):
+    """Against vectors the reference itself produced (no oracle/_ref needed at run time)."""
+    from _gpu_util import load_golden, rel_to_max, run_ours
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    g = load_golden()
+    P, W, H, deg, R = [int(x) for x in g[case + "/cfg"]]
+    t = lambda k: torch.from_numpy(g[case + "/" + k]).cuda()
+    tf = [float(x) for x in g[case + "/tanfov"]]
+    rs = GaussianRasterizationSettings(H, W, tf[0], tf[1], t("bg"), float(g[case + "/scale_modifier"][0]),
+                                       t("viewmatrix"), t("projmatrix"), deg, t("campos"), False, False)
+    sc = dict(means3D=t("means3D"), opacities=t("opacities"))
+    if case == "precomp":
+        sc.update(shs=torch.zeros(P, 16, 3, device="cuda"), scales=torch.ones(P, 3, device="cuda"),
+                  rotations=torch.ones(P, 4, device="cuda"))
+        o = run_ours(rs, sc, t("grad_image"), colors_precomp=t("colors_precomp"), cov3D_precomp=t("cov3D_precomp"))
+        pairs = [("colors", o["extra_grads"]["colors"]), ("cov3D", o["extra_grads"]["cov3D"])]
+    else:
+        sc.update(shs=t("shs"), scales=t("scales"), rotations=t("rotations"))
+        o = run_ours(rs, sc, t("grad_image"))
+        pairs = [(k, o["grads"][k]) for k in ("shs", "scales", "rotations")]
+    pairs += [("means3D", o["grads"]["means3D"]), ("opacities", o["grads"]["opacities"]), ("means2D", o["means2D_grad"])]
+    assert torch.equal(o["radii"], t("radii"))
+    assert float((o["color"] - t("color")).abs().max()) <= IMG_TOL
+    for k, got in pairs:
+        assert rel_to_max(got, t("grad_" + k)) <= GRAD_TOL, k
+
+
+def test_vs_cpu_oracle():
+    import synthetic
+    from _gpu_util import intermediates, make_view_settings, rel_to_max, run_ours
+    from oracle import oracle_c
+    P, W, H = 4000, 200, 120
+    sc, cam, rs = make_view_settings(P, W, H, scale_mult=2.5)
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    f = oracle_c.forward(rs, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+    b = oracle_c.backward(f, grad)
+    m = intermediates(rs, sc)
+    o = run_ours(rs, sc, grad)
+    assert m["R"] == f["num_rendered"]
+    assert np.array_equal(m["radii"].cpu().numpy(), f["radii"])
+    assert np.array_equal(m["keys_sorted"].cpu().numpy(), f["keys_sorted"].view(np.int64))
+    assert np.array_equal(m["point_list"].cpu().numpy().astype(np.int64), f["point_list"].astype(np.int64))
+    assert np.array_equal(m["ranges"].cpu().numpy().astype(np.int64), f["ranges"].astype(np.int64))
+    assert float(np.abs(o["color"].cpu().numpy() - f["color"]).max()) <= IMG_TOL
+    for k in ("means3D", "opacities", "shs", "scales", "rotations"):
+        assert rel_to_max(o["grads"][k].cpu(), torch.from_numpy(b[k])) <= GRAD_TOL, k
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_lower_sh_degrees_vs_reference(deg):
+    import synthetic
+    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    rd = _ref()
+    P, W, H = 30000, 400, 240
+    sc, cam, rs = make_view_settings(P, W, H, sh_degree=deg, scale_mult=1.5, scale_modifier=0.7)
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    f, b = _ref_fb(rd, rs, sc, grad)
+    o = run_ours(rs, sc, grad)
+    assert torch.equal(o["radii"], f["radii"])
+    assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
+    for k in ("means3D", "shs", "scales", "rotations", "opacities"):
+        assert rel_to_max(o["grads"][k], b[k]) <= GRAD_TOL, k
+    nz = (deg + 1) ** 2
+    assert float(o["grads"]["shs"][:, nz:].abs().max()) == 0.0      # inactive coefficients get zero gradient
+
+
+def test_precomputed_color_and_covariance_vs_reference():
+    import synthetic
+    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    rd = _ref()
+    P, W, H = 30000, 320, 320
+    sc, cam, rs = make_view_settings(P, W, H, scale_mult=2.0, sh_degree=0)
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    f0, _ = _ref_fb(rd, rs, sc, None)
+    cov = rd.slice_geom(f0["geom"], P)["cov3D"].clone()
+    cov[f0["radii"] == 0] = torch.tensor([1e-3, 0, 0, 1e-3, 0, 1e-3], device="cuda")
+    colors = torch.rand(P, 3, device="cuda")
+    f, b = _ref_fb(rd, rs, sc, grad, shs=None, scales=None, rotations=None, colors_precomp=colors, cov3D_precomp=cov)
+    o = run_ours(rs, sc, grad, colors_precomp=colors, cov3D_precomp=cov)
+    assert torch.equal(o["radii"], f["radii"])
+    assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
+    assert rel_to_max(o["extra_grads"]["colors"], b["colors"]) <= GRAD_TOL
+    assert rel_to_max(o["extra_grads"]["cov3D"], b["cov3D"]) <= GRAD_TOL
+    assert rel_to_max(o["grads"]["means3D"], b["means3D"]) <= GRAD_TOL
+    assert o["grads"]["shs"] is None and o["grads"]["scales"] is None
+
+
+def test_fused_se3_per_gaussian():
+    """Protocol of SURVEY.md 7: (i) SE3 stage vs the torch op graph within 1e-6;
+    (ii) OUR deformed means fed to the reference -> downstream bit-exact; gradients 1e-4."""
+    import synthetic
+    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    from oracle import rigid_body_port
+    rd = _ref()
+    P, W, H = 100000, 640, 360
+    sc, cam, rs = make_view_settings(P, W, H)
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    S, th = synthetic.make_twists(P, device="cuda")
+    o = run_ours(rs, sc, grad, twists=(S, th))
+    x = sc["means3D"].clone().requires_grad_(True)
+    S_, th_ = S.clone().requires_grad_(True), th.clone().requires_grad_(True)
+    y = rigid_body_port.deform_points(x, S_, th_)
+    assert float((o["deformed"] - y).abs().max()) <= 1e-6
+    yd = o["deformed"].detach()
+    f, b = _ref_fb(rd, rs, sc, grad, means=yd)
+    assert torch.equal(o["radii"], f["radii"])
+    assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
+    (y * b["means3D"]).sum().backward()
+    assert rel_to_max(o["grads"]["means3D"], x.grad) <= GRAD_TOL
+    assert rel_to_max(o["extra_grads"]["S"], S_.grad) <= GRAD_TOL
+    assert rel_to_max(o["extra_grads"]["theta"], th_.grad) <= GRAD_TOL
+    for k in ("shs", "scales", "rotations", "opacities"):
+        assert rel_to_max(o["grads"][k], b[k]) <= GRAD_TOL, k
+
+
+def test_fused_se3_rigid_bodies():
+    """64 rigid bodies (config C3): body table + body_id must equal the per-Gaussian expansion."""
+    import synthetic
+    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    P, W, H = 60000, 400, 400
+    sc, cam, rs = make_view_settings(P, W, H, scale_mult=1.5)
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    body_id, S, th = synthetic.make_bodies(sc["means3D"], frame=150, device="cuda")
+    ob = run_ours(rs, sc, grad, twists=(S, th), body_id=body_id)
+    idx = body_id.long()
+    og = run_ours(rs, sc, grad, twists=(S[idx].contiguous(), th[idx].contiguous()))
+    assert torch.equal(ob["deformed"], og["deformed"])
+    assert torch.equal(ob["radii"], og["radii"]) and torch.equal(ob["color"], og["color"])
+    dS = torch.zeros_like(S).index_add_(0, idx, og["extra_grads"]["S"])
+    dth = torch.zeros_like(th).index_add_(0, idx, og["extra_grads"]["theta"])
+    assert rel_to_max(ob["extra_grads"]["S"], dS) <= GRAD_TOL
+    assert rel_to_max(ob["extra_grads"]["theta"], dth) <= GRAD_TOL
+    assert rel_to_max(ob["grads"]["means3D"], og["grads"]["means3D"]) <= GRAD_TOL
+
+
+def test_rigid_body_module_vs_reference_golden():
+    import rigid_body
+    from _gpu_util import GOLD
+    g = torch.load(os.path.join(GOLD, "se3_golden.pt"))
+    S = g["S"].cuda().requires_grad_(True)
+    th = g["theta"].cuda().requires_grad_(True)
+    T = rigid_body.exp_se3(S, th)
+    assert T.shape == (S.shape[0], 4, 4)
+    assert float((T.detach().cpu() - g["T"]).abs().max()) <= 1e-6
+    (T * g["gT"].cuda()).sum().backward()
+    assert float((S.grad.cpu() - g["dS_T"]).abs().max()) <= 1e-4 * float(g["dS_T"].abs().max())
+    assert float((th.grad.cpu() - g["dtheta_T"]).abs().max()) <= 1e-4 * float(g["dtheta_T"].abs().max())
+    # the apply recipe composed from the drop-in helpers
+    x = g["x"].cuda()
+    y = rigid_body.from_homogenous(torch.bmm(T.detach(), rigid_body.to_homogenous(x).unsqueeze(-1)).squeeze(-1))
+    assert float((y.cpu() - g["y"]).abs().max()) <= 1e-6
+
+
+def test_mark_visible_and_knn():
+    from _gpu_util import load_golden, make_view_settings
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from oracle import oracle_c
+    from simple_knn._C import distCUDA2
+    g = load_golden()
+    sc, cam, rs = make_view_settings(50000, 64, 64)
+    vis = GaussianRasterizer(rs).markVisible(sc["means3D"])
+    assert vis.dtype == torch.bool
+    assert np.array_equal(vis.cpu().numpy(), oracle_c.mark_visible(sc["means3D"], rs.viewmatrix, rs.projmatrix))
+    d = distCUDA2(torch.from_numpy(g["knn/points"]).cuda())
+    np.testing.assert_allclose(d.cpu().numpy(), g["knn/dist2"], rtol=2e-6, atol=0)
+    from oracle import ref_driver
+    if ref_driver.available():
+        for n in (1000, 100000, 1000000):
+            pts = sc["means3D"] if n == 50000 else torch.rand(n, 3, device="cuda") * torch.tensor([2.0, 1.0, 0.3], device="cuda")
+            np.testing.assert_allclose(distCUDA2(pts).cpu().numpy(), ref_driver.dist_cuda2(pts).cpu().numpy(), rtol=2e-6, atol=0)
+        assert bool(torch.equal(vis, ref_driver.mark_visible(sc["means3D"], rs.viewmatrix, rs.projmatrix)))
+    # tiny and degenerate clouds
+    small = torch.tensor([[0.0, 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3], [5, 5, 5]], device="cuda")
+    np.testing.assert_allclose(distCUDA2(small).cpu().numpy(), oracle_c.knn_dist2(small), rtol=1e-6)
+    flat = torch.rand(3000, 3, device="cuda") * torch.tensor([1.0, 1.0, 0.0], device="cuda")
+    np.testing.assert_allclose(distCUDA2(flat).cpu().numpy(), oracle_c.knn_dist2(flat), rtol=2e-6, atol=1e-12)
+
+
+def test_edge_cases():
+    import synthetic
+    from _gpu_util import make_view_settings, run_ours
+    from diff_gaussian_rasterization import GaussianRasterizer
+    # P == 0 short-circuits (rasterize_points.cu:81,161)
+    sc, cam, rs = make_view_settings(16, 64, 48)
+    empty = {k: v[:0].contiguous() for k, v in sc.items()}
+    color, radii = GaussianRasterizer(rs)(means3D=empty["means3D"], means2D=torch.zeros(0, 3, device="cuda"),
+                                          opacities=empty["opacities"], shs=empty["shs"], scales=empty["scales"],
+                                          rotations=empty["rotations"])
+    assert radii.numel() == 0 and color.shape == (3, 48, 64)
+    assert torch.allclose(color, rs.bg.view(3, 1, 1).expand(3, 48, 64))
+    # everything behind the camera: R == 0, image == background, zero gradients
+    behind = dict(sc)
+    behind["means3D"] = sc["means3D"] + torch.tensor([0.0, 0.0, -20.0], device="cuda")
+    grad = synthetic.make_image_grad(64, 48, device="cuda")
+    o = run_ours(rs, behind, grad)
+    assert int((o["radii"] > 0).sum()) == 0
+    assert torch.allclose(o["color"], rs.bg.view(3, 1, 1).expand(3, 48, 64))
+    assert all(float(g.abs().max()) == 0.0 for g in o["grads"].values())
+    # one huge Gaussian covering every tile, and an opacity-0 one in front of it
+    one = dict(means3D=torch.tensor([[0.0, 0, 0], [0.0, 0, -1.0]], device="cuda"), scales=torch.tensor([[3.0, 3, 3], [0.2, 0.2, 0.2]], device="cuda"),
+               rotations=torch.tensor([[1.0, 0, 0, 0], [1.0, 0, 0, 0]], device="cuda"), opacities=torch.tensor([[0.9], [0.0]], device="cuda"),
+               shs=torch.zeros(2, 16, 3, device="cuda"))
+    o = run_ours(rs, one, grad)
+    assert int(o["radii"][0]) > 64 and torch.isfinite(o["color"]).all()
+    from oracle import oracle_c
+    f = oracle_c.forward(rs, one["means3D"], one["opacities"], shs=one["shs"], scales=one["scales"], rotations=one["rotations"])
+    assert float(np.abs(o["color"].cpu().numpy() - f["color"]).max()) <= IMG_TOL
+    # non-contiguous inputs (the reference .contiguous()-es everything)
+    sc2, cam2, rs2 = make_view_settings(5000, 96, 80, scale_mult=2.0)
+    nc = dict(sc2)
+    nc["means3D"] = sc2["means3D"].t().contiguous().t()
+    nc["shs"] = sc2["shs"].permute(1, 0, 2).contiguous().permute(1, 0, 2)
+    a = run_ours(rs2, sc2, None)
+    b = run_ours(rs2, nc, None)
+    assert torch.equal(a["color"], b["color"])
+    # forward is deterministic
+    assert torch.equal(a["color"], run_ours(rs2, sc2, None)["color"])
+
+
+def test_sort_pairs_is_a_stable_sort():
+    from _gpu_util import sort_pairs
+    g = torch.Generator().manual_seed(0)
+    for n, bits, kind in ((0, 45, "rand"), (1, 45, "rand"), (4095, 45, "rand"), (4097, 47, "rand"), (100003, 45, "dups"),
+                          (1 << 20, 13, "rand"), (3000017, 44, "tile"), (1 << 20, 64, "rand")):
+        if kind == "dups":
+            keys = torch.randint(0, 50, (n,), generator=g, dtype=torch.int64) << 20
+        elif kind == "tile":
+            keys = (torch.randint(0, 8160, (n,), generator=g, dtype=torch.int64) << 32) | \
+                (torch.rand((n,), generator=g) * 5 + 0.2).view(torch.int32).to(torch.int64)
+        else:
+            keys = torch.randint(-2 ** 63, 2 ** 63 - 1, (n,), generator=g, dtype=torch.int64)
+        keys = keys.cuda()
+        vals = torch.arange(n, dtype=torch.int32, device="cuda")
+        ks, vs = sort_pairs(keys, vals, 0, bits)
+        if bits == 64:
+            order = torch.sort(keys ^ (-2 ** 63), stable=True).indices        # unsigned order
+        else:
+            order = torch.sort(keys & ((1 << bits) - 1), stable=True).indices
+        assert torch.equal(ks, keys[order]) and torch.equal(vs.long(), order), (n, bits, kind)
+
+
+def test_full_size_properties_c2():
+    """BASELINE configs[1] size: properties that need no oracle."""
+    from _gpu_util import intermediates, make_view_settings
+    import gsr_runtime as rt
+    P, W, H = 1000000, 1920, 1080
+    sc, cam, rs = make_view_settings(P, W, H, bg=(0, 0, 0))
+    n0 = rt.launch_count()
+    m = intermediates(rs, sc)
+    assert rt.launch_count() - n0 >= 13               # the kernels ran from libgsr_b200.so
+    R = m["R"]
+    assert R == int(m["tiles_touched"].long().sum()) and int(m["point_offsets"][-1]) == R
+    k = m["keys_sorted"] & ((1 << 45) - 1)
+    assert bool((k[1:] >= k[:-1]).all())                                   # sorted
+    assert int(torch.bincount(m["point_list"].long(), minlength=P).sum()) == R
+    assert torch.equal(torch.bincount(m["point_list"].long(), minlength=P).int(), m["tiles_touched"])  # a permutation of the duplicates
+    tile = (m["keys_sorted"] >> 32)
+    rg = m["ranges"].long()
+    cnt = torch.bincount(tile, minlength=rg.shape[0])
+    assert torch.equal(rg[:, 1] - rg[:, 0], cnt)                            # ranges partition the list by tile
+    nz = cnt > 0
+    assert bool((tile[rg[nz, 0]] == torch.nonzero(nz).flatten()).all())
+    assert torch.isfinite(m["color"]).all() and float(m["final_T"].min()) >= 0.0 and float(m["final_T"].max()) <= 1.0

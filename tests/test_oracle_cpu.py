@@ -1,0 +1,125 @@
+"""Pin the CPU oracle (oracle/gsr_oracle.c, oracle/rigid_body_port.py) against golden
+vectors produced by the REFERENCE itself:
+  tests/golden/raster_golden.npz  <- reference CUDA rasterizer + simple-knn run on a B200
+                                     (tests/golden/make_raster_golden.py)
+  tests/golden/se3_golden.pt      <- reference scene/rigid_body.py (tests/golden/make_se3_golden.py)
+No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_c, rigid_body_port
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "raster_golden.npz"))
+
+
+class _RS:
+    pass
+
+
+def _settings(g, case):
+    P, W, H, deg, R = [int(x) for x in g[case + "/cfg"]]
+    rs = _RS()
+    rs.image_width, rs.image_height, rs.sh_degree = W, H, deg
+    rs.tanfovx, rs.tanfovy = [float(x) for x in g[case + "/tanfov"]]
+    rs.scale_modifier = float(g[case + "/scale_modifier"][0])
+    rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos = (g[case + "/" + k] for k in ("bg", "viewmatrix", "projmatrix", "campos"))
+    return rs, P, W, H, R
+
+
+def _inputs(g, case):
+    kw = {}
+    for k in ("shs", "scales", "rotations", "colors_precomp", "cov3D_precomp"):
+        if case + "/" + k in g.files:
+            kw[k] = g[case + "/" + k]
+    return kw
+
+
+def _run(g, case):
+    rs, P, W, H, R = _settings(g, case)
+    return rs, oracle_c.forward(rs, g[case + "/means3D"], g[case + "/opacities"], **_inputs(g, case)), R
+
+
+@pytest.mark.parametrize("case", ["sh3", "sh1", "precomp"])
+def test_oracle_forward_matches_reference(gold, case):
+    g = gold
+    rs, f, R = _run(g, case)
+    vis = g[case + "/radii"] > 0
+    # integer / bit work: exact
+    assert f["num_rendered"] == R
+    np.testing.assert_array_equal(f["radii"], g[case + "/radii"])
+    np.testing.assert_array_equal(f["tiles_touched"].astype(np.int64), g[case + "/tiles_touched"].astype(np.int64))
+    np.testing.assert_array_equal(f["keys_sorted"].view(np.int64), g[case + "/keys_sorted"])
+    np.testing.assert_array_equal(f["point_list"].astype(np.int64), g[case + "/point_list"].astype(np.int64))
+    np.testing.assert_array_equal(f["ranges"].astype(np.int64), g[case + "/ranges"].astype(np.int64))
+    # the geometry chain reproduces the reference's roundings: bit-exact floats
+    for k in ("depths", "means2D", "conic_opacity"):
+        a = f[k][vis].view(np.int32)
+        b = g[case + "/" + k][vis].view(np.int32)
+        assert (a == b).all(), k
+    if case != "precomp":
+        assert (f["cov3D"][vis].view(np.int32) == g[case + "/cov3D"][vis].view(np.int32)).all()
+        np.testing.assert_allclose(f["rgb"][vis], g[case + "/rgb"][vis], rtol=0, atol=2e-6)
+        np.testing.assert_array_equal(f["clamped"][vis].astype(bool), g[case + "/clamped"][vis].astype(bool))
+    # blending uses the host libm's expf: tolerance, not bit-exact
+    np.testing.assert_allclose(f["color"], g[case + "/color"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(f["final_T"], g[case + "/final_T"], rtol=0, atol=1e-6)
+    mism = (f["n_contrib"].astype(np.int64) != g[case + "/n_contrib"].astype(np.int64)).mean()
+    assert mism < 1e-3, "n_contrib mismatch fraction %g" % mism
+
+
+@pytest.mark.parametrize("case", ["sh3", "sh1", "precomp"])
+def test_oracle_backward_matches_reference(gold, case):
+    g = gold
+    rs, f, R = _run(g, case)
+    b = oracle_c.backward(f, g[case + "/grad_image"])
+    names = ["means2D", "opacities", "means3D"]
+    if case == "precomp":
+        names += ["colors", "cov3D"]
+    else:
+        names += ["shs", "scales", "rotations"]
+    for k in names:
+        ref = g[case + "/grad_" + k].reshape(b[k].shape)
+        scale = max(float(np.abs(ref).max()), 1e-12)
+        err = float(np.abs(b[k] - ref).max()) / scale
+        assert err < 1e-4, "%s: relative-to-max error %g" % (k, err)
+
+
+def test_oracle_mark_visible_and_msb(gold):
+    g = gold
+    got = oracle_c.mark_visible(g["sh3/means3D"], g["sh3/viewmatrix"], g["sh3/projmatrix"])
+    np.testing.assert_array_equal(got, g["sh3/mark_visible"].astype(bool))
+    # rasterizer_impl.cu:35-50 at the tile counts of the benchmark configs
+    assert [oracle_c.higher_msb(n) for n in (8160, 2500, 32400)] == [13, 12, 15]
+
+
+def test_oracle_knn_matches_reference(gold):
+    got = oracle_c.knn_dist2(gold["knn/points"])
+    np.testing.assert_allclose(got, gold["knn/dist2"], rtol=2e-6, atol=0)
+    assert got[10] < got.mean()           # the duplicated point has a zero nearest distance
+
+
+def test_rigid_body_port_matches_reference_golden():
+    g = torch.load(os.path.join(GOLD, "se3_golden.pt"))
+    S = g["S"].clone().requires_grad_(True)
+    th = g["theta"].clone().requires_grad_(True)
+    x = g["x"].clone().requires_grad_(True)
+    T = rigid_body_port.exp_se3(S, th)
+    y = rigid_body_port.from_homogenous(torch.bmm(T, rigid_body_port.to_homogenous(x).unsqueeze(-1)).squeeze(-1))
+    (y * g["gy"]).sum().backward()
+    # same torch build as the generator -> bit-exact; allow an ulp across builds
+    for name, got in (("T", T), ("y", y), ("dS", S.grad), ("dtheta", th.grad), ("dx", x.grad)):
+        torch.testing.assert_close(got.detach(), g[name], rtol=1e-6, atol=1e-6, msg=name)
+    torch.testing.assert_close(rigid_body_port.skew(g["S"][:, :3]), g["skew"], rtol=0, atol=0)
+    torch.testing.assert_close(rigid_body_port.exp_so3(g["S"][:, :3], g["theta"]), g["exp_so3"], rtol=1e-6, atol=1e-6)
+    # bottom row / rotation sanity of the SE3 matrices
+    assert torch.equal(T[:, 3].detach(), torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(T.shape[0], 4))
+    R = T[:, :3, :3].detach()
+    torch.testing.assert_close(torch.bmm(R, R.transpose(1, 2)), torch.eye(3).expand_as(R), rtol=0, atol=1e-5)

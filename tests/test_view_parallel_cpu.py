@@ -1,0 +1,98 @@
+"""World-size-2 (gloo, CPU) test of the view-parallel path: each rank renders its share
+of the cameras (with the CPU oracle standing in for the GPU kernels), gradients are
+summed through ONE flat all-reduce, and the result must equal the single-process sum
+over all cameras."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import synthetic
+import view_parallel as vp
+from oracle import oracle_c
+
+P, W, H, NVIEWS = 300, 48, 32, 4
+KEYS = ("means3D", "scales", "rotations", "opacities", "shs")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _view_grads(sc, k):
+    cam = synthetic.make_camera(k, NVIEWS, W, H)
+    rs = synthetic.raster_settings(cam, torch.tensor([0.1, 0.0, 0.2]))
+    f = oracle_c.forward(rs, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+    b = oracle_c.backward(f, synthetic.make_image_grad(W, H, seed=1))
+    loss = float((f["color"] * synthetic.make_image_grad(W, H, seed=1).numpy()).sum())
+    return {k2: torch.from_numpy(np.ascontiguousarray(b[k2])) for k2 in KEYS}, loss, f["radii"]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = synthetic.make_scene(P, seed=0, scale_mult=3.0)
+    params = [sc[k].clone().requires_grad_(True) for k in KEYS]
+    buf = vp.FlatGradBuffer(params)
+    views = vp.partition_views(NVIEWS, world, rank)
+    stats = dict(accum=torch.zeros(P, 1), denom=torch.zeros(P, 1), radii=torch.zeros(P))
+
+    def render_view(i):
+        grads, loss, radii = _view_grads(sc, i)
+        for p, k in zip(params, KEYS):
+            p.grad += grads[k].view_as(p)                 # what autograd's AccumulateGrad does
+        vis = torch.from_numpy(radii > 0)
+        stats["accum"][vis] += 1.0
+        stats["denom"][vis] += 1.0
+        stats["radii"] = torch.maximum(stats["radii"], torch.from_numpy(radii).float())
+        return torch.tensor(loss)
+
+    total = vp.render_step(render_view, views, buf)
+    dist.all_reduce(total)
+    vp.reduce_densification_stats(stats["accum"], stats["denom"], stats["radii"])
+    # every .grad is still a view into the flat buffer (no pack/unpack)
+    assert all(p.grad.data_ptr() >= buf.flat.data_ptr() for p in params)
+    torch.save(dict(flat=buf.flat.clone(), loss=total, views=views, stats=stats), os.path.join(out_dir, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_partition_covers_all_views_once():
+    for n, w in ((64, 8), (7, 2), (3, 4), (0, 2)):
+        parts = [vp.partition_views(n, w, r) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_two_rank_allreduce_equals_single_process_sum(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "r0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "r1.pt"))
+    assert r0["views"] == [0, 2] and r1["views"] == [1, 3]
+    # replicas agree bit for bit after the collective
+    assert torch.equal(r0["flat"], r1["flat"]) and torch.equal(r0["loss"], r1["loss"])
+    assert all(torch.equal(r0["stats"][k], r1["stats"][k]) for k in r0["stats"])
+    # and equal the single-process accumulation over all four views
+    sc = synthetic.make_scene(P, seed=0, scale_mult=3.0)
+    ref = {k: torch.zeros_like(sc[k]) for k in KEYS}
+    loss = 0.0
+    seen = torch.zeros(P)
+    for k in range(NVIEWS):
+        g, l, radii = _view_grads(sc, k)
+        for kk in KEYS:
+            ref[kk] += g[kk].view_as(ref[kk])
+        loss += l
+        seen += torch.from_numpy(radii > 0).float()
+    flat_ref = torch.cat([ref[k].reshape(-1) for k in KEYS])
+    assert flat_ref.numel() == P * 59                    # 59 floats (236 B) per Gaussian
+    torch.testing.assert_close(r0["flat"], flat_ref, rtol=1e-5, atol=1e-5 * float(flat_ref.abs().max()))
+    assert abs(float(r0["loss"]) - loss) <= 1e-4 * abs(loss)
+    assert torch.equal(r0["stats"]["denom"].reshape(-1), seen)
