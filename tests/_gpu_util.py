@@ -29,7 +29,7 @@ def make_view_settings(P, W, H, k=0, K=1, bg=(0.1, 0.2, 0.3), seed=0, scale_mult
     dev = "cuda"
     sc = synthetic.make_scene(P, seed=seed, device=dev, scale_mult=scale_mult)
     cam = synthetic.make_camera(k, K, W, H, device=dev)
-    rs = synthetic.raster_settings(cam, torch.tensor(bg, device=dev), sh_degree=sh_degree, scale_modifier=scale_modifier)
+    rs = synthetic.raster_settings(cam, torch.tensor(bg, device=dev, dtype=torch.float32), sh_degree=sh_degree, scale_modifier=scale_modifier)
     return sc, cam, rs
 
 
