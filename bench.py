@@ -306,10 +306,12 @@ def main():
         alg = {  # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x units per launch; R = last view's)
             "preprocess_fwd": 316.0 * args.P,
             "preprocess_bwd": 572.0 * args.P,
-            "duplicate_with_keys": 12.0 * R + 20.0 * args.P,
-            "sort_histogram": 8.0 * R,
-            "sort_onesweep_pass": 24.0 * R,
-            "tile_ranges": 8.0 * R + 8.0 * tiles,
+            "duplicate_with_keys": 8.0 * R + 28.0 * args.P,
+            "depth_sort_histogram": 4.0 * args.P,          # depth order of the Gaussians: (u32 key, u32 id), 4 passes
+            "depth_sort_onesweep_pass": 16.0 * args.P,
+            "tile_sort_histogram": 4.0 * R,                # duplicates by tile id: (u32 tile, u32 id), 2 passes
+            "tile_sort_onesweep_pass": 16.0 * R,
+            "tile_ranges": 4.0 * R + 8.0 * tiles,
         }
         kernels = {}
         for name, (cnt, tot) in prof.items():

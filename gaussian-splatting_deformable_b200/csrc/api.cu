@@ -69,7 +69,11 @@ namespace {
 
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct GeomLayout { size_t depths, tiles, recs, clamped, offsets, cov3d, block_sums, total, bytes; };
+struct GeomLayout {
+    // the depth sort is 4 passes (even): its result lands back in the "a" buffers
+    size_t in_b_order() const { return dvals_a; }
+    size_t depths, tiles, recs, clamped, cov3d, block_sums, total, dkeys_a, dkeys_b, dvals_a, dvals_b,
+                    dsort_temp, dsort_temp_bytes, sblock_sums, bytes; };
 GeomLayout geom_layout(int P) {
     GeomLayout L{};
     size_t o = 0;
@@ -78,10 +82,15 @@ GeomLayout geom_layout(int P) {
     L.tiles = o; o += al(4 * p);
     L.recs = o; o += al(48 * p);
     L.clamped = o; o += al(p);
-    L.offsets = o; o += al(4 * p);
     L.cov3d = o; o += al(24 * p);
     L.block_sums = o; o += al(4 * ((p + 255) / 256 + 1));
     L.total = o; o += 256;
+    L.dkeys_a = o; o += al(4 * p);
+    L.dkeys_b = o; o += al(4 * p);
+    L.dvals_a = o; o += al(4 * p);
+    L.dvals_b = o; o += al(4 * p);
+    L.dsort_temp = o; L.dsort_temp_bytes = gsr_sort_temp_bytes((uint32_t)p, 0, 32); o += al(L.dsort_temp_bytes);
+    L.sblock_sums = o; o += al(4 * ((p + 255) / 256 + 1));
     L.bytes = o;
     return L;
 }
@@ -107,18 +116,19 @@ int tile_bits(uint32_t n) {
     if (n >> msb) msb++;
     return msb;
 }
-struct BinLayout { size_t keys_a, keys_b, vals_a, vals_b, sort_temp, sort_temp_bytes, bytes; int end_bit; int passes; };
+struct BinLayout { size_t tkeys_a, tkeys_b, vals_a, vals_b, sort_temp, sort_temp_bytes, keys64, bytes; int tile_bits; int passes; };
 BinLayout bin_layout(uint32_t R, int W, int H) {
     BinLayout L{};
     const uint32_t tiles = (uint32_t)((W + 15) / 16) * ((H + 15) / 16);
-    L.end_bit = 32 + tile_bits(tiles);
-    L.passes = (L.end_bit + 7) / 8;
+    L.tile_bits = tile_bits(tiles);
+    L.passes = (L.tile_bits + 7) / 8;
     size_t o = 0;
-    L.keys_a = o; o += al(8 * (size_t)R);
-    L.keys_b = o; o += al(8 * (size_t)R);
+    L.tkeys_a = o; o += al(4 * (size_t)R);
+    L.tkeys_b = o; o += al(4 * (size_t)R);
     L.vals_a = o; o += al(4 * (size_t)R);
     L.vals_b = o; o += al(4 * (size_t)R);
-    L.sort_temp = o; L.sort_temp_bytes = gsr_sort_temp_bytes(R, 0, L.end_bit); o += al(L.sort_temp_bytes);
+    L.sort_temp = o; L.sort_temp_bytes = gsr_sort_temp_bytes(R, 0, L.tile_bits); o += al(L.sort_temp_bytes);
+    L.keys64 = o; o += al(8 * (size_t)R);          // reference-format keys, filled on request only
     L.bytes = o + 256;
     return L;
 }
@@ -179,7 +189,7 @@ size_t gsr_grad_bytes(int P) { return al(48 * (size_t)(P > 0 ? P : 0)) + 256; }
 
 void gsr_geom_layout(int P, size_t out[6]) {
     const GeomLayout L = geom_layout(P);
-    out[0] = L.depths; out[1] = L.tiles; out[2] = L.recs; out[3] = L.clamped; out[4] = L.offsets; out[5] = L.cov3d;
+    out[0] = L.depths; out[1] = L.tiles; out[2] = L.recs; out[3] = L.clamped; out[4] = L.in_b_order(); out[5] = L.cov3d;
 }
 void gsr_image_layout(int W, int H, size_t out[3]) {
     const ImageLayout L = image_layout(W, H);
@@ -188,10 +198,10 @@ void gsr_image_layout(int W, int H, size_t out[3]) {
 void gsr_binning_layout(uint32_t R, int W, int H, size_t out[4]) {
     const BinLayout L = bin_layout(R, W, H);
     const bool in_b = (L.passes & 1) != 0;
-    out[0] = in_b ? L.keys_b : L.keys_a;
+    out[0] = L.keys64;
     out[1] = in_b ? L.vals_b : L.vals_a;
-    out[2] = in_b ? L.keys_a : L.keys_b;   // where the unsorted input was (overwritten by ping-pong if passes > 1)
-    out[3] = in_b ? L.vals_a : L.vals_b;
+    out[2] = in_b ? L.tkeys_b : L.tkeys_a;
+    out[3] = in_b ? L.tkeys_a : L.tkeys_b;
 }
 
 int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* means3D, const float* scales,
@@ -233,6 +243,12 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* mean
     a.clamped = reinterpret_cast<uint8_t*>(ws + L.clamped);
     a.cov3D_out = debug_dump_cov3D ? reinterpret_cast<float*>(ws + L.cov3d) : nullptr;
     a.block_sums = reinterpret_cast<uint32_t*>(ws + L.block_sums);
+    a.depth_keys = reinterpret_cast<uint32_t*>(ws + L.dkeys_a);
+    a.depth_vals = reinterpret_cast<uint32_t*>(ws + L.dvals_a);
+    // the depth sort's state (histograms, tickets, look-back words) is zeroed here because the
+    // preprocess kernel accumulates the digit histograms of its depth keys
+    a.depth_hist = reinterpret_cast<uint32_t*>(ws + L.dsort_temp);
+    GSR_CHECK(cudaMemsetAsync(ws + L.dsort_temp, 0, L.dsort_temp_bytes, stream));
     if (int rc = gsr_launch_preprocess_fwd(a, v, stream)) return rc;
     uint32_t* d_total = reinterpret_cast<uint32_t*>(ws + L.total);
     if (int rc = gsr_launch_scan_block_sums(a.block_sums, gsr_div_up(P, 256), d_total, stream)) return rc;
@@ -242,7 +258,7 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* mean
 }
 
 int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* radii, void* geom_ws, void* binning_ws,
-                       size_t binning_bytes, void* image_ws, float* out_color, void* stream_) {
+                       size_t binning_bytes, void* image_ws, float* out_color, int materialize_keys, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GsrView v;
     if (int rc = fill_view(view, 0, v)) return rc;
@@ -262,23 +278,44 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
         char* gw = reinterpret_cast<char*>(geom_ws);
         char* bw = reinterpret_cast<char*>(binning_ws);
         recs = reinterpret_cast<const float4*>(gw + L.recs);
-        uint64_t* keys_a = reinterpret_cast<uint64_t*>(bw + BL.keys_a);
-        uint64_t* keys_b = reinterpret_cast<uint64_t*>(bw + BL.keys_b);
+        const uint32_t* tiles_touched = reinterpret_cast<const uint32_t*>(gw + L.tiles);
+        // 1. Gaussians in depth order (stable; emit-nothing Gaussians sink to the end)
+        uint32_t* dkeys_a = reinterpret_cast<uint32_t*>(gw + L.dkeys_a);
+        uint32_t* dkeys_b = reinterpret_cast<uint32_t*>(gw + L.dkeys_b);
+        uint32_t* dvals_a = reinterpret_cast<uint32_t*>(gw + L.dvals_a);
+        uint32_t* dvals_b = reinterpret_cast<uint32_t*>(gw + L.dvals_b);
+        int d_in_b = 0;
+        if (int rc = gsr_launch_sort_pairs32(dkeys_a, dkeys_b, dvals_a, dvals_b, (uint32_t)P, 0, 32, gw + L.dsort_temp,
+                                             L.dsort_temp_bytes, &d_in_b, stream, 1, true))
+            return rc;
+        const uint32_t* order = d_in_b ? dvals_b : dvals_a;
+        // 2. offsets in that order, then the duplicates (tile id, Gaussian id)
+        uint32_t* sblock = reinterpret_cast<uint32_t*>(gw + L.sblock_sums);
+        uint32_t* d_total = reinterpret_cast<uint32_t*>(gw + L.total) + 1;
+        if (int rc = gsr_launch_sorted_block_sums(P, order, tiles_touched, sblock, stream)) return rc;
+        if (int rc = gsr_launch_scan_block_sums(sblock, gsr_div_up(P, 256), d_total, stream)) return rc;
+        uint32_t* tkeys_a = reinterpret_cast<uint32_t*>(bw + BL.tkeys_a);
+        uint32_t* tkeys_b = reinterpret_cast<uint32_t*>(bw + BL.tkeys_b);
         uint32_t* vals_a = reinterpret_cast<uint32_t*>(bw + BL.vals_a);
         uint32_t* vals_b = reinterpret_cast<uint32_t*>(bw + BL.vals_b);
-        if (int rc = gsr_launch_duplicate(P, radii, reinterpret_cast<const float*>(gw + L.depths),
-                                          reinterpret_cast<const uint32_t*>(gw + L.tiles), recs,
-                                          reinterpret_cast<const uint32_t*>(gw + L.block_sums),
-                                          reinterpret_cast<uint32_t*>(gw + L.offsets), keys_a, vals_a, v.grid_x, v.grid_y,
-                                          stream))
+        const GsrSortPlan tplan = gsr_make_sort_plan(0, BL.tile_bits);
+        GSR_CHECK(cudaMemsetAsync(bw + BL.sort_temp, 0, BL.sort_temp_bytes, stream));
+        if (int rc = gsr_launch_duplicate(P, order, radii, tiles_touched, recs, sblock, tkeys_a, vals_a, v.grid_x,
+                                          v.grid_y, tplan, reinterpret_cast<uint32_t*>(bw + BL.sort_temp), stream))
             return rc;
+        // 3. stable sort by tile id only
         int in_b = 0;
-        if (int rc = gsr_launch_sort_pairs(keys_a, keys_b, vals_a, vals_b, R, 0, BL.end_bit, bw + BL.sort_temp,
-                                           BL.sort_temp_bytes, &in_b, stream))
+        if (int rc = gsr_launch_sort_pairs32(tkeys_a, tkeys_b, vals_a, vals_b, R, 0, BL.tile_bits, bw + BL.sort_temp,
+                                             BL.sort_temp_bytes, &in_b, stream, 2, true))
             return rc;
-        const uint64_t* sorted_keys = in_b ? keys_b : keys_a;
+        const uint32_t* sorted_tiles = in_b ? tkeys_b : tkeys_a;
         point_list = in_b ? vals_b : vals_a;
-        if (int rc = gsr_launch_tile_ranges(R, sorted_keys, ranges, num_tiles, stream)) return rc;
+        if (int rc = gsr_launch_tile_ranges(R, sorted_tiles, ranges, num_tiles, stream)) return rc;
+        if (materialize_keys)
+            if (int rc = gsr_launch_materialize_keys(R, sorted_tiles, point_list,
+                                                     reinterpret_cast<const float*>(gw + L.depths),
+                                                     reinterpret_cast<uint64_t*>(bw + BL.keys64), stream))
+                return rc;
     } else {
         GSR_CHECK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
     }
@@ -404,6 +441,13 @@ int gsr_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_
     int dummy = 0;
     return gsr_launch_sort_pairs(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
                                  result_in_b ? result_in_b : &dummy, (cudaStream_t)stream_);
+}
+
+int gsr_sort_pairs32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n, int begin_bit,
+                     int end_bit, void* temp, size_t temp_bytes, int* result_in_b, void* stream_) {
+    int dummy = 0;
+    return gsr_launch_sort_pairs32(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
+                                   result_in_b ? result_in_b : &dummy, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

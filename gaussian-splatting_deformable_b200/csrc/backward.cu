@@ -150,43 +150,51 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                 V3 dRGB = {(cl & 1) ? 0.0f : g1.z, (cl & 2) ? 0.0f : g1.w, (cl & 4) ? 0.0f : g2x};
                 const float* shp = a.shs + (size_t)idx * M * 3;
                 float* dsh = a.dL_dsh + (size_t)idx * M * 3;
-                auto sh = [&](int k) -> V3 { return {shp[3 * k], shp[3 * k + 1], shp[3 * k + 2]}; };
+                const int deg = v.sh_degree;
+                // The 192-byte SH record as 12 x LDG.128 (M == 16), straight into registers.
+                float shv[48];
+                if (M == 16) {
+                    const float4* b4 = reinterpret_cast<const float4*>(shp);
+                    const int need = (deg + 1) * (deg + 1) * 3;
+#pragma unroll
+                    for (int k = 0; k < 12; k++) {
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (4 * k < need) t4 = __ldg(b4 + k);
+                        shv[4 * k] = t4.x; shv[4 * k + 1] = t4.y; shv[4 * k + 2] = t4.z; shv[4 * k + 3] = t4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 48; k++) shv[k] = (k < M * 3) ? shp[k] : 0.0f;
+                }
+                auto sh = [&](int k) -> V3 { return {shv[3 * k], shv[3 * k + 1], shv[3 * k + 2]}; };
                 V3 dir_orig = {mean.x - v.campos[0], mean.y - v.campos[1], mean.z - v.campos[2]};
                 const float len = sqrtf(dot(dir_orig, dir_orig));
                 const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
                 V3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
-                const int deg = v.sh_degree;
-                store_sh(dsh, 0, bSH_C0 * dRGB);
-                int written = 1;
+                // dRGB/dsh_k is a scalar per coefficient: dL_dsh[k] = coef[k] * dL_dRGB
+                float coef[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) coef[k] = 0.0f;
+                coef[0] = bSH_C0;
                 if (deg > 0) {
-                    store_sh(dsh, 1, (-bSH_C1 * y) * dRGB);
-                    store_sh(dsh, 2, (bSH_C1 * z) * dRGB);
-                    store_sh(dsh, 3, (-bSH_C1 * x) * dRGB);
-                    written = 4;
+                    coef[1] = -bSH_C1 * y; coef[2] = bSH_C1 * z; coef[3] = -bSH_C1 * x;
                     dRGBdx = (-bSH_C1) * sh(3);
                     dRGBdy = (-bSH_C1) * sh(1);
                     dRGBdz = bSH_C1 * sh(2);
                     if (deg > 1) {
                         const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                        store_sh(dsh, 4, (bSH_C2[0] * xy) * dRGB);
-                        store_sh(dsh, 5, (bSH_C2[1] * yz) * dRGB);
-                        store_sh(dsh, 6, (bSH_C2[2] * (2.f * zz - xx - yy)) * dRGB);
-                        store_sh(dsh, 7, (bSH_C2[3] * xz) * dRGB);
-                        store_sh(dsh, 8, (bSH_C2[4] * (xx - yy)) * dRGB);
-                        written = 9;
+                        coef[4] = bSH_C2[0] * xy; coef[5] = bSH_C2[1] * yz; coef[6] = bSH_C2[2] * (2.f * zz - xx - yy);
+                        coef[7] = bSH_C2[3] * xz; coef[8] = bSH_C2[4] * (xx - yy);
                         const V3 s4 = sh(4), s5 = sh(5), s6 = sh(6), s7 = sh(7), s8 = sh(8);
                         dRGBdx = dRGBdx + (bSH_C2[0] * y) * s4 + (bSH_C2[2] * 2.f * -x) * s6 + (bSH_C2[3] * z) * s7 + (bSH_C2[4] * 2.f * x) * s8;
                         dRGBdy = dRGBdy + (bSH_C2[0] * x) * s4 + (bSH_C2[1] * z) * s5 + (bSH_C2[2] * 2.f * -y) * s6 + (bSH_C2[4] * 2.f * -y) * s8;
                         dRGBdz = dRGBdz + (bSH_C2[1] * y) * s5 + (bSH_C2[2] * 2.f * 2.f * z) * s6 + (bSH_C2[3] * x) * s7;
                         if (deg > 2) {
-                            store_sh(dsh, 9, (bSH_C3[0] * y * (3.f * xx - yy)) * dRGB);
-                            store_sh(dsh, 10, (bSH_C3[1] * xy * z) * dRGB);
-                            store_sh(dsh, 11, (bSH_C3[2] * y * (4.f * zz - xx - yy)) * dRGB);
-                            store_sh(dsh, 12, (bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dRGB);
-                            store_sh(dsh, 13, (bSH_C3[4] * x * (4.f * zz - xx - yy)) * dRGB);
-                            store_sh(dsh, 14, (bSH_C3[5] * z * (xx - yy)) * dRGB);
-                            store_sh(dsh, 15, (bSH_C3[6] * x * (xx - 3.f * yy)) * dRGB);
-                            written = 16;
+                            coef[9] = bSH_C3[0] * y * (3.f * xx - yy); coef[10] = bSH_C3[1] * xy * z;
+                            coef[11] = bSH_C3[2] * y * (4.f * zz - xx - yy);
+                            coef[12] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                            coef[13] = bSH_C3[4] * x * (4.f * zz - xx - yy); coef[14] = bSH_C3[5] * z * (xx - yy);
+                            coef[15] = bSH_C3[6] * x * (xx - 3.f * yy);
                             const V3 s9 = sh(9), s10 = sh(10), s11 = sh(11), s12 = sh(12), s13 = sh(13), s14 = sh(14), s15 = sh(15);
                             dRGBdx = dRGBdx + (bSH_C3[0] * 3.f * 2.f * xy) * s9 + (bSH_C3[1] * yz) * s10 + (bSH_C3[2] * -2.f * xy) * s11 +
                                      (bSH_C3[3] * -3.f * 2.f * xz) * s12 + (bSH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * s13 +
@@ -200,7 +208,22 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                         }
                     }
                 }
-                for (int k = written; k < M; k++) store_sh(dsh, k, V3{0, 0, 0});
+                // dL_dsh record: 48 floats as 12 x STG.128 (element e of the record = coef[e/3] * dRGB[e%3])
+                const float dr[3] = {dRGB.x, dRGB.y, dRGB.z};
+                if (M == 16) {
+                    float4* d4 = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+                    for (int k = 0; k < 12; k++) {
+                        float4 o;
+                        o.x = coef[(4 * k) / 3] * dr[(4 * k) % 3];
+                        o.y = coef[(4 * k + 1) / 3] * dr[(4 * k + 1) % 3];
+                        o.z = coef[(4 * k + 2) / 3] * dr[(4 * k + 2) % 3];
+                        o.w = coef[(4 * k + 3) / 3] * dr[(4 * k + 3) % 3];
+                        d4[k] = o;
+                    }
+                } else {
+                    for (int e = 0; e < M * 3; e++) dsh[e] = coef[e / 3] * dr[e % 3];
+                }
                 const V3 dL_ddir = {dot(dRGBdx, dRGB), dot(dRGBdy, dRGB), dot(dRGBdz, dRGB)};
                 const V3 dmean_sh = dnormvdv(dir_orig, dL_ddir);
                 gm[0] += dmean_sh.x; gm[1] += dmean_sh.y; gm[2] += dmean_sh.z;
@@ -251,7 +274,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
             }
         } else if (a.dL_dsh) {
             float* dsh = a.dL_dsh + (size_t)idx * M * 3;
-            for (int k = 0; k < M * 3; k++) dsh[k] = 0.0f;
+            if (M == 16) {
+                float4* d4 = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+                for (int k = 0; k < 12; k++) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int k = 0; k < M * 3; k++) dsh[k] = 0.0f;
+            }
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];

@@ -3,6 +3,17 @@
 #pragma once
 #include "common.cuh"
 
+// Digit plan of a sort on bits [begin_bit, end_bit): ceil(bits/8) passes, bits split evenly.
+// The temp buffer starts with the digit histograms: u32 hist[pass][256].
+#define GSR_SORT_MAX_PASSES 8
+#define GSR_SORT_RADIX 256
+struct GsrSortPlan {
+    int passes;
+    int shift[GSR_SORT_MAX_PASSES];
+    uint32_t mask[GSR_SORT_MAX_PASSES];
+};
+GsrSortPlan gsr_make_sort_plan(int begin_bit, int end_bit);
+
 struct PreprocessArgs {
     int P;
     const float* means;          // [P,3] un-deformed
@@ -24,6 +35,9 @@ struct PreprocessArgs {
     uint8_t* clamped;            // [P] bit c set when colour channel c was clamped at 0
     float* cov3D_out;            // [P,6] or null (parity dumps)
     uint32_t* block_sums;        // [ceil(P/256)] sum of tiles_touched per 256-Gaussian block
+    uint32_t* depth_keys;        // [P] float bits of the view depth (0xffffffff when the Gaussian emits nothing)
+    uint32_t* depth_vals;        // [P] = idx (payload of the depth sort)
+    uint32_t* depth_hist;        // [4][256] digit histograms of depth_keys (pre-zeroed), accumulated here
 };
 
 int gsr_launch_preprocess_fwd(const PreprocessArgs& a, const GsrView& v, cudaStream_t stream);
@@ -32,20 +46,35 @@ int gsr_launch_mark_visible(int P, const float* means, const GsrView& v, uint8_t
 // ---- binning -------------------------------------------------------------
 // Exclusive scan of the per-block sums in place; total -> *d_total.
 int gsr_launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* d_total, cudaStream_t stream);
-// rasterizer_impl.cu:70-111 duplicateWithKeys (block-cooperative, balanced).
-int gsr_launch_duplicate(int P, const int* radii, const float* depths, const uint32_t* tiles_touched,
-                         const float4* recs, const uint32_t* block_offsets, uint32_t* point_offsets /*or null*/,
-                         uint64_t* keys, uint32_t* vals, int grid_x, int grid_y, cudaStream_t stream);
-// rasterizer_impl.cu:116-138 identifyTileRanges (+ the memset of :310).
-int gsr_launch_tile_ranges(uint32_t R, const uint64_t* sorted_keys, uint2* ranges, int num_tiles, cudaStream_t stream);
+// Per-256 sums of tiles_touched taken in DEPTH-SORTED order (order[] from the depth sort).
+int gsr_launch_sorted_block_sums(int P, const uint32_t* order, const uint32_t* tiles_touched, uint32_t* block_sums,
+                                 cudaStream_t stream);
+// rasterizer_impl.cu:70-111 duplicateWithKeys, walking the Gaussians in depth order and
+// emitting (tile id, Gaussian id) pairs (block-cooperative, balanced).
+int gsr_launch_duplicate(int P, const uint32_t* order, const int* radii, const uint32_t* tiles_touched,
+                         const float4* recs, const uint32_t* block_offsets, uint32_t* tile_ids, uint32_t* vals,
+                         int grid_x, int grid_y, GsrSortPlan tile_plan, uint32_t* tile_hist /* pre-zeroed */,
+                         cudaStream_t stream);
+// rasterizer_impl.cu:116-138 identifyTileRanges (+ the memset of :310) on sorted tile ids.
+int gsr_launch_tile_ranges(uint32_t R, const uint32_t* sorted_tile_ids, uint2* ranges, int num_tiles,
+                           cudaStream_t stream);
+// The reference's 64-bit sorted keys (tile << 32 | depth bits), for parity checks.
+int gsr_launch_materialize_keys(uint32_t R, const uint32_t* sorted_tile_ids, const uint32_t* point_list,
+                                const float* depths, uint64_t* keys64, cudaStream_t stream);
 
-// ---- onesweep radix sort of (u64 key, u32 value) pairs --------------------
+// ---- onesweep radix sort of (u64|u32 key, u32 value) pairs -----------------
+
 size_t gsr_sort_temp_bytes(uint32_t n, int begin_bit, int end_bit);
 // Sorts on bits [begin_bit, end_bit).  Ping-pongs between the a/b buffers and
 // returns (through *result_in_b) where the sorted data ended up.
 int gsr_launch_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n,
                           int begin_bit, int end_bit, void* temp, size_t temp_bytes, int* result_in_b,
                           cudaStream_t stream);
+
+int gsr_launch_sort_pairs32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n,
+                            int begin_bit, int end_bit, void* temp, size_t temp_bytes, int* result_in_b,
+                            cudaStream_t stream, int site = 0 /* profiler label: 1 depth sort, 2 tile sort */,
+                            bool hist_ready = false /* caller zeroed temp and already accumulated hist[][] */);
 
 // ---- blending -------------------------------------------------------------
 struct BlendFwdArgs {

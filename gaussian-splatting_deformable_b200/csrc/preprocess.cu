@@ -59,6 +59,10 @@ __device__ __forceinline__ V3 sh_to_rgb(int deg, float3 pos, const float* campos
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a, GsrView v) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     uint32_t tiles = 0;
+    uint32_t dkey = 0xffffffffu;
+    __shared__ uint32_t s_hist[4 * 256];   // digit histograms of this block's depth keys (depth sort, 4 x 8 bits)
+    for (int k = threadIdx.x; k < 4 * 256; k += 256) s_hist[k] = 0;
+    __syncthreads();
     if (idx < a.P) {
         float3 p = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
         if (a.deform_mode != GSR_DEFORM_NONE) {
@@ -131,6 +135,21 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a, G
         }
         a.radii[idx] = radius;
         a.tiles_touched[idx] = tiles;
+        dkey = tiles ? __float_as_uint(depth) : 0xffffffffu;
+        a.depth_keys[idx] = dkey;
+        a.depth_vals[idx] = (uint32_t)idx;
+    }
+    // Histograms for the depth sort, fused here so the sort never re-reads the keys.
+    // match-any aggregates equal digits (culled Gaussians all carry 0xff bytes).
+    {
+        const bool valid = idx < a.P;
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int p4 = 0; p4 < 4; p4++) {
+            const uint32_t d = valid ? ((dkey >> (8 * p4)) & 255u) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p4 * 256 + d], (uint32_t)__popc(peers));
+        }
     }
     // Per-block partial sum for the offsets scan (fused: saves re-reading tiles_touched).
     __shared__ uint32_t wsum[8];
@@ -144,6 +163,10 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a, G
 #pragma unroll
         for (int k = 0; k < 8; k++) t += wsum[k];
         a.block_sums[blockIdx.x] = t;
+    }
+    for (int k = threadIdx.x; k < 4 * 256; k += 256) {
+        const uint32_t c = s_hist[k];
+        if (c) atomicAdd(&a.depth_hist[k], c);
     }
 }
 

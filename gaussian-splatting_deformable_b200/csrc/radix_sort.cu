@@ -22,38 +22,23 @@
 namespace {
 
 constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int RADIX = GSR_SORT_RADIX;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int ITEMS = 16;
 constexpr int TILE_ITEMS = SORT_THREADS * ITEMS;   // 4096
-constexpr int MAX_PASSES = 8;
+constexpr int MAX_PASSES = GSR_SORT_MAX_PASSES;
 constexpr uint32_t FLAG_PARTIAL = 1u << 30;
 constexpr uint32_t FLAG_INCLUSIVE = 2u << 30;
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
 
-struct SortPlan {
-    int passes;
-    int shift[MAX_PASSES];
-    uint32_t mask[MAX_PASSES];
-};
-
-__host__ SortPlan make_plan(int begin_bit, int end_bit) {
-    SortPlan p{};
-    int bit = begin_bit;
-    while (bit < end_bit && p.passes < MAX_PASSES) {
-        const int nb = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
-        p.shift[p.passes] = bit;
-        p.mask[p.passes] = (1u << nb) - 1u;
-        p.passes++;
-        bit += nb;
-    }
-    return p;
-}
+typedef GsrSortPlan SortPlan;
+inline SortPlan make_plan(int begin_bit, int end_bit) { return gsr_make_sort_plan(begin_bit, end_bit); }
 
 // ---- 1. histograms of all passes in one read of the keys --------------------
-__global__ void __launch_bounds__(256) histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, SortPlan plan,
+template <typename KeyT>
+__global__ void __launch_bounds__(256) histogram_kernel(const KeyT* __restrict__ keys, uint32_t n, SortPlan plan,
                                                         uint32_t* __restrict__ g_hist /*[passes][RADIX]*/) {
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < plan.passes * RADIX; i += 256) s_hist[i] = 0;
@@ -65,7 +50,7 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint64_t* __restri
     for (uint32_t i0 = blockIdx.x * 256u; i0 < n; i0 += stride) {
         const uint32_t i = i0 + threadIdx.x;
         const bool valid = i < n;
-        const uint64_t k = valid ? keys[i] : 0ull;
+        const KeyT k = valid ? keys[i] : (KeyT)0;
 #pragma unroll
         for (int p = 0; p < MAX_PASSES; p++) {
             if (p < plan.passes) {
@@ -103,8 +88,9 @@ __global__ void __launch_bounds__(RADIX) scan_hist_kernel(uint32_t* g_hist) {
 }
 
 // ---- 3. one onesweep digit pass ---------------------------------------------
+template <typename KeyT>
 struct __align__(16) SortSmem {
-    uint64_t keys[TILE_ITEMS];               // 32 KB
+    KeyT keys[TILE_ITEMS];                   // 32 KB (u64) / 16 KB (u32)
     uint32_t vals[TILE_ITEMS];               // 16 KB
     uint32_t warp_hist[SORT_WARPS][RADIX];   //  8 KB  per-warp digit counts -> per-warp digit offsets
     uint32_t digit_base[RADIX];              // global position of the tile's first item of each digit, minus its local start
@@ -113,13 +99,14 @@ struct __align__(16) SortSmem {
     uint32_t tile;
 };
 
+template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
-onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, uint32_t n,
                 const uint32_t* __restrict__ g_offsets /*[RADIX] exclusive*/, volatile uint32_t* status /*[tiles][RADIX]*/,
                 uint32_t* ticket, uint32_t* err_flag, int shift, uint32_t mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem& s = *reinterpret_cast<SortSmem*>(smem_raw);
+    SortSmem<KeyT>& s = *reinterpret_cast<SortSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) s.tile = atomicAdd(ticket, 1u);
@@ -131,14 +118,14 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 
     // Warp-striped load: item j of lane l is element warp_base + j*32 + l, so the
     // (j, lane) order IS the input order - which stability requires.
-    uint64_t key[ITEMS];
+    KeyT key[ITEMS];
     uint32_t val[ITEMS];
     uint32_t rank[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const uint32_t i = warp_base + j * 32 + lane;
         if (i < n) { key[j] = keys_in[i]; val[j] = vals_in[i]; }
-        else { key[j] = ~0ull; val[j] = 0; }
+        else { key[j] = (KeyT)~(KeyT)0; val[j] = 0; }
     }
     // Stable ranking inside the warp: match-any groups lanes with equal digits.
     uint32_t* wh = s.warp_hist[warp];
@@ -223,7 +210,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     // ... and write digit-contiguous runs.
     const uint32_t count = min((uint32_t)TILE_ITEMS, n - tile_base);
     for (uint32_t i = tid; i < count; i += SORT_THREADS) {
-        const uint64_t k = s.keys[i];
+        const KeyT k = s.keys[i];
         const uint32_t d = (uint32_t)(k >> shift) & mask;
         const uint32_t pos = s.digit_base[d] + i;
         keys_out[pos] = k;
@@ -233,6 +220,25 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 
 }  // namespace
 
+GsrSortPlan gsr_make_sort_plan(int begin_bit, int end_bit) {
+    GsrSortPlan p{};
+    const int bits = end_bit - begin_bit;
+    if (bits <= 0) return p;
+    int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    if (passes > MAX_PASSES) passes = MAX_PASSES;
+    int bit = begin_bit;
+    for (int i = 0; i < passes; i++) {
+        const int left = end_bit - bit;
+        int nb = (left + (passes - i) - 1) / (passes - i);     // even split: 13 bits -> 7 + 6
+        if (nb > RADIX_BITS) nb = RADIX_BITS;
+        p.shift[i] = bit;
+        p.mask[i] = (1u << nb) - 1u;
+        bit += nb;
+    }
+    p.passes = passes;
+    return p;
+}
+
 static inline uint32_t sort_num_tiles(uint32_t n) { return (n + TILE_ITEMS - 1) / TILE_ITEMS; }
 
 // temp layout: [hist: MAX_PASSES*RADIX u32][tickets: MAX_PASSES u32 (padded to 64; word 63 = error flag)][status: passes*tiles*RADIX u32]
@@ -241,45 +247,66 @@ size_t gsr_sort_temp_bytes(uint32_t n, int begin_bit, int end_bit) {
     return sizeof(uint32_t) * ((size_t)MAX_PASSES * RADIX + 64 + (size_t)p.passes * sort_num_tiles(n) * RADIX);
 }
 
-int gsr_launch_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n,
-                          int begin_bit, int end_bit, void* temp, size_t temp_bytes, int* result_in_b,
-                          cudaStream_t stream) {
+template <typename KeyT>
+static int sort_pairs_impl(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n, int begin_bit,
+                           int end_bit, void* temp, size_t temp_bytes, int* result_in_b, cudaStream_t stream,
+                           int site = 0, bool hist_ready = false) {
+    // profiler labels: which call site of the pipeline this sort serves
+    static const char* const kHist[3] = {"sort_histogram", "depth_sort_histogram", "tile_sort_histogram"};
+    static const char* const kPass[3] = {"sort_onesweep_pass", "depth_sort_onesweep_pass", "tile_sort_onesweep_pass"};
     *result_in_b = 0;
     if (n == 0 || end_bit <= begin_bit) return 0;
     if (n >= (1u << 30)) return gsr_set_error_msg(-2, "radix sort: n must be < 2^30");
+    if (end_bit > (int)sizeof(KeyT) * 8) return gsr_set_error_msg(-2, "radix sort: end_bit exceeds the key width");
     const SortPlan plan = make_plan(begin_bit, end_bit);
     const size_t need = gsr_sort_temp_bytes(n, begin_bit, end_bit);
     if (temp_bytes < need) return gsr_set_error_msg(-3, "radix sort: temp buffer too small");
     static bool attr_set = false;
     if (!attr_set) {
-        GSR_CHECK(cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(SortSmem)));
+        GSR_CHECK(cudaFuncSetAttribute(onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(SortSmem<KeyT>)));
         attr_set = true;
     }
     uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
     uint32_t* tickets = hist + MAX_PASSES * RADIX;
     uint32_t* status = tickets + 64;
     const uint32_t tiles = sort_num_tiles(n);
-    GSR_CHECK(cudaMemsetAsync(temp, 0, need, stream));
-    int hist_blocks = (int)((n + 256u * 16u - 1) / (256u * 16u));
-    if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-    { GsrProfScope prof_("sort_histogram", stream);
-    histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys_a, n, plan, hist); }
-    GSR_CHECK_LAUNCH();
+    if (!hist_ready) {
+        GSR_CHECK(cudaMemsetAsync(temp, 0, need, stream));
+        int hist_blocks = (int)((n + 256u * 16u - 1) / (256u * 16u));
+        if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+        { GsrProfScope prof_(kHist[site], stream);
+        histogram_kernel<KeyT><<<hist_blocks, 256, 0, stream>>>(keys_a, n, plan, hist); }
+        GSR_CHECK_LAUNCH();
+    }
     { GsrProfScope prof_("sort_scan_hist", stream);
     scan_hist_kernel<<<plan.passes, RADIX, 0, stream>>>(hist); }
     GSR_CHECK_LAUNCH();
-    uint64_t* kin = keys_a; uint64_t* kout = keys_b;
+    KeyT* kin = keys_a; KeyT* kout = keys_b;
     uint32_t* vin = vals_a; uint32_t* vout = vals_b;
     for (int p = 0; p < plan.passes; p++) {
-        { GsrProfScope prof_("sort_onesweep_pass", stream);
-    onesweep_kernel<<<tiles, SORT_THREADS, sizeof(SortSmem), stream>>>(
+        { GsrProfScope prof_(kPass[site], stream);
+        onesweep_kernel<KeyT><<<tiles, SORT_THREADS, sizeof(SortSmem<KeyT>), stream>>>(
             kin, kout, vin, vout, n, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p,
             tickets + 63, plan.shift[p], plan.mask[p]); }
         GSR_CHECK_LAUNCH();
-        uint64_t* tk = kin; kin = kout; kout = tk;
+        KeyT* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
     *result_in_b = (plan.passes & 1) ? 1 : 0;
     return 0;
+}
+
+int gsr_launch_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n,
+                          int begin_bit, int end_bit, void* temp, size_t temp_bytes, int* result_in_b,
+                          cudaStream_t stream) {
+    return sort_pairs_impl<uint64_t>(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
+                                     result_in_b, stream);
+}
+
+int gsr_launch_sort_pairs32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t n,
+                            int begin_bit, int end_bit, void* temp, size_t temp_bytes, int* result_in_b,
+                            cudaStream_t stream, int site, bool hist_ready) {
+    return sort_pairs_impl<uint32_t>(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
+                                     result_in_b, stream, site, hist_ready);
 }

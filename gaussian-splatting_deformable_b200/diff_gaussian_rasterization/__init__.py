@@ -141,7 +141,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 num_rendered = int(mailbox.item()) & 0xFFFFFFFF
             binning = torch.empty(lib.gsr_binning_bytes(num_rendered, W, H), dtype=torch.uint8, device=dev)
             _rt.check(lib.gsr_forward_render(view, P, num_rendered, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
-                                             binning.numel(), _rt.ptr(img), _rt.ptr(color), stream))
+                                             binning.numel(), _rt.ptr(img), _rt.ptr(color),
+                                             1 if raster_settings.debug else 0, stream))
 
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered

@@ -68,7 +68,7 @@ _SIGNATURES = {
                                               _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
                                               _P, _P, ctypes.c_size_t, _P, ctypes.c_int, _P]),
     "gsr_forward_render": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P,
-                                          ctypes.c_size_t, _P, _P, _P]),
+                                          ctypes.c_size_t, _P, _P, ctypes.c_int, _P]),
     "gsr_backward": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                     _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
                                     _P, _P, _P, _P, _P,
@@ -82,6 +82,8 @@ _SIGNATURES = {
     "gsr_sort_bytes": (ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),
     "gsr_sort_pairs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, _P,
                                       ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), _P]),
+    "gsr_sort_pairs32": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, _P,
+                                        ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -185,7 +187,7 @@ def pinned_u32(device):
 def geom_layout(P):
     out = (ctypes.c_size_t * 6)()
     load().gsr_geom_layout(int(P), out)
-    return dict(zip(("depths", "tiles_touched", "recs", "clamped", "point_offsets", "cov3D"), list(out)))
+    return dict(zip(("depths", "tiles_touched", "recs", "clamped", "depth_order", "cov3D"), list(out)))
 
 
 def image_layout(W, H):
@@ -197,7 +199,7 @@ def image_layout(W, H):
 def binning_layout(R, W, H):
     out = (ctypes.c_size_t * 4)()
     load().gsr_binning_layout(int(R), int(W), int(H), out)
-    return dict(zip(("keys_sorted", "point_list", "keys_other", "vals_other"), list(out)))
+    return dict(zip(("keys_sorted", "point_list", "tile_ids_sorted", "scratch"), list(out)))
 
 
 def profile_enable(on=True):

@@ -91,12 +91,13 @@ size_t gsr_grad_bytes(int P);                       /* blend-backward gradient r
 /* Byte offsets of the geometry-workspace sub-arrays, for tests and tools:
  * out[0]=depths f32[P], out[1]=tiles_touched u32[P], out[2]=splat records float4[3P]
  * (x,y,conic.x,conic.y | conic.z,opacity,r,g | b,cut,0,0), out[3]=clamped u8[P],
- * out[4]=point_offsets u32[P] (inclusive scan), out[5]=cov3D f32[6P] (debug only) */
+ * out[4]=depth order u32[P] (Gaussian ids, front to back, after gsr_forward_render),
+ * out[5]=cov3D f32[6P] (debug only) */
 void gsr_geom_layout(int P, size_t out[6]);
 /* out[0]=final_T f32[WH], out[1]=n_contrib u32[WH], out[2]=ranges uint2[tiles] */
 void gsr_image_layout(int width, int height, size_t out[3]);
-/* out[0]=sorted keys u64[R], out[1]=sorted values (point_list) u32[R],
- * out[2]=unsorted keys, out[3]=unsorted values */
+/* out[0]=reference-format sorted keys u64[R] (only when materialize_keys was set),
+ * out[1]=point_list u32[R] (sorted Gaussian ids), out[2]=sorted tile ids u32[R], out[3]=scratch */
 void gsr_binning_layout(uint32_t num_rendered, int width, int height, size_t out[4]);
 
 /* ---- forward -------------------------------------------------------------
@@ -116,10 +117,12 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M,
                            int32_t* radii, void* geom_ws, size_t geom_bytes,
                            uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream);
 
-/* Stage 2: duplicate keys, onesweep sort, tile ranges, blend.  out_color[3,H,W]. */
+/* Stage 2: depth-order the Gaussians (onesweep), duplicate (tile id, Gaussian id) pairs,
+ * onesweep by tile id, tile ranges, blend.  out_color[3,H,W].  materialize_keys != 0 also
+ * writes the reference-format sorted 64-bit keys (tile << 32 | depth bits) for parity checks. */
 int gsr_forward_render(const gsr_view* view, int P, uint32_t num_rendered,
                        const int32_t* radii, void* geom_ws, void* binning_ws, size_t binning_bytes,
-                       void* image_ws, float* out_color, void* stream);
+                       void* image_ws, float* out_color, int materialize_keys, void* stream);
 
 /* ---- backward -------------------------------------------------------------
  * dL_dout_color[3,H,W] -> gradients.  Every output element is written (no
@@ -158,6 +161,9 @@ size_t gsr_sort_bytes(uint32_t n, int begin_bit, int end_bit);
 int gsr_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
                    uint32_t n, int begin_bit, int end_bit, void* temp, size_t temp_bytes,
                    int* result_in_b, void* stream);
+int gsr_sort_pairs32(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                     uint32_t n, int begin_bit, int end_bit, void* temp, size_t temp_bytes,
+                     int* result_in_b, void* stream);
 
 #ifdef __cplusplus
 }

@@ -84,7 +84,7 @@ def intermediates(rs, sc, M=16, deform=None):
     R = int(mb.item())
     binning = torch.zeros(lib.gsr_binning_bytes(R, W, H), dtype=torch.uint8, device=dev)
     rt.check(lib.gsr_forward_render(view, P, R, rt.ptr(radii), rt.ptr(geom), rt.ptr(binning), binning.numel(),
-                                    rt.ptr(img), rt.ptr(color), st))
+                                    rt.ptr(img), rt.ptr(color), 1, st))
     torch.cuda.synchronize()
     gl, il, bl = rt.geom_layout(P), rt.image_layout(W, H), rt.binning_layout(R, W, H)
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
@@ -97,27 +97,30 @@ def intermediates(rs, sc, M=16, deform=None):
     return dict(R=R, radii=radii, color=color,
                 depths=sl(geom, gl["depths"], P, torch.float32),
                 tiles_touched=sl(geom, gl["tiles_touched"], P, torch.int32),
-                point_offsets=sl(geom, gl["point_offsets"], P, torch.int32),
+                depth_order=sl(geom, gl["depth_order"], P, torch.int32),
                 cov3D=sl(geom, gl["cov3D"], 6 * P, torch.float32).view(P, 6),
                 clamped=torch.stack([(cl & 1) > 0, (cl & 2) > 0, (cl & 4) > 0], 1),
                 means2D=recs[:, 0:2], conic_opacity=recs[:, 2:6], rgb=recs[:, 6:9],
                 keys_sorted=sl(binning, bl["keys_sorted"], R, torch.int64),
                 point_list=sl(binning, bl["point_list"], R, torch.int32),
+                tile_ids_sorted=sl(binning, bl["tile_ids_sorted"], R, torch.int32),
                 final_T=sl(img, il["final_T"], W * H, torch.float32),
                 n_contrib=sl(img, il["n_contrib"], W * H, torch.int32),
                 ranges=sl(img, il["ranges"], 2 * tiles, torch.int32).view(tiles, 2))
 
 
 def sort_pairs(keys, vals, begin_bit, end_bit):
+    """gsr_sort_pairs (u64 keys) or gsr_sort_pairs32 (int32 keys), chosen by dtype."""
     lib = rt.load()
+    fn = lib.gsr_sort_pairs32 if keys.dtype == torch.int32 else lib.gsr_sort_pairs
     n = keys.numel()
     ka, kb = keys.clone(), torch.zeros_like(keys)
     va, vb = vals.clone(), torch.zeros_like(vals)
     nbytes = lib.gsr_sort_bytes(n, begin_bit, end_bit)
     temp = torch.zeros(max(nbytes, 4), dtype=torch.uint8, device=keys.device)
     in_b = ctypes.c_int(0)
-    rt.check(lib.gsr_sort_pairs(rt.ptr(ka), rt.ptr(kb), rt.ptr(va), rt.ptr(vb), n, begin_bit, end_bit,
-                                rt.ptr(temp), nbytes, ctypes.byref(in_b), rt.stream_ptr()))
+    rt.check(fn(rt.ptr(ka), rt.ptr(kb), rt.ptr(va), rt.ptr(vb), n, begin_bit, end_bit,
+                rt.ptr(temp), nbytes, ctypes.byref(in_b), rt.stream_ptr()))
     torch.cuda.synchronize()
     return (kb, vb) if in_b.value else (ka, va)
 

@@ -56,8 +56,8 @@ def test_workspace_sizes_and_layouts():
     assert il["n_contrib"] - il["final_T"] >= 4 * W * H and lib.gsr_image_bytes(W, H) >= il["ranges"] + 8 * 8160
     bl = rt.binning_layout(R, W, H)
     assert len(set(bl.values())) == 4
-    # 2 key arrays + 2 value arrays + onesweep state: between 24 B and 40 B per duplicate
-    assert 24 * R <= lib.gsr_binning_bytes(R, W, H) <= 40 * R
+    # 2 tile-id arrays + 2 value arrays + onesweep state + reference-format keys: 24..32 B per duplicate
+    assert 24 * R <= lib.gsr_binning_bytes(R, W, H) <= 32 * R
     assert lib.gsr_binning_bytes(0, W, H) < 1 << 20
     assert lib.gsr_grad_bytes(P) >= 48 * P
     # 45 key bits at 1080p -> 6 digit passes (even): the sorted data ends in the first buffer pair

@@ -23,7 +23,7 @@ def main():
     rt.check(lib.gsr_forward_preprocess(view, P, 16, rt.ptr(sc["means3D"]), rt.ptr(sc["scales"]), rt.ptr(sc["rotations"]), rt.ptr(sc["opacities"]), rt.ptr(sc["shs"]), None, None, rt.gsr_deform(), None, rt.ptr(radii), rt.ptr(geom), geom.numel(), mb.data_ptr(), 0, st))
     R = int(mb.item())
     binning = torch.zeros(lib.gsr_binning_bytes(R, W, H), dtype=torch.uint8, device=dev)
-    rt.check(lib.gsr_forward_render(view, P, R, rt.ptr(radii), rt.ptr(geom), rt.ptr(binning), binning.numel(), rt.ptr(img), rt.ptr(color), st))
+    rt.check(lib.gsr_forward_render(view, P, R, rt.ptr(radii), rt.ptr(geom), rt.ptr(binning), binning.numel(), rt.ptr(img), rt.ptr(color), 1, st))
     out = torch.zeros(8, dtype=torch.int64, device=dev)
     rt.check(lib.gsr_debug_blend_stats(view, P, R, rt.ptr(geom), rt.ptr(binning), rt.ptr(img), rt.ptr(out), st))
     torch.cuda.synchronize()

@@ -85,7 +85,7 @@ def mine_intermediates(rs, sc):
     R = int(mb.item())
     binning = torch.zeros(lib.gsr_binning_bytes(R, W, H), dtype=torch.uint8, device=dev)
     rt.check(lib.gsr_forward_render(view, P, R, rt.ptr(radii), rt.ptr(geom), rt.ptr(binning), binning.numel(),
-                                    rt.ptr(img), rt.ptr(color), st))
+                                    rt.ptr(img), rt.ptr(color), 1, st))
     torch.cuda.synchronize()
     gl, il, bl = rt.geom_layout(P), rt.image_layout(W, H), rt.binning_layout(R, W, H)
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
@@ -97,7 +97,7 @@ def mine_intermediates(rs, sc):
     return dict(R=R, radii=radii, color=color,
                 depths=sl(geom, gl["depths"], P, torch.float32),
                 tiles=sl(geom, gl["tiles_touched"], P, torch.int32),
-                offsets=sl(geom, gl["point_offsets"], P, torch.int32),
+                
                 cov3D=sl(geom, gl["cov3D"], 6 * P, torch.float32).view(P, 6),
                 clamped=sl(geom, gl["clamped"], P, torch.uint8),
                 means2D=recs[:, 0:2], conic_opacity=torch.cat([recs[:, 2:5], recs[:, 5:6]], 1),
@@ -153,7 +153,6 @@ def main():
     stat("rgb[vis]", mi["rgb"][vis], rg["rgb"][vis], log=log)
     cl_ref = (rg["clamped"][:, 0].int() | (rg["clamped"][:, 1].int() << 1) | (rg["clamped"][:, 2].int() << 2))
     stat("clamped[vis]", mi["clamped"][vis].int(), cl_ref[vis], log=log)
-    stat("point_offsets", mi["offsets"], torch.cumsum(rg["tiles_touched"], 0).int(), log=log)
     if mi["R"] == R:
         stat("keys_sorted", mi["keys"], rb["point_list_keys"], log=log)
         stat("point_list", mi["point_list"], rb["point_list"], log=log)
