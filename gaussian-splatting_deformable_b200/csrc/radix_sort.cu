@@ -100,7 +100,7 @@ struct __align__(16) SortSmem {
 };
 
 template <typename KeyT>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, sizeof(KeyT) == 4 ? 5 : 3)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, uint32_t n,
                 const uint32_t* __restrict__ g_offsets /*[RADIX] exclusive*/, volatile uint32_t* status /*[tiles][RADIX]*/,
@@ -118,16 +118,21 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
 
     // Warp-striped load: item j of lane l is element warp_base + j*32 + l, so the
     // (j, lane) order IS the input order - which stability requires.
+    // (values are loaded only after the look-back, when the key registers are free:
+    //  fewer live registers -> more resident CTAs to hide the latency of this chain)
     KeyT key[ITEMS];
-    uint32_t val[ITEMS];
     uint32_t rank[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const uint32_t i = warp_base + j * 32 + lane;
-        if (i < n) { key[j] = keys_in[i]; val[j] = vals_in[i]; }
-        else { key[j] = (KeyT)~(KeyT)0; val[j] = 0; }
+        key[j] = (i < n) ? keys_in[i] : (KeyT)~(KeyT)0;
     }
-    // Stable ranking inside the warp: match-any groups lanes with equal digits.
+    // Stable ranking inside the warp: match-any groups lanes with equal digits; the
+    // group's first lane bumps the warp's digit counter with ONE shared-memory atomic
+    // that returns the count of earlier items (no load/store/__syncwarp round trip, so
+    // the 16 items' match/atomic/shuffle chains overlap instead of serialising).
+    // A warp's shared-memory instructions execute in program order, so successive
+    // items see the counter values in item order - which is what stability needs.
     uint32_t* wh = s.warp_hist[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -138,10 +143,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
-        if (valid && lane == leader) { prev = wh[d]; wh[d] = prev + __popc(peers); }
+        if (valid && lane == leader) prev = atomicAdd(&wh[d], (uint32_t)__popc(peers));
         prev = __shfl_sync(0xffffffffu, prev, leader);
         rank[j] = prev + __popc(peers & lt_mask);
-        __syncwarp();
     }
     __syncthreads();
 
@@ -160,20 +164,35 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         *my = (tile == 0 ? FLAG_INCLUSIVE : FLAG_PARTIAL) | sum;
         uint32_t excl = 0;
         if (tile > 0) {
+            // Decoupled look-back, LOOKBACK predecessors per round trip: the dependent-load
+            // chain across tiles is what bounds a pass (~50 ns per tile when walked one
+            // status word at a time), so fetch a window of status words at once and
+            // consume the ready prefix.
+            constexpr int LOOKBACK = 8;
             int t = (int)tile - 1;
             uint32_t polls = 0;
-            while (true) {
-                const uint32_t st = status[(size_t)t * RADIX + d];
-                const uint32_t fl = st & FLAG_MASK;
-                if (fl == 0) {                          // predecessor not published yet: spin
+            bool found = false;
+            while (!found) {
+                uint32_t st[LOOKBACK];
+#pragma unroll
+                for (int b = 0; b < LOOKBACK; b++)
+                    st[b] = (t - b >= 0) ? status[(size_t)(t - b) * RADIX + d] : (2u << 30) /* FLAG_INCLUSIVE, value 0 */;
+                int used = 0;
+#pragma unroll
+                for (int b = 0; b < LOOKBACK; b++) {
+                    const uint32_t fl = st[b] & FLAG_MASK;
+                    if (!found && used == b && fl != 0) {      // ready and contiguous with what was consumed
+                        excl += st[b] & VALUE_MASK;
+                        used = b + 1;
+                        if (fl == FLAG_INCLUSIVE) found = true;
+                    }
+                }
+                t -= used;
+                if (used == 0) {
                     // Tickets make this wait finite; the poll bound only turns a would-be
                     // hang (e.g. a corrupted workspace) into a reported error.
-                    if (++polls > (1u << 26)) { atomicOr(err_flag, 1u); break; }
-                    continue;
+                    if (++polls > (1u << 24)) { atomicOr(err_flag, 1u); break; }
                 }
-                excl += st & VALUE_MASK;
-                if (fl == FLAG_INCLUSIVE) break;
-                t--;
             }
             *my = FLAG_INCLUSIVE | (excl + sum);
         }
@@ -195,7 +214,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     }
     __syncthreads();
 
-    // Reorder the tile by digit in shared memory ...
+    // Reorder the tile by digit in shared memory: keys first (rank[] becomes the slot) ...
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const uint32_t i = warp_base + j * 32 + lane;
@@ -203,7 +222,21 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
             const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
             const uint32_t pos = s.local_start[d] + s.warp_hist[warp][d] + rank[j];
             s.keys[pos] = key[j];
-            s.vals[pos] = val[j];
+            rank[j] = pos;
+        }
+    }
+    // ... then the values, loaded now that the key registers are dead.
+    {
+        uint32_t val[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const uint32_t i = warp_base + j * 32 + lane;
+            val[j] = (i < n) ? vals_in[i] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const uint32_t i = warp_base + j * 32 + lane;
+            if (i < n) s.vals[rank[j]] = val[j];
         }
     }
     __syncthreads();
