@@ -212,7 +212,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     if args.impl == "reference":
         from oracle import ref_driver
@@ -289,7 +290,8 @@ def main():
     if args.impl == "ours" and rank == 0:
         from diff_gaussian_rasterization import _RasterizeGaussians
         rt.profile_enable(True)
-        run_step()
+        zero_grads(leaves)
+        step_fn(leaves, cams, bg, grad, args)          # rank-local: NO collective here (other ranks are done)
         torch.cuda.synchronize()
         prof = rt.profile_dump()
         rt.profile_enable(False)
