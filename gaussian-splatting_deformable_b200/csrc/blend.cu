@@ -246,8 +246,8 @@ __device__ __forceinline__ float rcp_nr(float x) {
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
-template <int PPT>
-__global__ void __launch_bounds__(BLK / PPT) blend_bwd_kernel(BlendBwdArgs a) {
+template <int PPT, int MINB>
+__global__ void __launch_bounds__(BLK / PPT, MINB) blend_bwd_kernel(BlendBwdArgs a) {
     constexpr int NT = BLK / PPT;
     __shared__ float4 s_q0[NT];
     __shared__ float4 s_q1[NT];     // conic.z, opacity, cut, list position as bits
@@ -502,10 +502,15 @@ int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int ppt = env_int("GSR_BWD_PPT", 4);
+    static const int minb = env_int("GSR_BWD_MINB", 0);     // tuning aid: register cap through min CTAs/SM
     { GsrProfScope prof_("blend_bwd", stream);
-    if (ppt == 4) blend_bwd_kernel<4><<<grid, BLK / 4, 0, stream>>>(a);
-    else if (ppt == 2) blend_bwd_kernel<2><<<grid, BLK / 2, 0, stream>>>(a);
-    else blend_bwd_kernel<1><<<grid, BLK, 0, stream>>>(a); }
+    if (ppt == 4 && minb == 10) blend_bwd_kernel<4, 10><<<grid, BLK / 4, 0, stream>>>(a);
+    else if (ppt == 4 && minb == 12) blend_bwd_kernel<4, 12><<<grid, BLK / 4, 0, stream>>>(a);
+    else if (ppt == 4) blend_bwd_kernel<4, 8><<<grid, BLK / 4, 0, stream>>>(a);
+    else if (ppt == 2 && minb == 6) blend_bwd_kernel<2, 6><<<grid, BLK / 2, 0, stream>>>(a);
+    else if (ppt == 2 && minb == 8) blend_bwd_kernel<2, 8><<<grid, BLK / 2, 0, stream>>>(a);
+    else if (ppt == 2) blend_bwd_kernel<2, 5><<<grid, BLK / 2, 0, stream>>>(a);
+    else blend_bwd_kernel<1, 4><<<grid, BLK, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
