@@ -89,6 +89,35 @@ __device__ __forceinline__ int block_compact(bool keep, uint32_t* s_wcount, int&
 }
 
 // ---------------------------------------------------------------------------
+// TMA (bulk async copy) staging.  Every list entry is one contiguous 48-byte splat
+// record, i.e. one `cp.async.bulk` global->shared copy: the thread that owns the
+// entry issues it (SASS: UBLKCP), completion is tracked by an mbarrier per stage
+// (expect_tx = 48 x entries of the batch), and the batch lands in a 2-stage shared
+// ring with no register staging while the previous batch is being blended.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_48(void* dst_smem, const void* src_gmem, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 48, [%2];" ::"r"(
+                     smem_addr(dst_smem)), "l"(src_gmem), "r"(smem_addr(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // Forward.  PPT pixels per thread: a CTA has 256/PPT threads; warp w owns the PPT
 // consecutive 8x4 patches w*PPT .. w*PPT+PPT-1 (patch p at ((p&1)*8, (p>>1)*4)) and
 // lane l owns the same in-patch pixel of each.  Staged records, loop control and the
@@ -102,9 +131,11 @@ __device__ __forceinline__ void patch_pixel(int tid, int slot, int& lx, int& ly)
     ly = ((p >> 1) << 2) + (l >> 3);
 }
 
-template <int PPT>
+template <int PPT, bool TMA>
 __global__ void __launch_bounds__(BLK / PPT) blend_fwd_kernel(BlendFwdArgs a) {
     constexpr int NT = BLK / PPT;
+    __shared__ __align__(16) float4 s_raw[TMA ? 2 : 1][TMA ? NT * 3 : 1];   // TMA landing ring (2 stages x NT records)
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ float4 s_q0[NT];     // x, y, conic.x, conic.y
     __shared__ float4 s_q1[NT];     // conic.z, opacity, cut, (contributor number as bits)
     __shared__ float4 s_q2[NT];     // r, g, b, -
@@ -133,13 +164,27 @@ __global__ void __launch_bounds__(BLK / PPT) blend_fwd_kernel(BlendFwdArgs a) {
     const int todo = (int)(range.y - range.x);
     const int rounds = (todo + NT - 1) / NT;
 
-    // Software pipeline: gathers of batch i+1 are in flight while batch i is blended.
+    if (TMA) {
+        if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+    }
+    // Software pipeline: the gathers of batch i+1 are in flight while batch i is blended
+    // (TMA: into the shared ring; otherwise into registers).
     float4 n0, n1, n2;
     bool nvalid = false;
+    int issued = 0, consumed = 0;
     auto fetch = [&](int round) {
         const int pos = round * NT + tid;
         nvalid = pos < todo;
-        if (nvalid) {
+        if (TMA) {
+            const int st = round & 1;
+            if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], 48u * (uint32_t)min(NT, todo - round * NT));
+            if (nvalid) {
+                const uint32_t id = a.point_list[range.x + pos];
+                tma_load_48(&s_raw[st][3 * tid], a.recs + 3 * (size_t)id, &s_bar[st]);
+            }
+            issued = round + 1;
+        } else if (nvalid) {
             const uint32_t id = a.point_list[range.x + pos];
             const float4* r = a.recs + 3 * (size_t)id;
             n0 = __ldg(r); n1 = __ldg(r + 1); n2 = __ldg(r + 2);
@@ -153,9 +198,16 @@ __global__ void __launch_bounds__(BLK / PPT) blend_fwd_kernel(BlendFwdArgs a) {
         for (int s = 0; s < PPT; s++) all_done = all_done && done[s];
         // Whole CTA done?  (also the barrier that protects the staging buffers)
         if (__syncthreads_count(all_done) == NT) break;
+        const int pos = i * NT + tid;
+        if (TMA) {
+            const int st = i & 1;
+            mbar_wait(&s_bar[st], (uint32_t)(i >> 1) & 1u);
+            nvalid = pos < todo;
+            if (nvalid) { n0 = s_raw[st][3 * tid]; n1 = s_raw[st][3 * tid + 1]; n2 = s_raw[st][3 * tid + 2]; }
+            consumed = i + 1;
+        }
         const float4 q0 = n0, q1 = n1, q2 = n2;
         const bool keep = nvalid && tile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q2.y, tx0, ty0, tx1, ty1);
-        const int pos = i * NT + tid;
         if (i + 1 < rounds) fetch(i + 1);
         int n;
         const int slot = block_compact<NT>(keep, s_wcount, n);
@@ -188,6 +240,8 @@ __global__ void __launch_bounds__(BLK / PPT) blend_fwd_kernel(BlendFwdArgs a) {
             }
         }
     }
+    // A CTA must not retire with a bulk copy still landing in its shared memory.
+    if (TMA && issued > consumed) mbar_wait(&s_bar[consumed & 1], (uint32_t)(consumed >> 1) & 1u);
     const size_t HW = (size_t)a.H * a.W;
 #pragma unroll
     for (int s = 0; s < PPT; s++) {
@@ -246,9 +300,11 @@ __device__ __forceinline__ float rcp_nr(float x) {
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
-template <int PPT, int MINB>
+template <int PPT, int MINB, bool TMA>
 __global__ void __launch_bounds__(BLK / PPT, MINB) blend_bwd_kernel(BlendBwdArgs a) {
     constexpr int NT = BLK / PPT;
+    __shared__ __align__(16) float4 s_raw[TMA ? 2 : 1][TMA ? NT * 3 : 1];   // TMA landing ring
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ float4 s_q0[NT];
     __shared__ float4 s_q1[NT];     // conic.z, opacity, cut, list position as bits
     __shared__ float4 s_q2[NT];     // r, g, b, Gaussian id as bits
@@ -294,27 +350,46 @@ __global__ void __launch_bounds__(BLK / PPT, MINB) blend_bwd_kernel(BlendBwdArgs
 #pragma unroll
     for (int w = 0; w < NT / 32; w++) tile_last = max(tile_last, s_wmax[w]);
 
+    if (TMA) {
+        if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+    }
     float4 n0, n1, n2;
-    uint32_t nid = 0;
+    uint32_t nid = 0, cur_id = 0;
     bool nvalid = false;
-    auto fetch = [&](int start) {
+    auto fetch = [&](int start, int round) {
         const int pos = start - 1 - tid;       // back to front
         nvalid = pos >= 0;
-        if (nvalid) {
+        if (TMA) {
+            const int st = round & 1;
+            if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], 48u * (uint32_t)min(NT, start));
+            if (nvalid) {
+                nid = a.point_list[range.x + pos];
+                tma_load_48(&s_raw[st][3 * tid], a.recs + 3 * (size_t)nid, &s_bar[st]);
+            }
+        } else if (nvalid) {
             nid = a.point_list[range.x + pos];
             const float4* r = a.recs + 3 * (size_t)nid;
             n0 = __ldg(r); n1 = __ldg(r + 1); n2 = __ldg(r + 2);
         }
     };
-    if (tile_last > 0) fetch((int)tile_last);
+    if (tile_last > 0) fetch((int)tile_last, 0);
     float* const grad_base = reinterpret_cast<float*>(a.grad_recs);
 
-    for (int start = (int)tile_last; start > 0; start -= NT) {
-        const float4 q0 = n0, q1 = n1, q2 = n2;
-        const uint32_t id = nid;
+    int round = 0;
+    for (int start = (int)tile_last; start > 0; start -= NT, round++) {
         const int pos = start - 1 - tid;
+        cur_id = nid;
+        if (TMA) {
+            const int st = round & 1;
+            mbar_wait(&s_bar[st], (uint32_t)(round >> 1) & 1u);
+            nvalid = pos >= 0;
+            if (nvalid) { n0 = s_raw[st][3 * tid]; n1 = s_raw[st][3 * tid + 1]; n2 = s_raw[st][3 * tid + 2]; }
+        }
+        const float4 q0 = n0, q1 = n1, q2 = n2;
+        const uint32_t id = cur_id;
         const bool keep = nvalid && tile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q2.y, tx0, ty0, tx1, ty1);
-        if (start - NT > 0) fetch(start - NT);
+        if (start - NT > 0) fetch(start - NT, round + 1);
         int n;
         const int slot = block_compact<NT>(keep, s_wcount, n);   // barrier: previous batch fully consumed
         if (keep) {
@@ -487,14 +562,22 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-// Pixels per thread of the blend kernels (1, 2 or 4): GSR_FWD_PPT / GSR_BWD_PPT.
+// Variant selection: pixels per thread of the blend kernels (GSR_FWD_PPT / GSR_BWD_PPT =
+// 1, 2 or 4) and TMA bulk-copy staging of the splat records (GSR_BLEND_TMA = 0/1).
 int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int ppt = env_int("GSR_FWD_PPT", 2);
+    static const int tma = env_int("GSR_BLEND_TMA", 0);   // measured 4% slower than the register-staged gather at C2
     { GsrProfScope prof_("blend_fwd", stream);
-    if (ppt == 4) blend_fwd_kernel<4><<<grid, BLK / 4, 0, stream>>>(a);
-    else if (ppt == 2) blend_fwd_kernel<2><<<grid, BLK / 2, 0, stream>>>(a);
-    else blend_fwd_kernel<1><<<grid, BLK, 0, stream>>>(a); }
+    if (tma) {
+        if (ppt == 4) blend_fwd_kernel<4, true><<<grid, BLK / 4, 0, stream>>>(a);
+        else if (ppt == 2) blend_fwd_kernel<2, true><<<grid, BLK / 2, 0, stream>>>(a);
+        else blend_fwd_kernel<1, true><<<grid, BLK, 0, stream>>>(a);
+    } else {
+        if (ppt == 4) blend_fwd_kernel<4, false><<<grid, BLK / 4, 0, stream>>>(a);
+        else if (ppt == 2) blend_fwd_kernel<2, false><<<grid, BLK / 2, 0, stream>>>(a);
+        else blend_fwd_kernel<1, false><<<grid, BLK, 0, stream>>>(a);
+    } }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -502,15 +585,17 @@ int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int ppt = env_int("GSR_BWD_PPT", 4);
-    static const int minb = env_int("GSR_BWD_MINB", 0);     // tuning aid: register cap through min CTAs/SM
+    static const int tma = env_int("GSR_BLEND_TMA", 0);   // measured 4% slower than the register-staged gather at C2
     { GsrProfScope prof_("blend_bwd", stream);
-    if (ppt == 4 && minb == 10) blend_bwd_kernel<4, 10><<<grid, BLK / 4, 0, stream>>>(a);
-    else if (ppt == 4 && minb == 12) blend_bwd_kernel<4, 12><<<grid, BLK / 4, 0, stream>>>(a);
-    else if (ppt == 4) blend_bwd_kernel<4, 8><<<grid, BLK / 4, 0, stream>>>(a);
-    else if (ppt == 2 && minb == 6) blend_bwd_kernel<2, 6><<<grid, BLK / 2, 0, stream>>>(a);
-    else if (ppt == 2 && minb == 8) blend_bwd_kernel<2, 8><<<grid, BLK / 2, 0, stream>>>(a);
-    else if (ppt == 2) blend_bwd_kernel<2, 5><<<grid, BLK / 2, 0, stream>>>(a);
-    else blend_bwd_kernel<1, 4><<<grid, BLK, 0, stream>>>(a); }
+    if (tma) {
+        if (ppt == 4) blend_bwd_kernel<4, 8, true><<<grid, BLK / 4, 0, stream>>>(a);
+        else if (ppt == 2) blend_bwd_kernel<2, 5, true><<<grid, BLK / 2, 0, stream>>>(a);
+        else blend_bwd_kernel<1, 4, true><<<grid, BLK, 0, stream>>>(a);
+    } else {
+        if (ppt == 4) blend_bwd_kernel<4, 8, false><<<grid, BLK / 4, 0, stream>>>(a);
+        else if (ppt == 2) blend_bwd_kernel<2, 5, false><<<grid, BLK / 2, 0, stream>>>(a);
+        else blend_bwd_kernel<1, 4, false><<<grid, BLK, 0, stream>>>(a);
+    } }
     GSR_CHECK_LAUNCH();
     return 0;
 }
