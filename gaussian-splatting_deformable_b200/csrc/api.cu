@@ -355,7 +355,7 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
                  const void* binning_ws, const void* image_ws, void* grad_ws, const float* dL_dout_color,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dopacity, float* dL_dcolors, float* dL_dcov3D,
                  float* dL_dsh, float* dL_dscales, float* dL_drots, float* dL_dtwist_S, float* dL_dtwist_theta,
-                 void* stream_) {
+                 int accumulate_mask, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (P <= 0) return 0;
     GsrView v;
@@ -405,6 +405,7 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = scales ? dL_dscales : nullptr;
     a.dL_drots = scales ? dL_drots : nullptr;
     a.dL_dtwist_S = dL_dtwist_S; a.dL_dtwist_theta = dL_dtwist_theta;
+    a.acc = accumulate_mask;
     return gsr_launch_preprocess_bwd(a, v, stream);
 }
 

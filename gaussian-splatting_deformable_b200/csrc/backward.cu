@@ -61,7 +61,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         if (visible) { g0 = gr[0]; g1 = gr[1]; g2x = reinterpret_cast<const float*>(gr + 2)[0]; }
         // pass-through outputs
         a.dL_dmeans2D[3 * idx] = g0.x; a.dL_dmeans2D[3 * idx + 1] = g0.y; a.dL_dmeans2D[3 * idx + 2] = 0.0f;
-        a.dL_dopacity[idx] = g1.y;
+        // Accumulate mode (a.acc bit set): the output is the caller's running gradient
+        // (`+=`, culled Gaussians untouched) instead of a fresh tensor - the separate
+        // elementwise accumulation pass over 264 B/Gaussian per extra view disappears.
+        const int acc = a.acc;
+        if (acc & GSR_ACC_OPACITY) { if (visible) a.dL_dopacity[idx] += g1.y; }
+        else a.dL_dopacity[idx] = g1.y;
         a.dL_dcolors[3 * idx] = g1.z; a.dL_dcolors[3 * idx + 1] = g1.w; a.dL_dcolors[3 * idx + 2] = g2x;
 
         float dcov[6] = {0, 0, 0, 0, 0, 0};
@@ -219,10 +224,11 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                         o.y = coef[(4 * k + 1) / 3] * dr[(4 * k + 1) % 3];
                         o.z = coef[(4 * k + 2) / 3] * dr[(4 * k + 2) % 3];
                         o.w = coef[(4 * k + 3) / 3] * dr[(4 * k + 3) % 3];
+                        if (acc & GSR_ACC_SH) { const float4 old = d4[k]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
                         d4[k] = o;
                     }
                 } else {
-                    for (int e = 0; e < M * 3; e++) dsh[e] = coef[e / 3] * dr[e % 3];
+                    for (int e = 0; e < M * 3; e++) dsh[e] = coef[e / 3] * dr[e % 3] + ((acc & GSR_ACC_SH) ? dsh[e] : 0.0f);
                 }
                 const V3 dL_ddir = {dot(dRGBdx, dRGB), dot(dRGBdy, dRGB), dot(dRGBdz, dRGB)};
                 const V3 dmean_sh = dnormvdv(dir_orig, dL_ddir);
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                 drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
                 drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
             }
-        } else if (a.dL_dsh) {
+        } else if (a.dL_dsh && !(a.acc & GSR_ACC_SH)) {
             float* dsh = a.dL_dsh + (size_t)idx * M * 3;
             if (M == 16) {
                 float4* d4 = reinterpret_cast<float4*>(dsh);
@@ -285,9 +291,20 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 #pragma unroll
         for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
         if (a.dL_dscales) {
-            a.dL_dscales[3 * idx] = dscale[0]; a.dL_dscales[3 * idx + 1] = dscale[1]; a.dL_dscales[3 * idx + 2] = dscale[2];
+            if (acc & GSR_ACC_SCALES) {
+                if (visible) { a.dL_dscales[3 * idx] += dscale[0]; a.dL_dscales[3 * idx + 1] += dscale[1]; a.dL_dscales[3 * idx + 2] += dscale[2]; }
+            } else {
+                a.dL_dscales[3 * idx] = dscale[0]; a.dL_dscales[3 * idx + 1] = dscale[1]; a.dL_dscales[3 * idx + 2] = dscale[2];
+            }
         }
-        if (a.dL_drots) reinterpret_cast<float4*>(a.dL_drots)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        if (a.dL_drots) {
+            float4* dr4 = reinterpret_cast<float4*>(a.dL_drots) + idx;
+            if (acc & GSR_ACC_ROTS) {
+                if (visible) { const float4 o = *dr4; *dr4 = make_float4(o.x + drot[0], o.y + drot[1], o.z + drot[2], o.w + drot[3]); }
+            } else {
+                *dr4 = make_float4(drot[0], drot[1], drot[2], drot[3]);
+            }
+        }
 
         // ---- SE3 backward (closed form) ----
         float gx[3] = {gm[0], gm[1], gm[2]};
@@ -332,8 +349,17 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
             if (a.dL_dtwist_S) {
                 if (a.deform_mode == GSR_DEFORM_PER_GAUSSIAN) {
 #pragma unroll
-                    for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] = dS6[k];
-                    a.dL_dtwist_theta[idx] = dth;
+                    if (acc & GSR_ACC_TWIST) {
+                        if (visible) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] += dS6[k];
+                            a.dL_dtwist_theta[idx] += dth;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] = dS6[k];
+                        a.dL_dtwist_theta[idx] = dth;
+                    }
                 } else if (visible) {
                     float* dstS = body_smem ? (s_body + 7 * tix) : nullptr;
                     if (body_smem) {
@@ -348,7 +374,11 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                 }
             }
         }
-        a.dL_dmeans3D[3 * idx] = gx[0]; a.dL_dmeans3D[3 * idx + 1] = gx[1]; a.dL_dmeans3D[3 * idx + 2] = gx[2];
+        if (acc & GSR_ACC_MEANS3D) {
+            if (visible) { a.dL_dmeans3D[3 * idx] += gx[0]; a.dL_dmeans3D[3 * idx + 1] += gx[1]; a.dL_dmeans3D[3 * idx + 2] += gx[2]; }
+        } else {
+            a.dL_dmeans3D[3 * idx] = gx[0]; a.dL_dmeans3D[3 * idx + 1] = gx[1]; a.dL_dmeans3D[3 * idx + 2] = gx[2];
+        }
     }
     if (body_smem) {
         __syncthreads();

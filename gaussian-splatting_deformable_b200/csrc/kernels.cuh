@@ -119,7 +119,14 @@ struct PreprocessBwdArgs {
     float* dL_drots;             // [P,4] or null
     float* dL_dtwist_S;          // [P,6] direct, or [B,6] accumulated (pre-zeroed), or null
     float* dL_dtwist_theta;      // [P] or [B] (pre-zeroed), or null
+    int acc;                     // GSR_ACC_* bits: those outputs are accumulated into (`+=`) instead of written
 };
+#define GSR_ACC_MEANS3D 1
+#define GSR_ACC_OPACITY 2
+#define GSR_ACC_SH 4
+#define GSR_ACC_SCALES 8
+#define GSR_ACC_ROTS 16
+#define GSR_ACC_TWIST 32
 int gsr_launch_preprocess_bwd(const PreprocessBwdArgs& a, const GsrView& v, cudaStream_t stream);
 
 // ---- standalone SE3 (rigid_body drop-in) ------------------------------------

@@ -12,6 +12,12 @@ Additions that do not disturb reference call sites (keyword-only, default None):
 exponential-map deformation of scene/rigid_body.py into the preprocess kernel,
 forward and backward.  The deformed means of the last call are available as
 `rasterizer.deformed_means`.
+`accumulate_grads={"means3D": buf, "opacities": buf, "shs": buf, "scales": buf,
+"rotations": buf, "se3_S": buf, "se3_theta": buf}` (any subset): the backward kernel
+adds this view's gradient straight into the given fp32 buffers (e.g. views into one
+flat all-reduce buffer, see view_parallel.FlatGradBuffer) and autograd receives no
+gradient for those inputs - view-batched training then needs no per-view
+accumulation pass.
 """
 from typing import NamedTuple
 
@@ -57,6 +63,9 @@ class _Deform:
         return d
 
 
+_ACC_BITS = {"means3D": 1, "opacities": 2, "shs": 4, "scales": 8, "rotations": 16, "se3_S": 32, "se3_theta": 32}
+
+
 def rasterize_gaussians(
     means3D,
     means2D,
@@ -70,6 +79,7 @@ def rasterize_gaussians(
     se3_S=None,
     se3_theta=None,
     body_id=None,
+    accumulate_grads=None,
 ):
     return _RasterizeGaussians.apply(
         means3D,
@@ -84,6 +94,7 @@ def rasterize_gaussians(
         se3_S,
         se3_theta,
         body_id,
+        accumulate_grads,
     )
 
 
@@ -103,6 +114,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         se3_S=None,
         se3_theta=None,
         body_id=None,
+        accumulate_grads=None,
     ):
         lib = _rt.load()
         if means3D.dim() != 2 or means3D.shape[1] != 3:
@@ -144,6 +156,19 @@ class _RasterizeGaussians(torch.autograd.Function):
                                              binning.numel(), _rt.ptr(img), _rt.ptr(color),
                                              1 if raster_settings.debug else 0, stream))
 
+        acc = dict(accumulate_grads) if accumulate_grads else {}
+        shapes = {"means3D": means3D, "opacities": opacities, "shs": sh, "scales": scales, "rotations": rotations,
+                  "se3_S": se3_S, "se3_theta": se3_theta}
+        for k, buf in acc.items():
+            src = shapes.get(k)
+            if k not in _ACC_BITS or src is None or src.numel() == 0:
+                raise _rt.GsrError("accumulate_grads: no such differentiable input: %r" % k)
+            if (not buf.is_cuda) or buf.dtype != torch.float32 or not buf.is_contiguous() or buf.numel() != src.numel():
+                raise _rt.GsrError("accumulate_grads[%r] must be a contiguous CUDA float32 tensor of %d elements"
+                                   % (k, src.numel()))
+        if ("se3_S" in acc) != ("se3_theta" in acc):
+            raise _rt.GsrError("accumulate_grads: give both se3_S and se3_theta or neither")
+        ctx.acc = acc
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered
         ctx.M = M
@@ -175,23 +200,32 @@ class _RasterizeGaussians(torch.autograd.Function):
         M = ctx.M
         has_sh, has_colors, has_scales, has_cov = ctx.flags
         f32 = dict(dtype=torch.float32, device=dev)
-        grad_means3D = torch.empty((P, 3), **f32)
+        acc = ctx.acc
+        mask = 0
+        for k in acc:
+            mask |= _ACC_BITS[k]
+
+        def out(key, shape, needed=True):
+            if not needed:
+                return None
+            return acc[key] if key in acc else torch.empty(shape, **f32)
+        grad_means3D = out("means3D", (P, 3))
         grad_means2D = torch.empty((P, 3), **f32)
-        grad_opacities = torch.empty((P, 1), **f32)
+        grad_opacities = out("opacities", (P, 1))
         grad_colors = torch.empty((P, 3), **f32)
         grad_cov3D = torch.empty((P, 6), **f32)
-        grad_sh = torch.empty((P, M, 3), **f32) if has_sh else None
-        grad_scales = torch.empty((P, 3), **f32) if has_scales else None
-        grad_rots = torch.empty((P, 4), **f32) if has_scales else None
+        grad_sh = out("shs", (P, M, 3), has_sh)
+        grad_scales = out("scales", (P, 3), has_scales)
+        grad_rots = out("rotations", (P, 4), has_scales)
         grad_S = grad_theta = None
         deform = _Deform(tw_S if ctx.deform_mode else None, tw_theta if ctx.deform_mode else None,
                          body_id if ctx.deform_mode == _rt.DEFORM_RIGID_BODIES else None)
         if ctx.deform_mode == _rt.DEFORM_PER_GAUSSIAN:
-            grad_S = torch.empty((P, 6), **f32)
-            grad_theta = torch.empty((P,), **f32)
-        elif ctx.deform_mode == _rt.DEFORM_RIGID_BODIES:
-            grad_S = torch.zeros((ctx.num_bodies, 6), **f32)
-            grad_theta = torch.zeros((ctx.num_bodies,), **f32)
+            grad_S = out("se3_S", (P, 6))
+            grad_theta = out("se3_theta", (P,))
+        elif ctx.deform_mode == _rt.DEFORM_RIGID_BODIES:     # the kernel always accumulates body twists
+            grad_S = acc["se3_S"] if "se3_S" in acc else torch.zeros((ctx.num_bodies, 6), **f32)
+            grad_theta = acc["se3_theta"] if "se3_theta" in acc else torch.zeros((ctx.num_bodies,), **f32)
         if P != 0:
             g = grad_out_color
             if g.dtype != torch.float32:
@@ -205,20 +239,23 @@ class _RasterizeGaussians(torch.autograd.Function):
                     deform.c_struct(), _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning), _rt.ptr(img), _rt.ptr(grad_ws),
                     _rt.ptr(g), _rt.ptr(grad_means3D), _rt.ptr(grad_means2D), _rt.ptr(grad_opacities),
                     _rt.ptr(grad_colors), _rt.ptr(grad_cov3D), _rt.ptr(grad_sh), _rt.ptr(grad_scales),
-                    _rt.ptr(grad_rots), _rt.ptr(grad_S), _rt.ptr(grad_theta), _rt.stream_ptr(dev)))
+                    _rt.ptr(grad_rots), _rt.ptr(grad_S), _rt.ptr(grad_theta), mask, _rt.stream_ptr(dev)))
         # Same order as the reference (__init__.py:143-153), then the SE3 extras.
+        def ret(key, g):          # inputs whose gradient was accumulated in place get None from autograd
+            return None if key in acc else g
         grads = (
-            grad_means3D,
+            ret("means3D", grad_means3D),
             grad_means2D,
-            grad_sh,
+            ret("shs", grad_sh),
             grad_colors if has_colors else None,
-            grad_opacities,
-            grad_scales,
-            grad_rots,
+            ret("opacities", grad_opacities),
+            ret("scales", grad_scales),
+            ret("rotations", grad_rots),
             grad_cov3D if has_cov else None,
             None,
-            grad_S,
-            grad_theta,
+            ret("se3_S", grad_S),
+            ret("se3_theta", grad_theta),
+            None,
             None,
         )
         return grads
@@ -263,7 +300,7 @@ class GaussianRasterizer(nn.Module):
         return visible
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, *, se3_S=None, se3_theta=None, body_id=None):
+                cov3D_precomp=None, *, se3_S=None, se3_theta=None, body_id=None, accumulate_grads=None):
         raster_settings = self.raster_settings
 
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -291,6 +328,7 @@ class GaussianRasterizer(nn.Module):
             se3_S,
             se3_theta,
             body_id,
+            accumulate_grads,
         )
         self.deformed_means = _RasterizeGaussians.last_deformed_means
         return out

@@ -72,7 +72,7 @@ _SIGNATURES = {
     "gsr_backward": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                     _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
                                     _P, _P, _P, _P, _P,
-                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
     "gsr_debug_blend_stats": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P]),
     "gsr_mark_visible": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, _P, _P, _P]),
     "gsr_knn_bytes": (ctypes.c_size_t, [ctypes.c_int]),

@@ -128,7 +128,11 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t num_rendered,
  * dL_dout_color[3,H,W] -> gradients.  Every output element is written (no
  * pre-zeroing needed) except dL_dtwist_* in rigid-body mode, which are
  * ACCUMULATED into and must be zeroed by the caller.  Outputs may be NULL when
- * the corresponding input was absent (dL_dsh, dL_dscales, dL_drots, dL_dtwist_*). */
+ * the corresponding input was absent (dL_dsh, dL_dscales, dL_drots, dL_dtwist_*).
+ * accumulate_mask: for the outputs whose bit is set (1 means3D, 2 opacity, 4 sh, 8 scales,
+ * 16 rotations, 32 per-Gaussian twists) the buffer is the caller's running gradient and is
+ * accumulated into (`+=`; Gaussians culled in this view are not touched) - this is how
+ * view-batched training sums gradients over views without a separate accumulation pass. */
 int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
                  const float* means3D, const float* means_deformed,
                  const float* scales, const float* rotations, const float* shs,
@@ -138,7 +142,7 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
                  void* grad_ws, const float* dL_dout_color,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dopacity, float* dL_dcolors,
                  float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
-                 float* dL_dtwist_S, float* dL_dtwist_theta, void* stream);
+                 float* dL_dtwist_S, float* dL_dtwist_theta, int accumulate_mask, void* stream);
 
 /* Debug/measurement aid: replays the blend loop of a finished forward and writes 8
  * workload counters (device u64[8]): staged entries, tile-cull survivors,

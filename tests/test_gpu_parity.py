@@ -356,3 +356,39 @@ def test_full_size_properties_c2():
     nz = cnt > 0
     assert bool((tile[rg[nz, 0]] == torch.nonzero(nz).flatten()).all())
     assert torch.isfinite(m["color"]).all() and float(m["final_T"].min()) >= 0.0 and float(m["final_T"].max()) <= 1.0
+
+
+def test_accumulate_grads_matches_autograd_sum():
+    """View-batched training: the backward kernel adds each view's gradient straight into a flat
+    buffer (view_parallel.FlatGradBuffer).  Must equal autograd's own accumulation over views."""
+    import synthetic
+    import view_parallel as vp
+    from _gpu_util import make_view_settings, rel_to_max
+    from diff_gaussian_rasterization import GaussianRasterizer
+    P, W, H, V = 50000, 320, 240, 3
+    sc, _, _ = make_view_settings(P, W, H, scale_mult=1.5)
+    S, th = synthetic.make_twists(P, device="cuda")
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    bg = torch.zeros(3, device="cuda")
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+
+    def run(accumulate):
+        leaves = {k: sc[k].clone().requires_grad_(True) for k in names}
+        leaves["se3_S"], leaves["se3_theta"] = S.clone().requires_grad_(True), th.clone().requires_grad_(True)
+        buf = vp.FlatGradBuffer(list(leaves.values())) if accumulate else None
+        sinks = {k: v.grad for k, v in leaves.items()} if accumulate else None
+        for k in range(V):
+            cam = synthetic.make_camera(k, 8, W, H, device="cuda")
+            rs = synthetic.raster_settings(cam, bg)
+            m2d = torch.zeros(P, 3, device="cuda", requires_grad=True)
+            color, _ = GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                              shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                                              se3_S=leaves["se3_S"], se3_theta=leaves["se3_theta"], accumulate_grads=sinks)
+            (color * grad).sum().backward()
+        if accumulate:      # .grad tensors are still the views into the flat buffer
+            assert all(v.grad.data_ptr() >= buf.flat.data_ptr() for v in leaves.values())
+            assert buf.flat.numel() == P * 66
+        return {k: v.grad.clone() for k, v in leaves.items()}
+    a, b = run(True), run(False)
+    for k in a:
+        assert rel_to_max(a[k], b[k]) <= GRAD_TOL, k
