@@ -361,8 +361,10 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
     GsrView v;
     if (int rc = fill_view(view, M, v)) return rc;
     if (!means3D || !radii || !geom_ws || !image_ws || !grad_ws || !dL_dout_color || !dL_dmeans3D || !dL_dmeans2D ||
-        !dL_dopacity || !dL_dcolors || !dL_dcov3D)
+        !dL_dopacity)
         return gsr_set_error_msg(-1, "backward: required pointer is NULL");
+    if ((colors_precomp && !dL_dcolors) || (cov3D_precomp && !dL_dcov3D))
+        return gsr_set_error_msg(-1, "backward: gradient buffer for a precomputed input is NULL");
     if (shs && !dL_dsh) return gsr_set_error_msg(-1, "backward: dL_dsh required when shs given");
     const GeomLayout L = geom_layout(P);
     const ImageLayout IL = image_layout(v.W, v.H);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         const int acc = a.acc;
         if (acc & GSR_ACC_OPACITY) { if (visible) a.dL_dopacity[idx] += g1.y; }
         else a.dL_dopacity[idx] = g1.y;
-        a.dL_dcolors[3 * idx] = g1.z; a.dL_dcolors[3 * idx + 1] = g1.w; a.dL_dcolors[3 * idx + 2] = g2x;
+        if (a.dL_dcolors) { a.dL_dcolors[3 * idx] = g1.z; a.dL_dcolors[3 * idx + 1] = g1.w; a.dL_dcolors[3 * idx + 2] = g2x; }
 
         float dcov[6] = {0, 0, 0, 0, 0, 0};
         float dscale[3] = {0, 0, 0};
@@ -156,16 +156,18 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                 const float* shp = a.shs + (size_t)idx * M * 3;
                 float* dsh = a.dL_dsh + (size_t)idx * M * 3;
                 const int deg = v.sh_degree;
-                // The 192-byte SH record as 12 x LDG.128 (M == 16), straight into registers.
+                // The 192-byte SH record as 6 x LDG.256 (M == 16), straight into registers.
                 float shv[48];
-                if (M == 16) {
-                    const float4* b4 = reinterpret_cast<const float4*>(shp);
+                const bool wide = (M == 16) && (((reinterpret_cast<uintptr_t>(a.shs) | reinterpret_cast<uintptr_t>(a.dL_dsh)) & 31) == 0);
+                if (wide) {
                     const int need = (deg + 1) * (deg + 1) * 3;
 #pragma unroll
-                    for (int k = 0; k < 12; k++) {
-                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (4 * k < need) t4 = __ldg(b4 + k);
-                        shv[4 * k] = t4.x; shv[4 * k + 1] = t4.y; shv[4 * k + 2] = t4.z; shv[4 * k + 3] = t4.w;
+                    for (int k = 0; k < 6; k++) {
+                        if (8 * k < need) ld256_nc(shp + 8 * k, shv + 8 * k);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 8; e++) shv[8 * k + e] = 0.0f;
+                        }
                     }
                 } else {
 #pragma unroll
@@ -213,19 +215,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                         }
                     }
                 }
-                // dL_dsh record: 48 floats as 12 x STG.128 (element e of the record = coef[e/3] * dRGB[e%3])
+                // dL_dsh record: 48 floats as 6 x STG.256 (element e of the record = coef[e/3] * dRGB[e%3])
                 const float dr[3] = {dRGB.x, dRGB.y, dRGB.z};
-                if (M == 16) {
-                    float4* d4 = reinterpret_cast<float4*>(dsh);
+                if (wide) {
 #pragma unroll
-                    for (int k = 0; k < 12; k++) {
-                        float4 o;
-                        o.x = coef[(4 * k) / 3] * dr[(4 * k) % 3];
-                        o.y = coef[(4 * k + 1) / 3] * dr[(4 * k + 1) % 3];
-                        o.z = coef[(4 * k + 2) / 3] * dr[(4 * k + 2) % 3];
-                        o.w = coef[(4 * k + 3) / 3] * dr[(4 * k + 3) % 3];
-                        if (acc & GSR_ACC_SH) { const float4 old = d4[k]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                        d4[k] = o;
+                    for (int k = 0; k < 6; k++) {
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) o[e] = coef[(8 * k + e) / 3] * dr[(8 * k + e) % 3];
+                        if (acc & GSR_ACC_SH) {
+                            float old[8];
+                            ld256(dsh + 8 * k, old);
+#pragma unroll
+                            for (int e = 0; e < 8; e++) o[e] += old[e];
+                        }
+                        st256(dsh + 8 * k, o);
                     }
                 } else {
                     for (int e = 0; e < M * 3; e++) dsh[e] = coef[e / 3] * dr[e % 3] + ((acc & GSR_ACC_SH) ? dsh[e] : 0.0f);
@@ -280,16 +284,18 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
             }
         } else if (a.dL_dsh && !(a.acc & GSR_ACC_SH)) {
             float* dsh = a.dL_dsh + (size_t)idx * M * 3;
-            if (M == 16) {
-                float4* d4 = reinterpret_cast<float4*>(dsh);
+            if (M == 16 && ((reinterpret_cast<uintptr_t>(a.dL_dsh) & 31) == 0)) {
+                const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int k = 0; k < 12; k++) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 6; k++) st256(dsh + 8 * k, z8);
             } else {
                 for (int k = 0; k < M * 3; k++) dsh[k] = 0.0f;
             }
         }
+        if (a.dL_dcov3D) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+            for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+        }
         if (a.dL_dscales) {
             if (acc & GSR_ACC_SCALES) {
                 if (visible) { a.dL_dscales[3 * idx] += dscale[0]; a.dL_dscales[3 * idx + 1] += dscale[1]; a.dL_dscales[3 * idx + 2] += dscale[2]; }

@@ -71,6 +71,25 @@ struct GsrProfScope {
 
 static inline int gsr_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// 256-bit global loads/stores (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256).  A thread that
+// owns a 32-byte-aligned chunk moves one whole DRAM sector per instruction, so AoS
+// records (192-byte SH, its gradient) are read without the L2->L1 sector re-fetch that
+// 16-byte accesses to the same sector from different instructions cause.
+__device__ __forceinline__ void ld256_nc(const float* p, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ld256(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // SE3 exponential map applied to a point (closed form of rigid_body.exp_se3
 // followed by y = (T [x;1])[:3]):

@@ -96,19 +96,15 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a, G
                 if (a.colors_precomp) {
                     rgb = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
                 } else {
-                    // 192-byte SH record as 12 x LDG.128 (M == 16), scalar otherwise.
+                    // 192-byte SH record as 6 x LDG.256 (M == 16, 32-byte aligned), scalar otherwise.
                     float shv[48];
                     const int M = v.sh_coeffs;
                     const int need = (v.sh_degree + 1) * (v.sh_degree + 1) * 3;
                     const float* base = a.shs + (size_t)idx * M * 3;
-                    if (M == 16) {
-                        const float4* b4 = reinterpret_cast<const float4*>(base);
+                    if (M == 16 && ((reinterpret_cast<uintptr_t>(a.shs) & 31) == 0)) {
 #pragma unroll
-                        for (int k = 0; k < 12; k++) {
-                            if (4 * k < need) {
-                                const float4 t4 = __ldg(b4 + k);
-                                shv[4 * k] = t4.x; shv[4 * k + 1] = t4.y; shv[4 * k + 2] = t4.z; shv[4 * k + 3] = t4.w;
-                            }
+                        for (int k = 0; k < 6; k++) {
+                            if (8 * k < need) ld256_nc(base + 8 * k, shv + 8 * k);
                         }
                     } else {
 #pragma unroll

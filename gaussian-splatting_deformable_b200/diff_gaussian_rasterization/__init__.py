@@ -212,8 +212,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_means3D = out("means3D", (P, 3))
         grad_means2D = torch.empty((P, 3), **f32)
         grad_opacities = out("opacities", (P, 1))
-        grad_colors = torch.empty((P, 3), **f32)
-        grad_cov3D = torch.empty((P, 6), **f32)
+        grad_colors = torch.empty((P, 3), **f32) if has_colors else None
+        grad_cov3D = torch.empty((P, 6), **f32) if has_cov else None
         grad_sh = out("shs", (P, M, 3), has_sh)
         grad_scales = out("scales", (P, 3), has_scales)
         grad_rots = out("rotations", (P, 4), has_scales)

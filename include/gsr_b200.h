@@ -128,7 +128,8 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t num_rendered,
  * dL_dout_color[3,H,W] -> gradients.  Every output element is written (no
  * pre-zeroing needed) except dL_dtwist_* in rigid-body mode, which are
  * ACCUMULATED into and must be zeroed by the caller.  Outputs may be NULL when
- * the corresponding input was absent (dL_dsh, dL_dscales, dL_drots, dL_dtwist_*).
+ * the corresponding input was absent (dL_dsh, dL_dscales, dL_drots, dL_dtwist_*; dL_dcolors and
+ * dL_dcov3D are only needed with precomputed colours / covariances).
  * accumulate_mask: for the outputs whose bit is set (1 means3D, 2 opacity, 4 sh, 8 scales,
  * 16 rotations, 32 per-Gaussian twists) the buffer is the caller's running gradient and is
  * accumulated into (`+=`; Gaussians culled in this view are not touched) - this is how
