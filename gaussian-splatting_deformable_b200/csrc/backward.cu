@@ -42,6 +42,17 @@ __device__ __forceinline__ void store_sh(float* dst, int k, V3 g) {
     dst[3 * k] = g.x; dst[3 * k + 1] = g.y; dst[3 * k + 2] = g.z;
 }
 
+// Output of one value: plain store, or (accumulate mode) a fire-and-forget RED so that
+// no load of the running gradient sits in the thread's dependency chain.
+__device__ __forceinline__ void emit(float* p, float val, bool accumulate) {
+    if (accumulate) atomicAdd(p, val); else *p = val;
+}
+
+// Structure: ONE dependent chain of two DRAM round trips per thread.  (1) radii -> visible;
+// (2) every input of a visible Gaussian is loaded back to back (gradient record, mean, scale,
+// quaternion, clamp bits, the 192-byte SH record as 6 x LDG.256, twist) BEFORE the first store -
+// a store to a non-restrict pointer would otherwise pin all later loads behind it; (3) math;
+// (4) all stores.  Accumulate mode uses vector reductions (RED.ADD.F32x4 for the SH gradient).
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a, GsrView v) {
     extern __shared__ float s_body[];   // [num_bodies][7] when accumulating rigid-body twists in smem
     const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -51,238 +62,18 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         __syncthreads();
     }
     const int M = v.sh_coeffs;
-    float gm[3] = {0.f, 0.f, 0.f};         // dL/d(deformed mean)
-    bool visible = false;
-    if (idx < a.P) {
-        visible = a.radii[idx] > 0;
-        const float4* gr = a.grad_recs + 3 * (size_t)idx;
-        float4 g0 = make_float4(0, 0, 0, 0), g1 = g0;
-        float g2x = 0.0f;
-        if (visible) { g0 = gr[0]; g1 = gr[1]; g2x = reinterpret_cast<const float*>(gr + 2)[0]; }
-        // pass-through outputs
-        a.dL_dmeans2D[3 * idx] = g0.x; a.dL_dmeans2D[3 * idx + 1] = g0.y; a.dL_dmeans2D[3 * idx + 2] = 0.0f;
-        // Accumulate mode (a.acc bit set): the output is the caller's running gradient
-        // (`+=`, culled Gaussians untouched) instead of a fresh tensor - the separate
-        // elementwise accumulation pass over 264 B/Gaussian per extra view disappears.
-        const int acc = a.acc;
-        if (acc & GSR_ACC_OPACITY) { if (visible) a.dL_dopacity[idx] += g1.y; }
-        else a.dL_dopacity[idx] = g1.y;
-        if (a.dL_dcolors) { a.dL_dcolors[3 * idx] = g1.z; a.dL_dcolors[3 * idx + 1] = g1.w; a.dL_dcolors[3 * idx + 2] = g2x; }
-
-        float dcov[6] = {0, 0, 0, 0, 0, 0};
-        float dscale[3] = {0, 0, 0};
-        float drot[4] = {0, 0, 0, 0};
-        const float* mp = (a.means_deformed ? a.means_deformed : a.means) + 3 * (size_t)idx;
-        const float3 mean = make_float3(mp[0], mp[1], mp[2]);
-        if (visible) {
-            // ---- computeCov2DCUDA (backward.cu:144-274) ----
-            float cov6[6];
-            float3 s = make_float3(0, 0, 0);
-            float4 q = make_float4(0, 0, 0, 0);
-            if (a.cov3D_precomp) {
+    const int acc = a.acc;
+    const bool visible = (idx < a.P) && (a.radii[idx] > 0);
+    if (idx < a.P && !visible) {
+        // Culled: zeros to every output that is not a running sum; nothing is read.
+        a.dL_dmeans2D[3 * idx] = 0.0f; a.dL_dmeans2D[3 * idx + 1] = 0.0f; a.dL_dmeans2D[3 * idx + 2] = 0.0f;
+        if (!(acc & GSR_ACC_OPACITY)) a.dL_dopacity[idx] = 0.0f;
+        if (a.dL_dcolors) { a.dL_dcolors[3 * idx] = 0.0f; a.dL_dcolors[3 * idx + 1] = 0.0f; a.dL_dcolors[3 * idx + 2] = 0.0f; }
+        if (a.dL_dcov3D) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_precomp[6 * (size_t)idx + k];
-            } else {
-                s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-                q = reinterpret_cast<const float4*>(a.rotations)[idx];
-                cov3d_exact(s, v.scale_modifier, q, cov6);   // recomputed: saves a 24 B/Gaussian round trip
-            }
-            float3 t = make_float3(xform_row(v.view, 0, mean), xform_row(v.view, 1, mean), xform_row(v.view, 2, mean));
-            const float limx = 1.3f * v.tan_fovx, limy = 1.3f * v.tan_fovy;
-            const float txtz = t.x / t.z, tytz = t.y / t.z;
-            const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
-            const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
-            const EwaT e = ewa_T_exact(t, v);
-            t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
-            t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
-            const float3 cov = cov2d_exact(e, cov6);
-            const float ca = cov.x, cb = cov.y, cc = cov.z;
-            const float denom = ca * cc - cb * cb;
-            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-            const float dcx = g0.z, dcy = g0.w, dcz = g1.x;   // dL_dconic (xx, xy, yy)
-            float dL_da = 0, dL_db = 0, dL_dc = 0;
-            // glm column-major T[c][r]: T[0][*] = (T00,T01,T02), T[1][*] = (T10,T11,T12)
-            const float T00 = e.T00, T01 = e.T01, T02 = e.T02, T10 = e.T10, T11 = e.T11, T12 = e.T12;
-            if (denom2inv != 0) {
-                dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
-                dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
-                dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
-                dcov[0] = (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
-                dcov[3] = (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
-                dcov[5] = (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
-                dcov[1] = 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
-                dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
-                dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
-            }
-            // Vrk (symmetric) rows
-            const float V00 = cov6[0], V01 = cov6[1], V02 = cov6[2], V11 = cov6[3], V12 = cov6[4], V22 = cov6[5];
-            const float dL_dT00 = 2 * (T00 * V00 + T01 * V01 + T02 * V02) * dL_da + (T10 * V00 + T11 * V01 + T12 * V02) * dL_db;
-            const float dL_dT01 = 2 * (T00 * V01 + T01 * V11 + T02 * V12) * dL_da + (T10 * V01 + T11 * V11 + T12 * V12) * dL_db;
-            const float dL_dT02 = 2 * (T00 * V02 + T01 * V12 + T02 * V22) * dL_da + (T10 * V02 + T11 * V12 + T12 * V22) * dL_db;
-            const float dL_dT10 = 2 * (T10 * V00 + T11 * V01 + T12 * V02) * dL_dc + (T00 * V00 + T01 * V01 + T02 * V02) * dL_db;
-            const float dL_dT11 = 2 * (T10 * V01 + T11 * V11 + T12 * V12) * dL_dc + (T00 * V01 + T01 * V11 + T02 * V12) * dL_db;
-            const float dL_dT12 = 2 * (T10 * V02 + T11 * V12 + T12 * V22) * dL_dc + (T00 * V02 + T01 * V12 + T02 * V22) * dL_db;
-            // W[c][r] = view[c + 4 r]
-            const float* Vm = v.view;
-            const float dL_dJ00 = Vm[0] * dL_dT00 + Vm[4] * dL_dT01 + Vm[8] * dL_dT02;
-            const float dL_dJ02 = Vm[2] * dL_dT00 + Vm[6] * dL_dT01 + Vm[10] * dL_dT02;
-            const float dL_dJ11 = Vm[1] * dL_dT10 + Vm[5] * dL_dT11 + Vm[9] * dL_dT12;
-            const float dL_dJ12 = Vm[2] * dL_dT10 + Vm[6] * dL_dT11 + Vm[10] * dL_dT12;
-            const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
-            const float h_x = v.focal_x, h_y = v.focal_y;
-            const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
-            const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
-            const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
-                                 (2 * h_y * t.y) * tz3 * dL_dJ12;
-            // transformVec4x3Transpose (auxiliary.h:89-97)
-            gm[0] = Vm[0] * dL_dtx + Vm[1] * dL_dty + Vm[2] * dL_dtz;
-            gm[1] = Vm[4] * dL_dtx + Vm[5] * dL_dty + Vm[6] * dL_dtz;
-            gm[2] = Vm[8] * dL_dtx + Vm[9] * dL_dty + Vm[10] * dL_dtz;
-
-            // ---- projection part (backward.cu:370-387) ----
-            const float* proj = v.proj;
-            const float m_hom_w = proj[3] * mean.x + proj[7] * mean.y + proj[11] * mean.z + proj[15];
-            const float m_w = 1.0f / (m_hom_w + 0.0000001f);
-            const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
-            const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-            gm[0] += (proj[0] * m_w - proj[3] * mul1) * g0.x + (proj[1] * m_w - proj[3] * mul2) * g0.y;
-            gm[1] += (proj[4] * m_w - proj[7] * mul1) * g0.x + (proj[5] * m_w - proj[7] * mul2) * g0.y;
-            gm[2] += (proj[8] * m_w - proj[11] * mul1) * g0.x + (proj[9] * m_w - proj[11] * mul2) * g0.y;
-
-            // ---- SH backward (backward.cu:20-139) ----
-            if (a.shs) {
-                const uint8_t cl = a.clamped[idx];
-                V3 dRGB = {(cl & 1) ? 0.0f : g1.z, (cl & 2) ? 0.0f : g1.w, (cl & 4) ? 0.0f : g2x};
-                const float* shp = a.shs + (size_t)idx * M * 3;
-                float* dsh = a.dL_dsh + (size_t)idx * M * 3;
-                const int deg = v.sh_degree;
-                // The 192-byte SH record as 6 x LDG.256 (M == 16), straight into registers.
-                float shv[48];
-                const bool wide = (M == 16) && (((reinterpret_cast<uintptr_t>(a.shs) | reinterpret_cast<uintptr_t>(a.dL_dsh)) & 31) == 0);
-                if (wide) {
-                    const int need = (deg + 1) * (deg + 1) * 3;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        if (8 * k < need) ld256_nc(shp + 8 * k, shv + 8 * k);
-                        else {
-#pragma unroll
-                            for (int e = 0; e < 8; e++) shv[8 * k + e] = 0.0f;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 48; k++) shv[k] = (k < M * 3) ? shp[k] : 0.0f;
-                }
-                auto sh = [&](int k) -> V3 { return {shv[3 * k], shv[3 * k + 1], shv[3 * k + 2]}; };
-                V3 dir_orig = {mean.x - v.campos[0], mean.y - v.campos[1], mean.z - v.campos[2]};
-                const float len = sqrtf(dot(dir_orig, dir_orig));
-                const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-                V3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
-                // dRGB/dsh_k is a scalar per coefficient: dL_dsh[k] = coef[k] * dL_dRGB
-                float coef[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) coef[k] = 0.0f;
-                coef[0] = bSH_C0;
-                if (deg > 0) {
-                    coef[1] = -bSH_C1 * y; coef[2] = bSH_C1 * z; coef[3] = -bSH_C1 * x;
-                    dRGBdx = (-bSH_C1) * sh(3);
-                    dRGBdy = (-bSH_C1) * sh(1);
-                    dRGBdz = bSH_C1 * sh(2);
-                    if (deg > 1) {
-                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                        coef[4] = bSH_C2[0] * xy; coef[5] = bSH_C2[1] * yz; coef[6] = bSH_C2[2] * (2.f * zz - xx - yy);
-                        coef[7] = bSH_C2[3] * xz; coef[8] = bSH_C2[4] * (xx - yy);
-                        const V3 s4 = sh(4), s5 = sh(5), s6 = sh(6), s7 = sh(7), s8 = sh(8);
-                        dRGBdx = dRGBdx + (bSH_C2[0] * y) * s4 + (bSH_C2[2] * 2.f * -x) * s6 + (bSH_C2[3] * z) * s7 + (bSH_C2[4] * 2.f * x) * s8;
-                        dRGBdy = dRGBdy + (bSH_C2[0] * x) * s4 + (bSH_C2[1] * z) * s5 + (bSH_C2[2] * 2.f * -y) * s6 + (bSH_C2[4] * 2.f * -y) * s8;
-                        dRGBdz = dRGBdz + (bSH_C2[1] * y) * s5 + (bSH_C2[2] * 2.f * 2.f * z) * s6 + (bSH_C2[3] * x) * s7;
-                        if (deg > 2) {
-                            coef[9] = bSH_C3[0] * y * (3.f * xx - yy); coef[10] = bSH_C3[1] * xy * z;
-                            coef[11] = bSH_C3[2] * y * (4.f * zz - xx - yy);
-                            coef[12] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-                            coef[13] = bSH_C3[4] * x * (4.f * zz - xx - yy); coef[14] = bSH_C3[5] * z * (xx - yy);
-                            coef[15] = bSH_C3[6] * x * (xx - 3.f * yy);
-                            const V3 s9 = sh(9), s10 = sh(10), s11 = sh(11), s12 = sh(12), s13 = sh(13), s14 = sh(14), s15 = sh(15);
-                            dRGBdx = dRGBdx + (bSH_C3[0] * 3.f * 2.f * xy) * s9 + (bSH_C3[1] * yz) * s10 + (bSH_C3[2] * -2.f * xy) * s11 +
-                                     (bSH_C3[3] * -3.f * 2.f * xz) * s12 + (bSH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * s13 +
-                                     (bSH_C3[5] * 2.f * xz) * s14 + (bSH_C3[6] * 3.f * (xx - yy)) * s15;
-                            dRGBdy = dRGBdy + (bSH_C3[0] * 3.f * (xx - yy)) * s9 + (bSH_C3[1] * xz) * s10 +
-                                     (bSH_C3[2] * (-3.f * yy + 4.f * zz - xx)) * s11 + (bSH_C3[3] * -3.f * 2.f * yz) * s12 +
-                                     (bSH_C3[4] * -2.f * xy) * s13 + (bSH_C3[5] * -2.f * yz) * s14 + (bSH_C3[6] * -3.f * 2.f * xy) * s15;
-                            dRGBdz = dRGBdz + (bSH_C3[1] * xy) * s10 + (bSH_C3[2] * 4.f * 2.f * yz) * s11 +
-                                     (bSH_C3[3] * 3.f * (2.f * zz - xx - yy)) * s12 + (bSH_C3[4] * 4.f * 2.f * xz) * s13 +
-                                     (bSH_C3[5] * (xx - yy)) * s14;
-                        }
-                    }
-                }
-                // dL_dsh record: 48 floats as 6 x STG.256 (element e of the record = coef[e/3] * dRGB[e%3])
-                const float dr[3] = {dRGB.x, dRGB.y, dRGB.z};
-                if (wide) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        float o[8];
-#pragma unroll
-                        for (int e = 0; e < 8; e++) o[e] = coef[(8 * k + e) / 3] * dr[(8 * k + e) % 3];
-                        if (acc & GSR_ACC_SH) {
-                            float old[8];
-                            ld256(dsh + 8 * k, old);
-#pragma unroll
-                            for (int e = 0; e < 8; e++) o[e] += old[e];
-                        }
-                        st256(dsh + 8 * k, o);
-                    }
-                } else {
-                    for (int e = 0; e < M * 3; e++) dsh[e] = coef[e / 3] * dr[e % 3] + ((acc & GSR_ACC_SH) ? dsh[e] : 0.0f);
-                }
-                const V3 dL_ddir = {dot(dRGBdx, dRGB), dot(dRGBdy, dRGB), dot(dRGBdz, dRGB)};
-                const V3 dmean_sh = dnormvdv(dir_orig, dL_ddir);
-                gm[0] += dmean_sh.x; gm[1] += dmean_sh.y; gm[2] += dmean_sh.z;
-            }
-
-            // ---- cov3D backward (backward.cu:278-341) ----
-            if (a.scales) {
-                const float r = q.x, x = q.y, y = q.z, z = q.w;
-                // R as glm columns; Rt[k] = row k of that column-major matrix (= column k of transpose)
-                const float R[3][3] = {
-                    {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-                    {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-                    {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};   // R[c][r']
-                const float sv[3] = {v.scale_modifier * s.x, v.scale_modifier * s.y, v.scale_modifier * s.z};
-                float Mm[3][3];     // M = S * R : M[c][r'] = sv[r'] * R[c][r']
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int rr = 0; rr < 3; rr++) Mm[c][rr] = sv[rr] * R[c][rr];
-                // dL_dSigma (column-major, symmetric)
-                const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
-                                        {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
-                                        {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-                // dL_dM = 2 * M * dL_dSigma  (glm product: (A*B)[c][r'] = sum_k A[k][r'] B[c][k])
-                float dM[3][3];
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int rr = 0; rr < 3; rr++)
-                        dM[c][rr] = 2.0f * (Mm[0][rr] * dS[c][0] + Mm[1][rr] * dS[c][1] + Mm[2][rr] * dS[c][2]);
-                // Rt = transpose(R): Rt[k][j] = R[j][k];  dL_dMt[k][j] = dM[j][k]
-                float dMt[3][3];
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-#pragma unroll
-                    for (int j = 0; j < 3; j++) dMt[k][j] = dM[j][k];
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    dscale[k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-#pragma unroll
-                    for (int j = 0; j < 3; j++) dMt[k][j] *= sv[k];
-                drot[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
-                drot[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
-                drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
-                drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
-            }
-        } else if (a.dL_dsh && !(a.acc & GSR_ACC_SH)) {
+            for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = 0.0f;
+        }
+        if (a.dL_dsh && !(acc & GSR_ACC_SH)) {
             float* dsh = a.dL_dsh + (size_t)idx * M * 3;
             if (M == 16 && ((reinterpret_cast<uintptr_t>(a.dL_dsh) & 31) == 0)) {
                 const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -292,99 +83,329 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
                 for (int k = 0; k < M * 3; k++) dsh[k] = 0.0f;
             }
         }
-        if (a.dL_dcov3D) {
+        if (a.dL_dscales && !(acc & GSR_ACC_SCALES)) { a.dL_dscales[3 * idx] = 0.0f; a.dL_dscales[3 * idx + 1] = 0.0f; a.dL_dscales[3 * idx + 2] = 0.0f; }
+        if (a.dL_drots && !(acc & GSR_ACC_ROTS)) reinterpret_cast<float4*>(a.dL_drots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.dL_dtwist_S && a.deform_mode == GSR_DEFORM_PER_GAUSSIAN && !(acc & GSR_ACC_TWIST)) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+            for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] = 0.0f;
+            a.dL_dtwist_theta[idx] = 0.0f;
         }
-        if (a.dL_dscales) {
-            if (acc & GSR_ACC_SCALES) {
-                if (visible) { a.dL_dscales[3 * idx] += dscale[0]; a.dL_dscales[3 * idx + 1] += dscale[1]; a.dL_dscales[3 * idx + 2] += dscale[2]; }
+        if (!(acc & GSR_ACC_MEANS3D)) { a.dL_dmeans3D[3 * idx] = 0.0f; a.dL_dmeans3D[3 * idx + 1] = 0.0f; a.dL_dmeans3D[3 * idx + 2] = 0.0f; }
+    }
+    if (visible) {
+        // ================= (2) all loads =================
+        const float4* gr = a.grad_recs + 3 * (size_t)idx;
+        const float4 g0 = gr[0], g1 = gr[1];
+        const float g2x = reinterpret_cast<const float*>(gr + 2)[0];
+        const float* mp = (a.means_deformed ? a.means_deformed : a.means) + 3 * (size_t)idx;
+        const float3 mean = make_float3(mp[0], mp[1], mp[2]);
+        float cov6[6];
+        float3 s = make_float3(0, 0, 0);
+        float4 q = make_float4(0, 0, 0, 0);
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_precomp[6 * (size_t)idx + k];
+        } else {
+            s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+            q = reinterpret_cast<const float4*>(a.rotations)[idx];
+        }
+        const int deg = v.sh_degree;
+        float shv[48];
+        uint8_t cl = 0;
+        const bool wide = a.shs && (M == 16) &&
+                          (((reinterpret_cast<uintptr_t>(a.shs) | reinterpret_cast<uintptr_t>(a.dL_dsh)) & 31) == 0);
+        if (a.shs) {
+            cl = a.clamped[idx];
+            const float* shp = a.shs + (size_t)idx * M * 3;
+            if (wide) {
+                const int need = (deg + 1) * (deg + 1) * 3;
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    if (8 * k < need) ld256_nc(shp + 8 * k, shv + 8 * k);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) shv[8 * k + e] = 0.0f;
+                    }
+                }
             } else {
-                a.dL_dscales[3 * idx] = dscale[0]; a.dL_dscales[3 * idx + 1] = dscale[1]; a.dL_dscales[3 * idx + 2] = dscale[2];
+#pragma unroll
+                for (int k = 0; k < 48; k++) shv[k] = (k < M * 3) ? shp[k] : 0.0f;
             }
         }
-        if (a.dL_drots) {
-            float4* dr4 = reinterpret_cast<float4*>(a.dL_drots) + idx;
-            if (acc & GSR_ACC_ROTS) {
-                if (visible) { const float4 o = *dr4; *dr4 = make_float4(o.x + drot[0], o.y + drot[1], o.z + drot[2], o.w + drot[3]); }
-            } else {
-                *dr4 = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        const int tix = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) ? a.body_id[idx] : idx;
+        float3 w = make_float3(0, 0, 0), tv = w, x0 = w;
+        float th = 0.0f;
+        if (a.deform_mode != GSR_DEFORM_NONE) {
+            const float* S = a.twist_S + 6 * (size_t)tix;
+            w = make_float3(S[0], S[1], S[2]); tv = make_float3(S[3], S[4], S[5]);
+            th = a.twist_theta[tix];
+            x0 = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
+        }
+
+        // ================= (3) math =================
+        float gm[3];                            // dL/d(deformed mean)
+        float dcov[6] = {0, 0, 0, 0, 0, 0};
+        float dscale[3] = {0, 0, 0};
+        float drot[4] = {0, 0, 0, 0};
+        // ---- computeCov2DCUDA (backward.cu:144-274) ----
+        if (!a.cov3D_precomp) cov3d_exact(s, v.scale_modifier, q, cov6);   // recomputed: saves a 24 B/Gaussian round trip
+        float3 t = make_float3(xform_row(v.view, 0, mean), xform_row(v.view, 1, mean), xform_row(v.view, 2, mean));
+        const float limx = 1.3f * v.tan_fovx, limy = 1.3f * v.tan_fovy;
+        const float txtz = t.x / t.z, tytz = t.y / t.z;
+        const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
+        const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
+        const EwaT e = ewa_T_exact(t, v);
+        t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+        t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+        const float3 cov = cov2d_exact(e, cov6);
+        const float ca = cov.x, cb = cov.y, cc = cov.z;
+        const float denom = ca * cc - cb * cb;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        const float dcx = g0.z, dcy = g0.w, dcz = g1.x;   // dL_dconic (xx, xy, yy)
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        // glm column-major T[c][r]: T[0][*] = (T00,T01,T02), T[1][*] = (T10,T11,T12)
+        const float T00 = e.T00, T01 = e.T01, T02 = e.T02, T10 = e.T10, T11 = e.T11, T12 = e.T12;
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
+            dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
+            dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
+            dcov[0] = (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
+            dcov[3] = (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
+            dcov[5] = (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
+            dcov[1] = 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
+            dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
+            dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
+        }
+        // Vrk (symmetric) rows
+        const float V00 = cov6[0], V01 = cov6[1], V02 = cov6[2], V11 = cov6[3], V12 = cov6[4], V22 = cov6[5];
+        const float dL_dT00 = 2 * (T00 * V00 + T01 * V01 + T02 * V02) * dL_da + (T10 * V00 + T11 * V01 + T12 * V02) * dL_db;
+        const float dL_dT01 = 2 * (T00 * V01 + T01 * V11 + T02 * V12) * dL_da + (T10 * V01 + T11 * V11 + T12 * V12) * dL_db;
+        const float dL_dT02 = 2 * (T00 * V02 + T01 * V12 + T02 * V22) * dL_da + (T10 * V02 + T11 * V12 + T12 * V22) * dL_db;
+        const float dL_dT10 = 2 * (T10 * V00 + T11 * V01 + T12 * V02) * dL_dc + (T00 * V00 + T01 * V01 + T02 * V02) * dL_db;
+        const float dL_dT11 = 2 * (T10 * V01 + T11 * V11 + T12 * V12) * dL_dc + (T00 * V01 + T01 * V11 + T02 * V12) * dL_db;
+        const float dL_dT12 = 2 * (T10 * V02 + T11 * V12 + T12 * V22) * dL_dc + (T00 * V02 + T01 * V12 + T02 * V22) * dL_db;
+        // W[c][r] = view[c + 4 r]
+        const float* Vm = v.view;
+        const float dL_dJ00 = Vm[0] * dL_dT00 + Vm[4] * dL_dT01 + Vm[8] * dL_dT02;
+        const float dL_dJ02 = Vm[2] * dL_dT00 + Vm[6] * dL_dT01 + Vm[10] * dL_dT02;
+        const float dL_dJ11 = Vm[1] * dL_dT10 + Vm[5] * dL_dT11 + Vm[9] * dL_dT12;
+        const float dL_dJ12 = Vm[2] * dL_dT10 + Vm[6] * dL_dT11 + Vm[10] * dL_dT12;
+        const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+        const float h_x = v.focal_x, h_y = v.focal_y;
+        const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+        const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+        const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
+                             (2 * h_y * t.y) * tz3 * dL_dJ12;
+        // transformVec4x3Transpose (auxiliary.h:89-97)
+        gm[0] = Vm[0] * dL_dtx + Vm[1] * dL_dty + Vm[2] * dL_dtz;
+        gm[1] = Vm[4] * dL_dtx + Vm[5] * dL_dty + Vm[6] * dL_dtz;
+        gm[2] = Vm[8] * dL_dtx + Vm[9] * dL_dty + Vm[10] * dL_dtz;
+
+        // ---- projection part (backward.cu:370-387) ----
+        const float* proj = v.proj;
+        const float m_hom_w = proj[3] * mean.x + proj[7] * mean.y + proj[11] * mean.z + proj[15];
+        const float m_w = 1.0f / (m_hom_w + 0.0000001f);
+        const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+        const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+        gm[0] += (proj[0] * m_w - proj[3] * mul1) * g0.x + (proj[1] * m_w - proj[3] * mul2) * g0.y;
+        gm[1] += (proj[4] * m_w - proj[7] * mul1) * g0.x + (proj[5] * m_w - proj[7] * mul2) * g0.y;
+        gm[2] += (proj[8] * m_w - proj[11] * mul1) * g0.x + (proj[9] * m_w - proj[11] * mul2) * g0.y;
+
+        // ---- SH backward (backward.cu:20-139) ----
+        float coef[16];     // dRGB/dsh_k is a scalar per coefficient: dL_dsh[k] = coef[k] * dL_dRGB
+        V3 dRGB = {0, 0, 0};
+        if (a.shs) {
+            dRGB = {(cl & 1) ? 0.0f : g1.z, (cl & 2) ? 0.0f : g1.w, (cl & 4) ? 0.0f : g2x};
+            auto sh = [&](int k) -> V3 { return {shv[3 * k], shv[3 * k + 1], shv[3 * k + 2]}; };
+            V3 dir_orig = {mean.x - v.campos[0], mean.y - v.campos[1], mean.z - v.campos[2]};
+            const float len = sqrtf(dot(dir_orig, dir_orig));
+            const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+            V3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 16; k++) coef[k] = 0.0f;
+            coef[0] = bSH_C0;
+            if (deg > 0) {
+                coef[1] = -bSH_C1 * y; coef[2] = bSH_C1 * z; coef[3] = -bSH_C1 * x;
+                dRGBdx = (-bSH_C1) * sh(3);
+                dRGBdy = (-bSH_C1) * sh(1);
+                dRGBdz = bSH_C1 * sh(2);
+                if (deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    coef[4] = bSH_C2[0] * xy; coef[5] = bSH_C2[1] * yz; coef[6] = bSH_C2[2] * (2.f * zz - xx - yy);
+                    coef[7] = bSH_C2[3] * xz; coef[8] = bSH_C2[4] * (xx - yy);
+                    const V3 s4 = sh(4), s5 = sh(5), s6 = sh(6), s7 = sh(7), s8 = sh(8);
+                    dRGBdx = dRGBdx + (bSH_C2[0] * y) * s4 + (bSH_C2[2] * 2.f * -x) * s6 + (bSH_C2[3] * z) * s7 + (bSH_C2[4] * 2.f * x) * s8;
+                    dRGBdy = dRGBdy + (bSH_C2[0] * x) * s4 + (bSH_C2[1] * z) * s5 + (bSH_C2[2] * 2.f * -y) * s6 + (bSH_C2[4] * 2.f * -y) * s8;
+                    dRGBdz = dRGBdz + (bSH_C2[1] * y) * s5 + (bSH_C2[2] * 2.f * 2.f * z) * s6 + (bSH_C2[3] * x) * s7;
+                    if (deg > 2) {
+                        coef[9] = bSH_C3[0] * y * (3.f * xx - yy); coef[10] = bSH_C3[1] * xy * z;
+                        coef[11] = bSH_C3[2] * y * (4.f * zz - xx - yy);
+                        coef[12] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                        coef[13] = bSH_C3[4] * x * (4.f * zz - xx - yy); coef[14] = bSH_C3[5] * z * (xx - yy);
+                        coef[15] = bSH_C3[6] * x * (xx - 3.f * yy);
+                        const V3 s9 = sh(9), s10 = sh(10), s11 = sh(11), s12 = sh(12), s13 = sh(13), s14 = sh(14), s15 = sh(15);
+                        dRGBdx = dRGBdx + (bSH_C3[0] * 3.f * 2.f * xy) * s9 + (bSH_C3[1] * yz) * s10 + (bSH_C3[2] * -2.f * xy) * s11 +
+                                 (bSH_C3[3] * -3.f * 2.f * xz) * s12 + (bSH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * s13 +
+                                 (bSH_C3[5] * 2.f * xz) * s14 + (bSH_C3[6] * 3.f * (xx - yy)) * s15;
+                        dRGBdy = dRGBdy + (bSH_C3[0] * 3.f * (xx - yy)) * s9 + (bSH_C3[1] * xz) * s10 +
+                                 (bSH_C3[2] * (-3.f * yy + 4.f * zz - xx)) * s11 + (bSH_C3[3] * -3.f * 2.f * yz) * s12 +
+                                 (bSH_C3[4] * -2.f * xy) * s13 + (bSH_C3[5] * -2.f * yz) * s14 + (bSH_C3[6] * -3.f * 2.f * xy) * s15;
+                        dRGBdz = dRGBdz + (bSH_C3[1] * xy) * s10 + (bSH_C3[2] * 4.f * 2.f * yz) * s11 +
+                                 (bSH_C3[3] * 3.f * (2.f * zz - xx - yy)) * s12 + (bSH_C3[4] * 4.f * 2.f * xz) * s13 +
+                                 (bSH_C3[5] * (xx - yy)) * s14;
+                    }
+                }
             }
+            const V3 dL_ddir = {dot(dRGBdx, dRGB), dot(dRGBdy, dRGB), dot(dRGBdz, dRGB)};
+            const V3 dmean_sh = dnormvdv(dir_orig, dL_ddir);
+            gm[0] += dmean_sh.x; gm[1] += dmean_sh.y; gm[2] += dmean_sh.z;
+        }
+
+        // ---- cov3D backward (backward.cu:278-341) ----
+        if (a.scales) {
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            // R as glm columns; Rt[k] = row k of that column-major matrix (= column k of transpose)
+            const float R[3][3] = {
+                {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};   // R[c][r']
+            const float sv[3] = {v.scale_modifier * s.x, v.scale_modifier * s.y, v.scale_modifier * s.z};
+            float Mm[3][3];     // M = S * R : M[c][r'] = sv[r'] * R[c][r']
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) Mm[c][rr] = sv[rr] * R[c][rr];
+            // dL_dSigma (column-major, symmetric)
+            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            // dL_dM = 2 * M * dL_dSigma  (glm product: (A*B)[c][r'] = sum_k A[k][r'] B[c][k])
+            float dM[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++)
+                    dM[c][rr] = 2.0f * (Mm[0][rr] * dS[c][0] + Mm[1][rr] * dS[c][1] + Mm[2][rr] * dS[c][2]);
+            // Rt = transpose(R): Rt[k][j] = R[j][k];  dL_dMt[k][j] = dM[j][k]
+            float dMt[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) dMt[k][j] = dM[j][k];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                dscale[k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) dMt[k][j] *= sv[k];
+            drot[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+            drot[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+            drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+            drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
         }
 
         // ---- SE3 backward (closed form) ----
         float gx[3] = {gm[0], gm[1], gm[2]};
+        float dS6[6] = {0, 0, 0, 0, 0, 0};
+        float dth = 0.0f;
         if (a.deform_mode != GSR_DEFORM_NONE) {
-            const int tix = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) ? a.body_id[idx] : idx;
-            float dS6[6] = {0, 0, 0, 0, 0, 0};
-            float dth = 0.0f;
-            if (visible) {
-                const float* S = a.twist_S + 6 * (size_t)tix;
-                const float3 w = make_float3(S[0], S[1], S[2]), tv = make_float3(S[3], S[4], S[5]);
-                const float th = a.twist_theta[tix];
-                const float3 x0 = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
-                const float3 g = make_float3(gm[0], gm[1], gm[2]);
-                float sn, cs;
-                sincosf(th, &sn, &cs);
-                const float ka = sn, kb = 1.0f - cs, kc = th - sn;
-                const float3 wg = cross3(w, g), wwg = skew2(w, g);
-                // dL/dx = R^T g = g - a (w x g) + b W^2 g
-                gx[0] = g.x - ka * wg.x + kb * wwg.x;
-                gx[1] = g.y - ka * wg.y + kb * wwg.y;
-                gx[2] = g.z - ka * wg.z + kb * wwg.z;
-                // dL/dv = th g - b (w x g) + c W^2 g
-                dS6[3] = th * g.x - kb * wg.x + kc * wwg.x;
-                dS6[4] = th * g.y - kb * wg.y + kc * wwg.y;
-                dS6[5] = th * g.z - kb * wg.z + kc * wwg.z;
-                // dL/dth = g . ( cos (w x x) + sin W^2 x + v + sin (w x v) + (1-cos) W^2 v )
-                const float3 wx = cross3(w, x0), wwx = skew2(w, x0), wv = cross3(w, tv), wwv = skew2(w, tv);
-                dth = g.x * (cs * wx.x + sn * wwx.x + tv.x + sn * wv.x + kb * wwv.x) +
-                      g.y * (cs * wx.y + sn * wwx.y + tv.y + sn * wv.y + kb * wwv.y) +
-                      g.z * (cs * wx.z + sn * wwx.z + tv.z + sn * wv.z + kb * wwv.z);
-                // dL/dw = a (x x g) + b D(x) + b (v x g) + c D(v),  D(u) = g (w.u) + u (w.g) - 2 w (g.u)
-                const float3 xg = cross3(x0, g), vg = cross3(tv, g);
-                const float wdx = dot3(w, x0), wdv = dot3(w, tv), wdg = dot3(w, g), gdx = dot3(g, x0), gdv = dot3(g, tv);
-                const float3 Dx = make_float3(g.x * wdx + x0.x * wdg - 2.f * w.x * gdx, g.y * wdx + x0.y * wdg - 2.f * w.y * gdx,
-                                              g.z * wdx + x0.z * wdg - 2.f * w.z * gdx);
-                const float3 Dv = make_float3(g.x * wdv + tv.x * wdg - 2.f * w.x * gdv, g.y * wdv + tv.y * wdg - 2.f * w.y * gdv,
-                                              g.z * wdv + tv.z * wdg - 2.f * w.z * gdv);
-                dS6[0] = ka * xg.x + kb * Dx.x + kb * vg.x + kc * Dv.x;
-                dS6[1] = ka * xg.y + kb * Dx.y + kb * vg.y + kc * Dv.y;
-                dS6[2] = ka * xg.z + kb * Dx.z + kb * vg.z + kc * Dv.z;
-            }
-            if (a.dL_dtwist_S) {
-                if (a.deform_mode == GSR_DEFORM_PER_GAUSSIAN) {
+            const float3 g = make_float3(gm[0], gm[1], gm[2]);
+            float sn, cs;
+            sincosf(th, &sn, &cs);
+            const float ka = sn, kb = 1.0f - cs, kc = th - sn;
+            const float3 wg = cross3(w, g), wwg = skew2(w, g);
+            // dL/dx = R^T g = g - a (w x g) + b W^2 g
+            gx[0] = g.x - ka * wg.x + kb * wwg.x;
+            gx[1] = g.y - ka * wg.y + kb * wwg.y;
+            gx[2] = g.z - ka * wg.z + kb * wwg.z;
+            // dL/dv = th g - b (w x g) + c W^2 g
+            dS6[3] = th * g.x - kb * wg.x + kc * wwg.x;
+            dS6[4] = th * g.y - kb * wg.y + kc * wwg.y;
+            dS6[5] = th * g.z - kb * wg.z + kc * wwg.z;
+            // dL/dth = g . ( cos (w x x) + sin W^2 x + v + sin (w x v) + (1-cos) W^2 v )
+            const float3 wx = cross3(w, x0), wwx = skew2(w, x0), wv = cross3(w, tv), wwv = skew2(w, tv);
+            dth = g.x * (cs * wx.x + sn * wwx.x + tv.x + sn * wv.x + kb * wwv.x) +
+                  g.y * (cs * wx.y + sn * wwx.y + tv.y + sn * wv.y + kb * wwv.y) +
+                  g.z * (cs * wx.z + sn * wwx.z + tv.z + sn * wv.z + kb * wwv.z);
+            // dL/dw = a (x x g) + b D(x) + b (v x g) + c D(v),  D(u) = g (w.u) + u (w.g) - 2 w (g.u)
+            const float3 xg = cross3(x0, g), vg = cross3(tv, g);
+            const float wdx = dot3(w, x0), wdv = dot3(w, tv), wdg = dot3(w, g), gdx = dot3(g, x0), gdv = dot3(g, tv);
+            const float3 Dx = make_float3(g.x * wdx + x0.x * wdg - 2.f * w.x * gdx, g.y * wdx + x0.y * wdg - 2.f * w.y * gdx,
+                                          g.z * wdx + x0.z * wdg - 2.f * w.z * gdx);
+            const float3 Dv = make_float3(g.x * wdv + tv.x * wdg - 2.f * w.x * gdv, g.y * wdv + tv.y * wdg - 2.f * w.y * gdv,
+                                          g.z * wdv + tv.z * wdg - 2.f * w.z * gdv);
+            dS6[0] = ka * xg.x + kb * Dx.x + kb * vg.x + kc * Dv.x;
+            dS6[1] = ka * xg.y + kb * Dx.y + kb * vg.y + kc * Dv.y;
+            dS6[2] = ka * xg.z + kb * Dx.z + kb * vg.z + kc * Dv.z;
+        }
+
+        // ================= (4) all stores =================
+        a.dL_dmeans2D[3 * idx] = g0.x; a.dL_dmeans2D[3 * idx + 1] = g0.y; a.dL_dmeans2D[3 * idx + 2] = 0.0f;
+        emit(a.dL_dopacity + idx, g1.y, acc & GSR_ACC_OPACITY);
+        if (a.dL_dcolors) { a.dL_dcolors[3 * idx] = g1.z; a.dL_dcolors[3 * idx + 1] = g1.w; a.dL_dcolors[3 * idx + 2] = g2x; }
+        if (a.dL_dcov3D) {
 #pragma unroll
-                    if (acc & GSR_ACC_TWIST) {
-                        if (visible) {
+            for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+        }
+        if (a.shs) {
+            // dL_dsh record: 48 floats (element e = coef[e/3] * dRGB[e%3]) as 6 x STG.256, or,
+            // accumulating, 12 x RED.ADD.F32x4
+            float* dsh = a.dL_dsh + (size_t)idx * M * 3;
+            const float dr[3] = {dRGB.x, dRGB.y, dRGB.z};
+            if (wide) {
+                if (acc & GSR_ACC_SH) {
 #pragma unroll
-                            for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] += dS6[k];
-                            a.dL_dtwist_theta[idx] += dth;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] = dS6[k];
-                        a.dL_dtwist_theta[idx] = dth;
+                    for (int k = 0; k < 12; k++) {
+                        float4 o;
+                        o.x = coef[(4 * k) / 3] * dr[(4 * k) % 3];
+                        o.y = coef[(4 * k + 1) / 3] * dr[(4 * k + 1) % 3];
+                        o.z = coef[(4 * k + 2) / 3] * dr[(4 * k + 2) % 3];
+                        o.w = coef[(4 * k + 3) / 3] * dr[(4 * k + 3) % 3];
+                        if (4 * k < (deg + 1) * (deg + 1) * 3) atomicAdd(reinterpret_cast<float4*>(dsh) + k, o);
                     }
-                } else if (visible) {
-                    float* dstS = body_smem ? (s_body + 7 * tix) : nullptr;
-                    if (body_smem) {
+                } else {
 #pragma unroll
-                        for (int k = 0; k < 6; k++) atomicAdd(dstS + k, dS6[k]);
-                        atomicAdd(dstS + 6, dth);
-                    } else {
+                    for (int k = 0; k < 6; k++) {
+                        float o[8];
 #pragma unroll
-                        for (int k = 0; k < 6; k++) atomicAdd(a.dL_dtwist_S + 6 * (size_t)tix + k, dS6[k]);
-                        atomicAdd(a.dL_dtwist_theta + tix, dth);
+                        for (int e8 = 0; e8 < 8; e8++) o[e8] = coef[(8 * k + e8) / 3] * dr[(8 * k + e8) % 3];
+                        st256(dsh + 8 * k, o);
                     }
                 }
+            } else {
+#pragma unroll
+                for (int e1 = 0; e1 < 48; e1++)
+                    if (e1 < M * 3) emit(dsh + e1, coef[e1 / 3] * dr[e1 % 3], acc & GSR_ACC_SH);
             }
         }
-        if (acc & GSR_ACC_MEANS3D) {
-            if (visible) { a.dL_dmeans3D[3 * idx] += gx[0]; a.dL_dmeans3D[3 * idx + 1] += gx[1]; a.dL_dmeans3D[3 * idx + 2] += gx[2]; }
-        } else {
-            a.dL_dmeans3D[3 * idx] = gx[0]; a.dL_dmeans3D[3 * idx + 1] = gx[1]; a.dL_dmeans3D[3 * idx + 2] = gx[2];
+        if (a.dL_dscales) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) emit(a.dL_dscales + 3 * idx + k, dscale[k], acc & GSR_ACC_SCALES);
         }
+        if (a.dL_drots) {
+            float4* dr4 = reinterpret_cast<float4*>(a.dL_drots) + idx;
+            const float4 o = make_float4(drot[0], drot[1], drot[2], drot[3]);
+            if (acc & GSR_ACC_ROTS) atomicAdd(dr4, o); else *dr4 = o;
+        }
+        if (a.dL_dtwist_S && a.deform_mode != GSR_DEFORM_NONE) {
+            if (a.deform_mode == GSR_DEFORM_PER_GAUSSIAN) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) emit(a.dL_dtwist_S + 6 * (size_t)idx + k, dS6[k], acc & GSR_ACC_TWIST);
+                emit(a.dL_dtwist_theta + idx, dth, acc & GSR_ACC_TWIST);
+            } else if (body_smem) {
+                float* dstS = s_body + 7 * tix;
+#pragma unroll
+                for (int k = 0; k < 6; k++) atomicAdd(dstS + k, dS6[k]);
+                atomicAdd(dstS + 6, dth);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) atomicAdd(a.dL_dtwist_S + 6 * (size_t)tix + k, dS6[k]);
+                atomicAdd(a.dL_dtwist_theta + tix, dth);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) emit(a.dL_dmeans3D + 3 * idx + k, gx[k], acc & GSR_ACC_MEANS3D);
     }
     if (body_smem) {
         __syncthreads();

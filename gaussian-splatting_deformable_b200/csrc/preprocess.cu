@@ -56,7 +56,7 @@ __device__ __forceinline__ V3 sh_to_rgb(int deg, float3 pos, const float* campos
 }
 
 
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a, GsrView v) {
+__global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a, GsrView v) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     uint32_t tiles = 0;
     uint32_t dkey = 0xffffffffu;
@@ -64,70 +64,85 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a, G
     for (int k = threadIdx.x; k < 4 * 256; k += 256) s_hist[k] = 0;
     __syncthreads();
     if (idx < a.P) {
+        // ---- (1) every unconditional load first: no store may sit between them (a store to a
+        // non-restrict pointer pins all later loads behind it and serialises DRAM round trips) ----
         float3 p = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
+        float3 w = make_float3(0, 0, 0), tv = w;
+        float th = 0.0f;
         if (a.deform_mode != GSR_DEFORM_NONE) {
             const int t = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) ? a.body_id[idx] : idx;
             const float* S = a.twist_S + 6 * (size_t)t;
-            const float3 w = make_float3(S[0], S[1], S[2]), tv = make_float3(S[3], S[4], S[5]);
-            p = se3_apply(p, w, tv, a.twist_theta[t]);
+            w = make_float3(S[0], S[1], S[2]); tv = make_float3(S[3], S[4], S[5]);
+            th = a.twist_theta[t];
+        }
+        float cov6[6];
+        float3 s = make_float3(0, 0, 0);
+        float4 q = make_float4(0, 0, 0, 0);
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_precomp[6 * (size_t)idx + k];
+        } else {
+            s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+            q = reinterpret_cast<const float4*>(a.rotations)[idx];
+        }
+        const float op = a.opacities[idx];
+        // ---- (2) geometry ----
+        if (a.deform_mode != GSR_DEFORM_NONE) p = se3_apply(p, w, tv, th);
+        int radius = 0;
+        const float depth = xform_row(v.view, 2, p);
+        SplatGeom g;
+        g.ok = false;
+        if (depth > GSR_NEAR) {
+            if (!a.cov3D_precomp) cov3d_exact(s, v.scale_modifier, q, cov6);
+            g = splat_geometry_exact(p, cov6, v);
+        }
+        // ---- (3) second round trip, survivors only: the 192-byte SH record ----
+        V3 rgb = {0, 0, 0};
+        uint8_t cl = 0;
+        if (g.ok) {
+            if (a.colors_precomp) {
+                rgb = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
+            } else {
+                // 6 x LDG.256 (M == 16, 32-byte aligned), scalar otherwise.
+                float shv[48];
+                const int M = v.sh_coeffs;
+                const int need = (v.sh_degree + 1) * (v.sh_degree + 1) * 3;
+                const float* base = a.shs + (size_t)idx * M * 3;
+                if (M == 16 && ((reinterpret_cast<uintptr_t>(a.shs) & 31) == 0)) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        if (8 * k < need) ld256_nc(base + 8 * k, shv + 8 * k);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 48; k++) shv[k] = (k < need) ? base[k] : 0.0f;
+                }
+                auto fetch = [&](int k) -> V3 { return {shv[3 * k], shv[3 * k + 1], shv[3 * k + 2]}; };
+                rgb = sh_to_rgb(v.sh_degree, p, v.campos, fetch);
+                cl = (rgb.x < 0 ? 1 : 0) | (rgb.y < 0 ? 2 : 0) | (rgb.z < 0 ? 4 : 0);
+                rgb.x = fmaxf(rgb.x, 0.0f); rgb.y = fmaxf(rgb.y, 0.0f); rgb.z = fmaxf(rgb.z, 0.0f);
+            }
+        }
+        // ---- (4) stores ----
+        if (a.deform_mode != GSR_DEFORM_NONE) {
             a.means_out[3 * idx] = p.x; a.means_out[3 * idx + 1] = p.y; a.means_out[3 * idx + 2] = p.z;
         }
-        int radius = 0;
-        // Near-cull first so culled Gaussians cost 12 B of reads.
-        const float depth = xform_row(v.view, 2, p);
-        if (depth > GSR_NEAR) {
-            float cov6[6];
-            if (a.cov3D_precomp) {
+        if (a.cov3D_out && depth > GSR_NEAR && !a.cov3D_precomp) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_precomp[6 * (size_t)idx + k];
-            } else {
-                const float3 s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-                const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-                cov3d_exact(s, v.scale_modifier, q, cov6);
-                if (a.cov3D_out) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) a.cov3D_out[6 * (size_t)idx + k] = cov6[k];
-                }
-            }
-            const SplatGeom g = splat_geometry_exact(p, cov6, v);
-            if (g.ok) {
-                V3 rgb;
-                uint8_t cl = 0;
-                if (a.colors_precomp) {
-                    rgb = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
-                } else {
-                    // 192-byte SH record as 6 x LDG.256 (M == 16, 32-byte aligned), scalar otherwise.
-                    float shv[48];
-                    const int M = v.sh_coeffs;
-                    const int need = (v.sh_degree + 1) * (v.sh_degree + 1) * 3;
-                    const float* base = a.shs + (size_t)idx * M * 3;
-                    if (M == 16 && ((reinterpret_cast<uintptr_t>(a.shs) & 31) == 0)) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) {
-                            if (8 * k < need) ld256_nc(base + 8 * k, shv + 8 * k);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 48; k++) shv[k] = (k < need) ? base[k] : 0.0f;
-                    }
-                    auto fetch = [&](int k) -> V3 { return {shv[3 * k], shv[3 * k + 1], shv[3 * k + 2]}; };
-                    rgb = sh_to_rgb(v.sh_degree, p, v.campos, fetch);
-                    cl = (rgb.x < 0 ? 1 : 0) | (rgb.y < 0 ? 2 : 0) | (rgb.z < 0 ? 4 : 0);
-                    rgb.x = fmaxf(rgb.x, 0.0f); rgb.y = fmaxf(rgb.y, 0.0f); rgb.z = fmaxf(rgb.z, 0.0f);
-                }
-                const float op = a.opacities[idx];
-                // alpha = min(.99, op*exp(power)) >= 1/255 needs power >= log(1/(255 op)).
-                // Margin 1e-3 dwarfs the rounding of expf and of this log.
-                float cut = (op > 0.0f) ? (__logf(1.0f / (255.0f * op)) - 1e-3f) : 1.0f;
-                radius = g.radius;
-                tiles = (g.rmax.y - g.rmin.y) * (g.rmax.x - g.rmin.x);
-                a.depths[idx] = g.depth;
-                float4* r = a.recs + 3 * (size_t)idx;
-                r[0] = make_float4(g.pix.x, g.pix.y, g.conic.x, g.conic.y);
-                r[1] = make_float4(g.conic.z, op, rgb.x, rgb.y);
-                r[2] = make_float4(rgb.z, cut, 0.0f, 0.0f);
-                a.clamped[idx] = cl;
-            }
+            for (int k = 0; k < 6; k++) a.cov3D_out[6 * (size_t)idx + k] = cov6[k];
+        }
+        if (g.ok) {
+            // alpha = min(.99, op*exp(power)) >= 1/255 needs power >= log(1/(255 op)).
+            // Margin 1e-3 dwarfs the rounding of expf and of this log.
+            float cut = (op > 0.0f) ? (__logf(1.0f / (255.0f * op)) - 1e-3f) : 1.0f;
+            radius = g.radius;
+            tiles = (g.rmax.y - g.rmin.y) * (g.rmax.x - g.rmin.x);
+            a.depths[idx] = g.depth;
+            float4* r = a.recs + 3 * (size_t)idx;
+            r[0] = make_float4(g.pix.x, g.pix.y, g.conic.x, g.conic.y);
+            r[1] = make_float4(g.conic.z, op, rgb.x, rgb.y);
+            r[2] = make_float4(rgb.z, cut, 0.0f, 0.0f);
+            a.clamped[idx] = cl;
         }
         a.radii[idx] = radius;
         a.tiles_touched[idx] = tiles;
