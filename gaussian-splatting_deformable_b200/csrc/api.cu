@@ -73,7 +73,7 @@ struct GeomLayout {
     // the depth sort is 4 passes (even): its result lands back in the "a" buffers
     size_t in_b_order() const { return dvals_a; }
     size_t depths, tiles, recs, clamped, cov3d, block_sums, total, dkeys_a, dkeys_b, dvals_a, dvals_b,
-                    dsort_temp, dsort_temp_bytes, sblock_sums, bytes; };
+                    dsort_temp, dsort_temp_bytes, sblock_sums, rects, srec, bytes; };
 GeomLayout geom_layout(int P) {
     GeomLayout L{};
     size_t o = 0;
@@ -91,6 +91,8 @@ GeomLayout geom_layout(int P) {
     L.dvals_b = o; o += al(4 * p);
     L.dsort_temp = o; L.dsort_temp_bytes = gsr_sort_temp_bytes((uint32_t)p, 0, 32); o += al(L.dsort_temp_bytes);
     L.sblock_sums = o; o += al(4 * ((p + 255) / 256 + 1));
+    L.rects = o; o += al(8 * p);
+    L.srec = o; o += al(16 * p);
     L.bytes = o;
     return L;
 }
@@ -116,7 +118,8 @@ int tile_bits(uint32_t n) {
     if (n >> msb) msb++;
     return msb;
 }
-struct BinLayout { size_t tkeys_a, tkeys_b, vals_a, vals_b, sort_temp, sort_temp_bytes, keys64, bytes; int tile_bits; int passes; };
+struct BinLayout { size_t tkeys_a, tkeys_b, vals_a, vals_b, sort_temp, sort_temp_bytes, keys64, matrix, totals, tile_base, bytes;
+                   int tile_bits; int passes; int sweep; };
 BinLayout bin_layout(uint32_t R, int W, int H) {
     BinLayout L{};
     const uint32_t tiles = (uint32_t)((W + 15) / 16) * ((H + 15) / 16);
@@ -129,6 +132,12 @@ BinLayout bin_layout(uint32_t R, int W, int H) {
     L.vals_b = o; o += al(4 * (size_t)R);
     L.sort_temp = o; L.sort_temp_bytes = gsr_sort_temp_bytes(R, 0, L.tile_bits); o += al(L.sort_temp_bytes);
     L.keys64 = o; o += al(8 * (size_t)R);          // reference-format keys, filled on request only
+    // counting-sort path (tile_sweep.cu): point_list = vals_a, sorted tile ids (debug) = tkeys_a
+    const int gx = (W + 15) / 16, gy = (H + 15) / 16;
+    L.sweep = gsr_make_tile_bin_plan(gx, gy).feasible;
+    L.matrix = o; o += al(gsr_tile_matrix_bytes(gx, gy));
+    L.totals = o; o += al(4 * (size_t)tiles);
+    L.tile_base = o; o += al(4 * (size_t)tiles);
     L.bytes = o + 256;
     return L;
 }
@@ -197,7 +206,7 @@ void gsr_image_layout(int W, int H, size_t out[3]) {
 }
 void gsr_binning_layout(uint32_t R, int W, int H, size_t out[4]) {
     const BinLayout L = bin_layout(R, W, H);
-    const bool in_b = (L.passes & 1) != 0;
+    const bool in_b = !L.sweep && (L.passes & 1) != 0;
     out[0] = L.keys64;
     out[1] = in_b ? L.vals_b : L.vals_a;
     out[2] = in_b ? L.tkeys_b : L.tkeys_a;
@@ -248,6 +257,7 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* mean
     // the depth sort's state (histograms, tickets, look-back words) is zeroed here because the
     // preprocess kernel accumulates the digit histograms of its depth keys
     a.depth_hist = reinterpret_cast<uint32_t*>(ws + L.dsort_temp);
+    a.rects = reinterpret_cast<uint2*>(ws + L.rects);
     GSR_CHECK(cudaMemsetAsync(ws + L.dsort_temp, 0, L.dsort_temp_bytes, stream));
     if (int rc = gsr_launch_preprocess_fwd(a, v, stream)) return rc;
     uint32_t* d_total = reinterpret_cast<uint32_t*>(ws + L.total);
@@ -289,6 +299,26 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
                                              L.dsort_temp_bytes, &d_in_b, stream, 1, true))
             return rc;
         const uint32_t* order = d_in_b ? dvals_b : dvals_a;
+        const uint32_t* sorted_tiles = nullptr;
+        if (BL.sweep) {
+            // 2+3. stable counting sort of the (never materialised) duplicates by tile id
+            const GsrTileBinPlan pl = gsr_make_tile_bin_plan(v.grid_x, v.grid_y);
+            uint32_t* plist = reinterpret_cast<uint32_t*>(bw + BL.vals_a);
+            // emitting Gaussians = keys whose top byte is not 0xff = scanned top-digit histogram at bin 255
+            const uint32_t* n_emit = reinterpret_cast<const uint32_t*>(gw + L.dsort_temp) + 3 * GSR_SORT_RADIX + 255;
+            if (int rc = gsr_launch_tile_binning(P, n_emit, order, reinterpret_cast<const uint2*>(gw + L.rects),
+                                                 reinterpret_cast<uint4*>(gw + L.srec), pl, v.grid_x, v.grid_y,
+                                                 reinterpret_cast<uint32_t*>(bw + BL.matrix),
+                                                 reinterpret_cast<uint32_t*>(bw + BL.totals),
+                                                 reinterpret_cast<uint32_t*>(bw + BL.tile_base), ranges, plist, stream))
+                return rc;
+            point_list = plist;
+            if (materialize_keys) {
+                uint32_t* tids = reinterpret_cast<uint32_t*>(bw + BL.tkeys_a);
+                if (int rc = gsr_launch_expand_tile_ids(num_tiles, ranges, tids, stream)) return rc;
+                sorted_tiles = tids;
+            }
+        } else {
         // 2. offsets in that order, then the duplicates (tile id, Gaussian id)
         uint32_t* sblock = reinterpret_cast<uint32_t*>(gw + L.sblock_sums);
         uint32_t* d_total = reinterpret_cast<uint32_t*>(gw + L.total) + 1;
@@ -308,9 +338,10 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
         if (int rc = gsr_launch_sort_pairs32(tkeys_a, tkeys_b, vals_a, vals_b, R, 0, BL.tile_bits, bw + BL.sort_temp,
                                              BL.sort_temp_bytes, &in_b, stream, 2, true))
             return rc;
-        const uint32_t* sorted_tiles = in_b ? tkeys_b : tkeys_a;
+        sorted_tiles = in_b ? tkeys_b : tkeys_a;
         point_list = in_b ? vals_b : vals_a;
         if (int rc = gsr_launch_tile_ranges(R, sorted_tiles, ranges, num_tiles, stream)) return rc;
+        }
         if (materialize_keys)
             if (int rc = gsr_launch_materialize_keys(R, sorted_tiles, point_list,
                                                      reinterpret_cast<const float*>(gw + L.depths),
@@ -339,7 +370,7 @@ int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t R, const void* g
     const GeomLayout L = geom_layout(P);
     const ImageLayout IL = image_layout(v.W, v.H);
     const BinLayout BL = bin_layout(R, v.W, v.H);
-    const bool in_b = (BL.passes & 1) != 0;
+    const bool in_b = !BL.sweep && (BL.passes & 1) != 0;
     BlendFwdArgs b{};
     b.ranges = reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(image_ws) + IL.ranges);
     b.point_list = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(binning_ws) + (in_b ? BL.vals_b : BL.vals_a));
@@ -376,7 +407,7 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
         if (!binning_ws) return gsr_set_error_msg(-1, "backward: binning workspace is NULL");
         const BinLayout BL = bin_layout(R, v.W, v.H);
         const char* bw = reinterpret_cast<const char*>(binning_ws);
-        const bool in_b = (BL.passes & 1) != 0;
+        const bool in_b = !BL.sweep && (BL.passes & 1) != 0;
         BlendBwdArgs b{};
         b.ranges = reinterpret_cast<const uint2*>(iw + IL.ranges);
         b.point_list = reinterpret_cast<const uint32_t*>(bw + (in_b ? BL.vals_b : BL.vals_a));

@@ -38,6 +38,7 @@ struct PreprocessArgs {
     uint32_t* depth_keys;        // [P] float bits of the view depth (0xffffffff when the Gaussian emits nothing)
     uint32_t* depth_vals;        // [P] = idx (payload of the depth sort)
     uint32_t* depth_hist;        // [4][256] digit histograms of depth_keys (pre-zeroed), accumulated here
+    uint2* rects;                // [P] tile rect (rmin.x | rmin.y << 16, rmax.x | rmax.y << 16); (0,0) when nothing is emitted
 };
 
 int gsr_launch_preprocess_fwd(const PreprocessArgs& a, const GsrView& v, cudaStream_t stream);
@@ -61,6 +62,26 @@ int gsr_launch_tile_ranges(uint32_t R, const uint32_t* sorted_tile_ids, uint2* r
 // The reference's 64-bit sorted keys (tile << 32 | depth bits), for parity checks.
 int gsr_launch_materialize_keys(uint32_t R, const uint32_t* sorted_tile_ids, const uint32_t* point_list,
                                 const float* depths, uint64_t* keys64, cudaStream_t stream);
+
+// ---- tile binning as one stable counting sort over the depth-ordered Gaussians (tile_sweep.cu) ----
+#define GSR_SWEEP_WARPS 8                 // warps (= tile-row stripes) per CTA
+#define GSR_SWEEP_ROWS 4                  // tile rows per stripe (lane = row * 8 + column)
+#define GSR_SWEEP_MAX_STRIPE_TILES 4096   // counters per warp (16 KB): images up to 16384 px wide
+#define GSR_SWEEP_MAX_CHUNKS 1024         // rows of the chunk x tile matrix
+struct GsrTileBinPlan {
+    int feasible;          // 0: fall back to the radix path
+    int chunks;            // rows of the matrix (<= GSR_SWEEP_MAX_CHUNKS); a chunk is ceil(n_emit / chunks) Gaussians
+    int stripes, groups, stripe_tiles, num_tiles;
+};
+GsrTileBinPlan gsr_make_tile_bin_plan(int grid_x, int grid_y);
+size_t gsr_tile_matrix_bytes(int grid_x, int grid_y);
+// order[P] = Gaussian ids in depth order; rects[P]; srec[P] scratch; matrix[chunks][tiles] scratch;
+// totals/tile_base [tiles] scratch.  Writes ranges[tiles] and point_list[R].
+// n_emit (device) = number of Gaussians that emit duplicates (the depth sort puts them first).
+int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
+                            const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
+                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, cudaStream_t stream);
+int gsr_launch_expand_tile_ids(int num_tiles, const uint2* ranges, uint32_t* tile_ids, cudaStream_t stream);
 
 // ---- onesweep radix sort of (u64|u32 key, u32 value) pairs -----------------
 

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
         }
         a.radii[idx] = radius;
         a.tiles_touched[idx] = tiles;
+        a.rects[idx] = g.ok ? make_uint2(g.rmin.x | (g.rmin.y << 16), g.rmax.x | (g.rmax.y << 16)) : make_uint2(0u, 0u);
         dkey = tiles ? __float_as_uint(depth) : 0xffffffffu;
         a.depth_keys[idx] = dkey;
         a.depth_vals[idx] = (uint32_t)idx;

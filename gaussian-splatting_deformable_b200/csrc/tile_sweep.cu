@@ -1,0 +1,273 @@
+// Tile binning as ONE stable counting sort over the depth-ordered Gaussians.
+//
+// Replaces, like binning.cu + radix_sort.cu, rasterizer_impl.cu:70-138,277-318 of the
+// reference (duplicateWithKeys, cub::DeviceRadixSort::SortPairs on (tile | depth) keys,
+// identifyTileRanges) - and produces the identical point_list / ranges - but never
+// materialises or sorts the R (tile, Gaussian) duplicates:
+//
+//   the P Gaussians are already in depth order (4-pass onesweep on 8-byte pairs), so the
+//   reference's final order is "for every tile, the Gaussians that cover it, in depth
+//   order" = a STABLE partition of the duplicate stream by tile id.  A stable partition
+//   is a counting sort:
+//     up-sweep    count[chunk][tile]   (chunk = G consecutive Gaussians of the depth order)
+//     scan        start[chunk][tile] = base[tile] + sum_{c' < chunk} count[c'][tile]
+//                 (base = exclusive scan of the tile totals = the reference's `ranges`)
+//     down-sweep  every duplicate goes straight to point_list[start + rank-in-chunk]
+//   HBM traffic: 16 B x P (sorted rect records, read twice) + the chunk x tile matrix
+//   (3 passes) + 4 B x R written once.  The radix path moved 8 B x R + 2 x 16 B x R + 4 B x R.
+//
+// Work decomposition: one WARP per (chunk, stripe of 4 tile rows) with a warp-PRIVATE counter
+// array in shared memory; see tile_sweep_kernel.
+#include "kernels.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// srec[i] = (Gaussian id, rect lo, rect hi, 0) of the i-th Gaussian in depth order; one
+// coalesced LDG.128 per lane in the sweeps instead of an id load + dependent gather.
+// *n_emit = number of Gaussians that emit at least one duplicate (they sort first).
+__global__ void __launch_bounds__(256) gather_rects_kernel(const uint32_t* __restrict__ n_emit_p,
+                                                           const uint32_t* __restrict__ order,
+                                                           const uint2* __restrict__ rects, uint4* __restrict__ srec) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= *n_emit_p) return;
+    const uint32_t id = order[i];
+    const uint2 rc = rects[id];
+    srec[i] = make_uint4(id, rc.x, rc.y, 0u);
+}
+
+// One warp = (chunk of the depth order, stripe of GSR_SWEEP_ROWS tile rows).  Lane l maps to
+// cell (row l / CW, column l % CW) of a Gaussian's clipped rect, CW = 32 / GSR_SWEEP_ROWS columns
+// at a time: the cells of ONE Gaussian are distinct tiles, so a plain returning shared atomic per
+// lane ranks them, and Gaussians are taken one after the other in program (= depth) order - which
+// is all stability needs.  No scan, no search, no match, no CTA barrier.
+template <bool SCATTER>
+__global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_sweep_kernel(const uint32_t* __restrict__ n_emit_p,
+                                                                         const uint4* __restrict__ srec, GsrTileBinPlan pl,
+                                                                         int grid_x, int grid_y,
+                                                                         uint32_t* __restrict__ matrix,
+                                                                         const uint32_t* __restrict__ tile_base,
+                                                                         uint32_t* __restrict__ point_list) {
+    constexpr int ROWS = GSR_SWEEP_ROWS, CW = 32 / ROWS;
+    extern __shared__ uint32_t s_cnt_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stripe = blockIdx.y * GSR_SWEEP_WARPS + warp;
+    if (stripe >= pl.stripes) return;                       // warps are independent: no CTA barrier below
+    uint32_t* cnt = s_cnt_all + warp * pl.stripe_tiles;
+    const int row0 = stripe * ROWS;
+    const int row1 = min(grid_y, row0 + ROWS);
+    const int tile0 = row0 * grid_x, ntile = (row1 - row0) * grid_x;
+    const int chunk = blockIdx.x;
+    const uint32_t n_emit = *n_emit_p;
+    const uint32_t G = (((n_emit + pl.chunks - 1) / pl.chunks) + 31u) & ~31u;   // Gaussians per chunk
+    const uint32_t g_begin = chunk * G, g_end = min(n_emit, g_begin + G);
+    uint32_t* mrow = matrix + (size_t)chunk * pl.num_tiles + tile0;
+    if (g_begin >= g_end) {
+        if (!SCATTER) for (int i = lane; i < ntile; i += 32) mrow[i] = 0u;
+        return;
+    }
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (g_begin + lane < g_end) cur = srec[g_begin + lane];
+    if (SCATTER) { for (int i = lane; i < ntile; i += 32) cnt[i] = tile_base[tile0 + i] + mrow[i]; }
+    else { for (int i = lane; i < ntile; i += 32) cnt[i] = 0u; }
+    __syncwarp();
+
+    const int lrow = lane / CW, lcol = lane % CW;
+    for (uint32_t b = g_begin; b < g_end; b += 32) {
+        const uint4 rec = cur;
+        if (b + 32 + lane < g_end) cur = srec[b + 32 + lane];      // prefetch the next batch
+        else cur = make_uint4(0, 0, 0, 0);
+        const int x0 = rec.y & 0xffffu, y0 = rec.y >> 16, x1 = rec.z & 0xffffu, y1 = rec.z >> 16;
+        const int cy0 = max(y0, row0), cy1 = min(y1, row1);
+        const bool has = (x1 > x0) && (cy1 > cy0);
+        // per-lane description of the clipped rect: first stripe-local cell, width, height
+        const uint32_t first = (uint32_t)((cy0 - row0) * grid_x + x0);
+        const uint32_t wh = (uint32_t)(x1 - x0) | ((uint32_t)(cy1 - cy0) << 16);
+        uint32_t m = __ballot_sync(FULL, has);
+        while (m) {
+            const int g = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t gfirst = __shfl_sync(FULL, first, g);
+            const uint32_t gwh = __shfl_sync(FULL, wh, g);
+            const uint32_t gid = __shfl_sync(FULL, rec.x, g);
+            const int gw = (int)(gwh & 0xffffu), gh = (int)(gwh >> 16);
+            if (lrow < gh) {
+                const uint32_t rbase = gfirst + (uint32_t)(lrow * grid_x);
+                for (int c = lcol; c < gw; c += CW) {
+                    if (SCATTER) {
+                        const uint32_t pos = atomicAdd(&cnt[rbase + c], 1u);
+                        point_list[pos] = gid;
+                    } else {
+                        atomicAdd(&cnt[rbase + c], 1u);
+                    }
+                }
+            }
+        }
+    }
+    if (!SCATTER) {
+        __syncwarp();
+        for (int i = lane; i < ntile; i += 32) mrow[i] = cnt[i];
+    }
+}
+
+// Column scan of the chunk x tile count matrix: in place, counts -> exclusive prefix over the
+// chunks; totals[tile] = column sum.  CTA = 32 tiles x 8 row segments: every thread sums its
+// segment, the 8 partial sums are scanned in shared memory, then the segment is rewritten.
+__global__ void __launch_bounds__(256) tile_column_scan_kernel(int chunks, int num_tiles, uint32_t* __restrict__ matrix,
+                                                               uint32_t* __restrict__ totals) {
+    __shared__ uint32_t s_part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + tx;
+    const int seg = (chunks + 7) / 8;
+    const int r0 = ty * seg, r1 = min(chunks, r0 + seg);
+    uint32_t sum = 0;
+    if (t < num_tiles) {
+        int c = r0;
+        for (; c + 8 <= r1; c += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = matrix[(size_t)(c + k) * num_tiles + t];
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += v[k];
+        }
+        for (; c < r1; c++) sum += matrix[(size_t)c * num_tiles + t];
+    }
+    s_part[ty][tx] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) run += (k < ty) ? s_part[k][tx] : 0u;
+    if (t < num_tiles) {
+        int c = r0;
+        for (; c + 8 <= r1; c += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = matrix[(size_t)(c + k) * num_tiles + t];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { matrix[(size_t)(c + k) * num_tiles + t] = run; run += v[k]; }
+        }
+        for (; c < r1; c++) {
+            const uint32_t v = matrix[(size_t)c * num_tiles + t];
+            matrix[(size_t)c * num_tiles + t] = run;
+            run += v;
+        }
+        if (ty == 7) totals[t] = run;
+    }
+}
+
+// Exclusive scan of the tile totals by one CTA -> base[tile]; ranges[tile] = [base, base+total)
+// or (0,0) for an empty tile (what identifyTileRanges + its memset leave, rasterizer_impl.cu:116-138,310).
+__global__ void __launch_bounds__(1024) tile_base_kernel(int num_tiles, const uint32_t* __restrict__ totals,
+                                                         uint32_t* __restrict__ base, uint2* __restrict__ ranges) {
+    __shared__ uint32_t warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (num_tiles + 1023) / 1024;             // consecutive tiles per thread
+    const int i0 = threadIdx.x * per, i1 = min(num_tiles, i0 + per);
+    uint32_t v = 0;
+    for (int i = i0; i < i1; i++) v += totals[i];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, w, o);
+            if (lane >= o) w += t;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    uint32_t ex = (warp ? warp_tot[warp - 1] : 0u) + incl - v;
+    for (int i = i0; i < i1; i++) {
+        const uint32_t c = totals[i];
+        base[i] = ex;
+        ranges[i] = c ? make_uint2(ex, ex + c) : make_uint2(0u, 0u);
+        ex += c;
+    }
+}
+
+// Parity/debug: the sorted tile ids the reference's keys carry, rebuilt from the ranges.
+__global__ void __launch_bounds__(256) expand_tile_ids_kernel(int num_tiles, const uint2* __restrict__ ranges,
+                                                              uint32_t* __restrict__ tile_ids) {
+    const int t = blockIdx.x;
+    if (t >= num_tiles) return;
+    const uint2 r = ranges[t];
+    for (uint32_t i = r.x + threadIdx.x; i < r.y; i += 256) tile_ids[i] = (uint32_t)t;
+}
+
+int env_int2(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+// Plan for a grid_x x grid_y tile grid; feasible == 0 when a stripe of tile rows does not fit a
+// warp's counter array (image wider than 16 x GSR_SWEEP_MAX_STRIPE_TILES / GSR_SWEEP_ROWS pixels).
+GsrTileBinPlan gsr_make_tile_bin_plan(int grid_x, int grid_y) {
+    GsrTileBinPlan pl{};
+    pl.num_tiles = grid_x * grid_y;
+    static const int forced = env_int2("GSR_BINNING_RADIX", 0);
+    if (forced || grid_x <= 0 || grid_y <= 0 || grid_x * GSR_SWEEP_ROWS > GSR_SWEEP_MAX_STRIPE_TILES) { pl.feasible = 0; return pl; }
+    pl.feasible = 1;
+    static const int c_env = env_int2("GSR_SWEEP_CHUNKS", 0);
+    pl.chunks = (c_env > 0 && c_env <= GSR_SWEEP_MAX_CHUNKS) ? c_env : 512;
+    pl.stripes = (grid_y + GSR_SWEEP_ROWS - 1) / GSR_SWEEP_ROWS;
+    pl.groups = (pl.stripes + GSR_SWEEP_WARPS - 1) / GSR_SWEEP_WARPS;
+    pl.stripe_tiles = GSR_SWEEP_ROWS * grid_x;
+    return pl;
+}
+
+size_t gsr_tile_matrix_bytes(int grid_x, int grid_y) {
+    const GsrTileBinPlan pl = gsr_make_tile_bin_plan(grid_x, grid_y);
+    return pl.feasible ? (size_t)pl.chunks * (size_t)pl.num_tiles * sizeof(uint32_t) : 0;
+}
+
+int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
+                            const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
+                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    if (!pl.feasible) return gsr_set_error_msg(-2, "tile sweep: plan not feasible");
+    const size_t smem = (size_t)GSR_SWEEP_WARPS * pl.stripe_tiles * sizeof(uint32_t);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GSR_CHECK(cudaFuncSetAttribute(tile_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GSR_SWEEP_WARPS * GSR_SWEEP_MAX_STRIPE_TILES * (int)sizeof(uint32_t)));
+        GSR_CHECK(cudaFuncSetAttribute(tile_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GSR_SWEEP_WARPS * GSR_SWEEP_MAX_STRIPE_TILES * (int)sizeof(uint32_t)));
+        attr_done = true;
+    }
+    { GsrProfScope prof_("gather_rects", stream);
+    gather_rects_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(n_emit, order, rects, srec); }
+    GSR_CHECK_LAUNCH();
+    const dim3 grid(pl.chunks, pl.groups, 1);
+    { GsrProfScope prof_("tile_sweep_count", stream);
+    tile_sweep_kernel<false><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list); }
+    GSR_CHECK_LAUNCH();
+    { GsrProfScope prof_("tile_column_scan", stream);
+    tile_column_scan_kernel<<<gsr_div_up(pl.num_tiles, 32), 256, 0, stream>>>(pl.chunks, pl.num_tiles, matrix, totals); }
+    GSR_CHECK_LAUNCH();
+    { GsrProfScope prof_("tile_base_scan", stream);
+    tile_base_kernel<<<1, 1024, 0, stream>>>(pl.num_tiles, totals, tile_base, ranges); }
+    GSR_CHECK_LAUNCH();
+    { GsrProfScope prof_("tile_sweep_scatter", stream);
+    tile_sweep_kernel<true><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+
+int gsr_launch_expand_tile_ids(int num_tiles, const uint2* ranges, uint32_t* tile_ids, cudaStream_t stream) {
+    if (num_tiles <= 0) return 0;
+    { GsrProfScope prof_("expand_tile_ids", stream);
+    expand_tile_ids_kernel<<<num_tiles, 256, 0, stream>>>(num_tiles, ranges, tile_ids); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
