@@ -361,6 +361,11 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
 }
 
 // Debug: workload counters of the blend stage for a finished forward (see blend.cu).
+int gsr_debug_exp_check(float x_max, unsigned long long* out2, void* stream_) {
+    if (!out2 || !(x_max > 0.0f)) return gsr_set_error_msg(-1, "exp_check: bad arguments");
+    return gsr_launch_exp_check(x_max, out2, (cudaStream_t)stream_);
+}
+
 int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t R, const void* geom_ws, const void* binning_ws,
                           const void* image_ws, unsigned long long* out8, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

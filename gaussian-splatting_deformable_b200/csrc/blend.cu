@@ -566,6 +566,8 @@ static int env_int(const char* name, int dflt) {
 // 1, 2 or 4) and TMA bulk-copy staging of the splat records (GSR_BLEND_TMA = 0/1).
 int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
+    static const int ver = env_int("GSR_BLEND_FWD_V", 2);   // 2: blend_v2.cu (warp regions + packed FP32x2), 1: this file
+    if (ver == 2) return gsr_launch_blend_fwd_v2(a, stream);
     static const int ppt = env_int("GSR_FWD_PPT", 2);
     static const int tma = env_int("GSR_BLEND_TMA", 0);   // measured 4% slower than the register-staged gather at C2
     { GsrProfScope prof_("blend_fwd", stream);

@@ -1,0 +1,237 @@
+// Tile blending, second generation: warp-autonomous regions + packed FP32x2 pixel pairs.
+//
+// Replaces cuda_rasterizer/forward.cu:261-374 (renderCUDA fwd) and backward.cu:399-557
+// (renderCUDA bwd) like blend.cu, with the same bit-identical per-pixel decisions, but:
+//
+//   * a WARP owns an 8 x (8 NP) pixel region of the 16x16 tile and walks the tile's list on
+//     its own: it gathers 32 list entries at a time (one 48-byte record per lane, next batch in
+//     flight while the current one is blended), culls them against ITS region (the closed-form
+//     bound of blend.cu on a rectangle a quarter or half the size, so far fewer survivors),
+//     ballot-compacts the survivors into a warp-private shared ring, and stops as soon as its
+//     own pixels are done.  No CTA barrier anywhere.
+//   * a lane owns NP pairs of vertically adjacent pixels.  The two pixels of a pair share dx,
+//     and everything that differs is computed on both at once with sm_100's packed
+//     FFMA2/FMUL2/FADD2 (f32x2.cuh): same IEEE roundings as the reference's scalar
+//     sequence, half the issue slots.  expf is CUDA's own algorithm restated on packed
+//     values.  These kernels are issue-bound (profiles/), so issue slots are the currency.
+//   * backward: the per-Gaussian sums leave a warp as before (transposing butterfly + 9
+//     native RED.ADD.F32), once per (region, Gaussian).
+#include "f32x2.cuh"
+#include "geom_exact.cuh"
+#include "kernels.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// see blend.cu: true unless NO pixel centre in [x0,x1]x[y0,y1] can have power >= cut
+__device__ __forceinline__ bool rect_may_contribute(float mx, float my, float a, float b, float c, float cut,
+                                                    float x0, float y0, float x1, float y1) {
+    const float dxl = x0 - mx, dxh = x1 - mx, dyl = y0 - my, dyh = y1 - my;
+    const bool in_x = (dxl <= 0.0f) && (dxh >= 0.0f);
+    const bool in_y = (dyl <= 0.0f) && (dyh >= 0.0f);
+    if (in_x && in_y) return true;
+    if (!(a > 0.0f && c > 0.0f && a * c > b * b)) return true;   // not PD (or NaN): never cull
+    float qmin = 3.0e38f;
+    if (!in_x) {
+        const float dxe = dxl > 0.0f ? dxl : dxh;
+        const float dys = fminf(fmaxf(-b * dxe / c, dyl), dyh);
+        qmin = fminf(qmin, a * dxe * dxe + 2.0f * b * dxe * dys + c * dys * dys);
+    }
+    if (!in_y) {
+        const float dye = dyl > 0.0f ? dyl : dyh;
+        const float dxs = fminf(fmaxf(-b * dye / a, dxl), dxh);
+        qmin = fminf(qmin, a * dxs * dxs + 2.0f * b * dxs * dye + c * dye * dye);
+    }
+    const float dxm = fmaxf(fabsf(dxl), fabsf(dxh)), dym = fmaxf(fabsf(dyl), fabsf(dyh));
+    const float mag = 0.5f * (a * dxm * dxm + c * dym * dym) + fabsf(b) * dxm * dym;
+    const float margin = 1e-2f + 4e-6f * mag;
+    return !(-0.5f * qmin < cut - margin);
+}
+
+// The reference's exponent (forward.cu:335 as compiled, geom_exact.cuh:blend_power_exact)
+//   power = fma(fma(dx, dx*cx, dy*(dy*cz)), -0.5, -(dy*(dx*cy)))
+// for two pixels of one column: dx, s1 = dx*cx and s2 = dx*(-cy) are shared scalars.
+__device__ __forceinline__ f32x2 power2_exact(float dx, float s1, float s2, f32x2 dy, float cz) {
+    const f32x2 v = mul2(dy, mul2(dy, pk1(cz)));
+    const f32x2 w = fma2(pk1(dx), pk1(s1), v);
+    return fma2(w, pk1(-0.5f), mul2(dy, pk1(s2)));
+}
+
+// ---------------------------------------------------------------------------
+// Forward
+// ---------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(128 / NP) blend_fwd_v2_kernel(BlendFwdArgs a) {
+    constexpr int NW = 4 / NP;                       // warps (regions) per tile
+    __shared__ float4 s_q0[NW][32];                  // x, y, conic.x, -conic.y
+    __shared__ float4 s_q1[NW][32];                  // conic.z, opacity, cut, (list position + 1) as bits
+    __shared__ float4 s_q2[NW][32];                  // r, g, b, -
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.y * a.grid_x + blockIdx.x;
+    const int X0 = blockIdx.x * GSR_TILE + ((NP == 1) ? ((warp & 1) << 3) : (warp << 3));
+    const int Y0 = blockIdx.y * GSR_TILE + ((NP == 1) ? ((warp >> 1) << 3) : 0);
+    if (X0 >= a.W || Y0 >= a.H) return;             // region outside the image: warps are independent
+    const int px = X0 + (lane & 7);
+    const float pxf = (float)px;
+    const float rx0 = (float)X0, ry0 = (float)Y0;
+    const float rx1 = fminf(rx0 + 7.0f, (float)(a.W - 1)), ry1 = fminf(ry0 + (float)(8 * NP - 1), (float)(a.H - 1));
+
+    int pyi[NP];
+    f32x2 npy[NP], T[NP], C0[NP], C1[NP], C2[NP];
+    uint32_t lastA[NP], lastB[NP];
+    bool doneA[NP], doneB[NP], inA[NP], inB[NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        pyi[q] = Y0 + 8 * q + 2 * (lane >> 3);
+        npy[q] = pk(-(float)pyi[q], -(float)(pyi[q] + 1));
+        inA[q] = px < a.W && pyi[q] < a.H;
+        inB[q] = px < a.W && pyi[q] + 1 < a.H;
+        doneA[q] = !inA[q]; doneB[q] = !inB[q];
+        T[q] = pk1(1.0f); C0[q] = C1[q] = C2[q] = pk1(0.0f);
+        lastA[q] = lastB[q] = 0;
+    }
+    const uint2 range = a.ranges[tile];
+    const int todo = (int)(range.y - range.x);
+    float4* const q0s = s_q0[warp]; float4* const q1s = s_q1[warp]; float4* const q2s = s_q2[warp];
+
+    float4 n0, n1, n2;
+    bool nvalid = false;
+    auto fetch = [&](int base) {
+        nvalid = base + lane < todo;
+        if (nvalid) {
+            const uint32_t id = a.point_list[range.x + base + lane];
+            const float4* r = a.recs + 3 * (size_t)id;
+            n0 = __ldg(r); n1 = __ldg(r + 1); n2 = __ldg(r + 2);
+        }
+    };
+    if (todo > 0) fetch(0);
+    for (int base = 0; base < todo; base += 32) {
+        bool all_done = true;
+#pragma unroll
+        for (int q = 0; q < NP; q++) all_done = all_done && doneA[q] && doneB[q];
+        if (__all_sync(FULL, all_done)) break;
+        const float4 c0 = n0, c1 = n1, c2 = n2;
+        const bool keep = nvalid && rect_may_contribute(c0.x, c0.y, c0.z, c0.w, c1.x, c2.y, rx0, ry0, rx1, ry1);
+        if (base + 32 < todo) fetch(base + 32);
+        const unsigned m = __ballot_sync(FULL, keep);
+        const int n = __popc(m);
+        __syncwarp();                                // every lane is done reading the previous batch
+        if (keep) {
+            const int slot = __popc(m & ((1u << lane) - 1u));
+            q0s[slot] = make_float4(c0.x, c0.y, c0.z, -c0.w);
+            q1s[slot] = make_float4(c1.x, c1.y, c2.y, __uint_as_float((uint32_t)(base + lane) + 1u));
+            q2s[slot] = make_float4(c1.z, c1.w, c2.x, 0.0f);
+        }
+        __syncwarp();
+        for (int j = 0; j < n; j++) {
+            const float4 g0 = q0s[j];
+            const float4 g1 = q1s[j];
+            const float dx = g0.x - pxf;
+            const float s1 = FMUL(dx, g0.z), s2 = FMUL(dx, g0.w);
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const f32x2 dy = add2(pk1(g0.y), npy[q]);
+                const f32x2 pw = power2_exact(dx, s1, s2, dy, g1.x);
+                float pA, pB;
+                upk(pw, pA, pB);
+                const bool okA = !doneA[q] && !(pA > 0.0f || pA < g1.z);
+                const bool okB = !doneB[q] && !(pB > 0.0f || pB < g1.z);
+                if (!(okA || okB)) continue;
+                const f32x2 al = mul2(pk1(g1.y), exp2_exact(pw));
+                float aA, aB, tA, tB, TA, TB;
+                upk(al, aA, aB);
+                aA = fminf(0.99f, aA); aB = fminf(0.99f, aB);
+                bool cA = okA && !(aA < 1.0f / 255.0f);
+                bool cB = okB && !(aB < 1.0f / 255.0f);
+                const f32x2 test_T = mul2(T[q], rsub2(pk(aA, aB), 1.0f));
+                upk(test_T, tA, tB);
+                upk(T[q], TA, TB);
+                if (cA && tA < 0.0001f) { doneA[q] = true; cA = false; }
+                if (cB && tB < 0.0001f) { doneB[q] = true; cB = false; }
+                if (!(cA || cB)) continue;
+                // a pixel that does not blend this Gaussian adds T * (0 * colour) = +-0
+                const f32x2 w = pk(cA ? aA : 0.0f, cB ? aB : 0.0f);
+                const float4 col = q2s[j];
+                C0[q] = fma2(T[q], mul2(w, pk1(col.x)), C0[q]);
+                C1[q] = fma2(T[q], mul2(w, pk1(col.y)), C1[q]);
+                C2[q] = fma2(T[q], mul2(w, pk1(col.z)), C2[q]);
+                T[q] = pk(cA ? tA : TA, cB ? tB : TB);
+                const uint32_t pos1 = __float_as_uint(g1.w);
+                lastA[q] = cA ? pos1 : lastA[q];
+                lastB[q] = cB ? pos1 : lastB[q];
+            }
+        }
+    }
+    const size_t HW = (size_t)a.H * a.W;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        float TA, TB, r0, r1, g0, g1, b0, b1;
+        upk(T[q], TA, TB); upk(C0[q], r0, r1); upk(C1[q], g0, g1); upk(C2[q], b0, b1);
+        if (inA[q]) {
+            const size_t pix = (size_t)pyi[q] * a.W + px;
+            a.final_T[pix] = TA;
+            a.n_contrib[pix] = lastA[q];
+            a.out_color[pix] = fmaf(TA, a.bg[0], r0);
+            a.out_color[HW + pix] = fmaf(TA, a.bg[1], g0);
+            a.out_color[2 * HW + pix] = fmaf(TA, a.bg[2], b0);
+        }
+        if (inB[q]) {
+            const size_t pix = (size_t)(pyi[q] + 1) * a.W + px;
+            a.final_T[pix] = TB;
+            a.n_contrib[pix] = lastB[q];
+            a.out_color[pix] = fmaf(TB, a.bg[0], r1);
+            a.out_color[HW + pix] = fmaf(TB, a.bg[1], g1);
+            a.out_color[2 * HW + pix] = fmaf(TB, a.bg[2], b1);
+        }
+    }
+}
+
+// exhaustive check kernel: exp1_exact / exp2_exact against expf on every float in [lo_bits, hi_bits]
+__global__ void exp_check_kernel(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long bad1 = 0, bad2 = 0;
+    for (uint64_t b = (uint64_t)lo_bits + blockIdx.x * blockDim.x + threadIdx.x; b <= hi_bits; b += stride) {
+        const float x = __uint_as_float((uint32_t)b);
+        const float r = expf(x);
+        const float e1 = exp1_exact(x);
+        float e2a, e2b;
+        const float xb = x * 0.5f;
+        upk(exp2_exact(pk(x, xb)), e2a, e2b);
+        const float rb = expf(xb);
+        bad1 += __float_as_uint(r) != __float_as_uint(e1);
+        bad2 += (__float_as_uint(r) != __float_as_uint(e2a)) || (__float_as_uint(rb) != __float_as_uint(e2b));
+    }
+    if (bad1) atomicAdd(&mismatches[0], bad1);
+    if (bad2) atomicAdd(&mismatches[1], bad2);
+}
+
+int env_int_v2(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
+    dim3 grid(a.grid_x, a.grid_y, 1);
+    static const int np = env_int_v2("GSR_FWD_NP", 1);
+    { GsrProfScope prof_("blend_fwd", stream);
+    if (np == 2) blend_fwd_v2_kernel<2><<<grid, 64, 0, stream>>>(a);
+    else blend_fwd_v2_kernel<1><<<grid, 128, 0, stream>>>(a); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+
+// out[0] = floats in [-x_max, -0] where exp1_exact != expf, out[1] = where the packed version differs
+int gsr_launch_exp_check(float x_max, unsigned long long* out2, cudaStream_t stream) {
+    GSR_CHECK(cudaMemsetAsync(out2, 0, 16, stream));
+    uint32_t hi_bits;
+    const float neg = -x_max;
+    memcpy(&hi_bits, &neg, 4);
+    exp_check_kernel<<<148 * 8, 256, 0, stream>>>(0x80000000u, hi_bits, out2);
+    GSR_CHECK_LAUNCH();
+    return 0;
+}

@@ -107,6 +107,8 @@ struct BlendFwdArgs {
     uint32_t* n_contrib;     // [H*W]
 };
 int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream);
+int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream);      // blend_v2.cu
+int gsr_launch_exp_check(float x_max, unsigned long long* out2, cudaStream_t stream);
 int gsr_launch_blend_stats(const BlendFwdArgs& a, unsigned long long* out8, cudaStream_t stream);
 
 struct BlendBwdArgs {

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
         if (g.ok) {
             // alpha = min(.99, op*exp(power)) >= 1/255 needs power >= log(1/(255 op)).
             // Margin 1e-3 dwarfs the rounding of expf and of this log.
-            float cut = (op > 0.0f) ? (__logf(1.0f / (255.0f * op)) - 1e-3f) : 1.0f;
+            float cut = (op > 0.0f) ? fmaxf(__logf(1.0f / (255.0f * op)) - 1e-3f, -80.0f) : 1.0f;   // >= -80: see f32x2.cuh exp2_exact
             radius = g.radius;
             tiles = (g.rmax.y - g.rmin.y) * (g.rmax.x - g.rmin.x);
             a.depths[idx] = g.depth;

@@ -74,6 +74,7 @@ _SIGNATURES = {
                                     _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
     "gsr_debug_blend_stats": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P]),
+    "gsr_debug_exp_check": (ctypes.c_int, [ctypes.c_float, _P, _P]),
     "gsr_mark_visible": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, _P, _P, _P]),
     "gsr_knn_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_knn_dist2": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_size_t, _P]),

@@ -152,6 +152,11 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
 int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t num_rendered, const void* geom_ws,
                           const void* binning_ws, const void* image_ws, unsigned long long* out8, void* stream);
 
+/* Debug/parity aid: compares the library's restatements of CUDA's expf (scalar and packed
+ * FP32x2, csrc/f32x2.cuh) with expf itself on EVERY float in [-x_max, -0]; writes the two
+ * mismatch counts to out2 (device u64[2]).  Both must be 0 for the blend to be bit-exact. */
+int gsr_debug_exp_check(float x_max, unsigned long long* out2, void* stream);
+
 /* ---- the rest of the reference's operator surface -------------------------- */
 int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t* present, void* stream);
 

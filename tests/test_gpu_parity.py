@@ -392,3 +392,14 @@ def test_accumulate_grads_matches_autograd_sum():
     a, b = run(True), run(False)
     for k in a:
         assert rel_to_max(a[k], b[k]) <= GRAD_TOL, k
+
+
+def test_packed_expf_is_cudas_expf_on_every_float():
+    """The blend kernels evaluate expf on packed FP32x2 values (csrc/f32x2.cuh) with CUDA's own algorithm restated;
+    it must be bit-identical to expf (what forward.cu:342 / backward.cu:472 compile to) on the whole range
+    a blended pair can produce: every float in [-80, -0]."""
+    import gsr_runtime as rt
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    rc = rt.load().gsr_debug_exp_check(80.0, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, rt.last_error()
+    assert out.tolist() == [0, 0]
