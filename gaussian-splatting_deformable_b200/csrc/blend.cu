@@ -586,6 +586,8 @@ int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
 
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
+    static const int ver = env_int("GSR_BLEND_BWD_V", 2);   // 2: blend_v2.cu, 1: this file
+    if (ver == 2) return gsr_launch_blend_bwd_v2(a, stream);
     static const int ppt = env_int("GSR_BWD_PPT", 4);
     static const int tma = env_int("GSR_BLEND_TMA", 0);   // measured 4% slower than the register-staged gather at C2
     { GsrProfScope prof_("blend_bwd", stream);

@@ -189,6 +189,213 @@ __global__ void __launch_bounds__(128 / NP) blend_fwd_v2_kernel(BlendFwdArgs a) 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Backward
+// ---------------------------------------------------------------------------
+// Sum v[0..8] over the warp.  On return lane 4k (k = 0..7) holds the total of v[k] in v[0];
+// every lane holds the total of v[8] in v[8].  (Transposing butterfly: 14 shuffles.)
+__device__ __forceinline__ void warp_reduce9_v2(float (&v)[9], int lane) {
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = up ? v[i] : v[i + 4];
+            const float keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float send = up ? v[i] : v[i + 2];
+            const float keep = up ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    v[0] += __shfl_xor_sync(FULL, v[0], 2);
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[8] += __shfl_xor_sync(FULL, v[8], o);
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Per pixel, back to front (backward.cu:443-548).  With d_j = colour_j . dL/dpixel the reference's
+// three-channel "accumulated colour behind j" recurrence collapses to one scalar per pixel:
+//   a_j = alpha_{j+1} d_{j+1} + (1 - alpha_{j+1}) a_{j+1},   dL/dalpha_j = T_j (d_j - a_j)
+// (same sum, associated per pixel instead of per channel; gradients carry a 1e-4 tolerance).
+// A half of a pair that does not blend Gaussian j runs with alpha = G = 0: T, a and every sum are
+// then unchanged exactly, so no per-half branches are needed.
+template <int NP>
+__global__ void __launch_bounds__(128 / NP) blend_bwd_v2_kernel(BlendBwdArgs a) {
+    constexpr int NW = 4 / NP;
+    __shared__ float4 s_q0[NW][32];                  // x, y, conic.x, -conic.y
+    __shared__ float4 s_q1[NW][32];                  // conic.z, opacity, cut, list position as bits
+    __shared__ float4 s_q2[NW][32];                  // r, g, b, Gaussian id as bits
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.y * a.grid_x + blockIdx.x;
+    const int X0 = blockIdx.x * GSR_TILE + ((NP == 1) ? ((warp & 1) << 3) : (warp << 3));
+    const int Y0 = blockIdx.y * GSR_TILE + ((NP == 1) ? ((warp >> 1) << 3) : 0);
+    if (X0 >= a.W || Y0 >= a.H) return;
+    const int px = X0 + (lane & 7);
+    const float pxf = (float)px;
+    const float rx0 = (float)X0, ry0 = (float)Y0;
+    const float rx1 = fminf(rx0 + 7.0f, (float)(a.W - 1)), ry1 = fminf(ry0 + (float)(8 * NP - 1), (float)(a.H - 1));
+    const size_t HW = (size_t)a.H * a.W;
+    const bool has_bg = (a.bg[0] != 0.0f) || (a.bg[1] != 0.0f) || (a.bg[2] != 0.0f);
+    const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+
+    f32x2 npy[NP], T[NP], nTfin[NP], dp0[NP], dp1[NP], dp2[NP], bgdot[NP], acc[NP], la[NP], ld[NP];
+    uint32_t lastA[NP], lastB[NP];
+    uint32_t wlast = 0;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        const int py = Y0 + 8 * q + 2 * (lane >> 3);
+        npy[q] = pk(-(float)py, -(float)(py + 1));
+        const bool inA = px < a.W && py < a.H, inB = px < a.W && py + 1 < a.H;
+        const size_t pA = (size_t)py * a.W + px, pB = pA + a.W;
+        const float TA = inA ? a.final_T[pA] : 0.0f, TB = inB ? a.final_T[pB] : 0.0f;
+        lastA[q] = inA ? a.n_contrib[pA] : 0u;
+        lastB[q] = inB ? a.n_contrib[pB] : 0u;
+        float d[6] = {0, 0, 0, 0, 0, 0};
+        if (inA) { d[0] = a.dL_dpix[pA]; d[2] = a.dL_dpix[HW + pA]; d[4] = a.dL_dpix[2 * HW + pA]; }
+        if (inB) { d[1] = a.dL_dpix[pB]; d[3] = a.dL_dpix[HW + pB]; d[5] = a.dL_dpix[2 * HW + pB]; }
+        T[q] = pk(TA, TB); nTfin[q] = pk(-TA, -TB);
+        dp0[q] = pk(d[0], d[1]); dp1[q] = pk(d[2], d[3]); dp2[q] = pk(d[4], d[5]);
+        bgdot[q] = pk(a.bg[0] * d[0] + a.bg[1] * d[2] + a.bg[2] * d[4], a.bg[0] * d[1] + a.bg[1] * d[3] + a.bg[2] * d[5]);
+        acc[q] = la[q] = ld[q] = pk1(0.0f);
+        wlast = max(wlast, max(lastA[q], lastB[q]));
+    }
+    // nothing behind the region's deepest contributor matters to any of its pixels
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wlast = max(wlast, __shfl_xor_sync(FULL, wlast, o));
+    const uint2 range = a.ranges[tile];
+    float4* const q0s = s_q0[warp]; float4* const q1s = s_q1[warp]; float4* const q2s = s_q2[warp];
+    float* const grad_base = reinterpret_cast<float*>(a.grad_recs);
+
+    float4 n0, n1, n2;
+    uint32_t nid = 0;
+    bool nvalid = false;
+    auto fetch = [&](int start) {          // positions start-1, start-2, ... (back to front)
+        const int pos = start - 1 - lane;
+        nvalid = pos >= 0;
+        if (nvalid) {
+            nid = a.point_list[range.x + pos];
+            const float4* r = a.recs + 3 * (size_t)nid;
+            n0 = __ldg(r); n1 = __ldg(r + 1); n2 = __ldg(r + 2);
+        }
+    };
+    if (wlast > 0) fetch((int)wlast);
+    for (int start = (int)wlast; start > 0; start -= 32) {
+        const float4 c0 = n0, c1 = n1, c2 = n2;
+        const uint32_t cid = nid;
+        const bool keep = nvalid && rect_may_contribute(c0.x, c0.y, c0.z, c0.w, c1.x, c2.y, rx0, ry0, rx1, ry1);
+        if (start - 32 > 0) fetch(start - 32);
+        const unsigned m = __ballot_sync(FULL, keep);
+        const int n = __popc(m);
+        __syncwarp();
+        if (keep) {
+            const int slot = __popc(m & ((1u << lane) - 1u));
+            q0s[slot] = make_float4(c0.x, c0.y, c0.z, -c0.w);
+            q1s[slot] = make_float4(c1.x, c1.y, c2.y, __uint_as_float((uint32_t)(start - 1 - lane)));
+            q2s[slot] = make_float4(c1.z, c1.w, c2.x, __uint_as_float(cid));
+        }
+        __syncwarp();
+        for (int j = 0; j < n; j++) {
+            const float4 g0 = q0s[j];
+            const float4 g1 = q1s[j];
+            const uint32_t pos_j = __float_as_uint(g1.w);
+            const float dx = g0.x - pxf;
+            const float s1 = FMUL(dx, g0.z), s2 = FMUL(dx, g0.w);
+            f32x2 V[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) V[k] = pk1(0.0f);
+            bool any_act = false;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const f32x2 dy = add2(pk1(g0.y), npy[q]);
+                const f32x2 pw = power2_exact(dx, s1, s2, dy, g1.x);
+                float pA, pB;
+                upk(pw, pA, pB);
+                const bool okA = pos_j < lastA[q] && !(pA > 0.0f || pA < g1.z);
+                const bool okB = pos_j < lastB[q] && !(pB > 0.0f || pB < g1.z);
+                if (!(okA || okB)) continue;
+                const f32x2 Gp = exp2_exact(pw);
+                float GA, GB, aA, aB;
+                upk(Gp, GA, GB);
+                upk(mul2(pk1(g1.y), Gp), aA, aB);
+                aA = fminf(0.99f, aA); aB = fminf(0.99f, aB);
+                const bool actA = okA && !(aA < 1.0f / 255.0f);
+                const bool actB = okB && !(aB < 1.0f / 255.0f);
+                if (!(actA || actB)) continue;
+                any_act = true;
+                const f32x2 G = pk(actA ? GA : 0.0f, actB ? GB : 0.0f);
+                const f32x2 alpha = pk(actA ? aA : 0.0f, actB ? aB : 0.0f);
+                const float4 col = q2s[j];
+                // T_j = T_{j+1} / (1 - alpha): MUFU.RCP + one Newton step
+                const f32x2 om = rsub2(alpha, 1.0f);
+                float o0, o1;
+                upk(om, o0, o1);
+                const float r0 = rcp_approx(o0), r1 = rcp_approx(o1);
+                const f32x2 r = pk(r0, r1);
+                const f32x2 inv = fma2(r, fma2(om, pk(-r0, -r1), pk1(1.0f)), r);
+                T[q] = mul2(T[q], inv);
+                const f32x2 dcd = mul2(alpha, T[q]);                     // dchannel_dcolor
+                const f32x2 d = fma2(pk1(col.z), dp2[q], fma2(pk1(col.y), dp1[q], mul2(pk1(col.x), dp0[q])));
+                float ac0, ac1;
+                upk(acc[q], ac0, ac1);
+                const f32x2 nacc = pk(-ac0, -ac1);
+                acc[q] = fma2(la[q], add2(ld[q], nacc), acc[q]);          // a = la*ld + (1-la)*a
+                la[q] = alpha; ld[q] = d;
+                upk(acc[q], ac0, ac1);
+                f32x2 dL_dalpha = mul2(add2(d, pk(-ac0, -ac1)), T[q]);
+                if (has_bg) dL_dalpha = fma2(mul2(nTfin[q], inv), bgdot[q], dL_dalpha);
+                const f32x2 dL_dG = mul2(pk1(g1.y), dL_dalpha);
+                const f32x2 gdx = mul2(G, pk1(dx)), gdy = mul2(G, dy);
+                const f32x2 dG_ddelx = fma2(gdx, pk1(-g0.z), mul2(gdy, pk1(g0.w)));
+                const f32x2 dG_ddely = fma2(gdy, pk1(-g1.x), mul2(gdx, pk1(g0.w)));
+                const f32x2 h = mul2(dL_dG, pk1(-0.5f));
+                const f32x2 hgdx = mul2(h, gdx), hgdy = mul2(h, gdy);
+                V[0] = fma2(dL_dG, dG_ddelx, V[0]);
+                V[1] = fma2(dL_dG, dG_ddely, V[1]);
+                V[2] = fma2(hgdx, pk1(dx), V[2]);
+                V[3] = fma2(hgdx, dy, V[3]);
+                V[4] = fma2(hgdy, dy, V[4]);
+                V[5] = fma2(G, dL_dalpha, V[5]);
+                V[6] = fma2(dcd, dp0[q], V[6]);
+                V[7] = fma2(dcd, dp1[q], V[7]);
+                V[8] = fma2(dcd, dp2[q], V[8]);
+            }
+            if (!__any_sync(FULL, any_act)) continue;
+            float v[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) { float x0, x1; upk(V[k], x0, x1); v[k] = x0 + x1; }
+            warp_reduce9_v2(v, lane);
+            float* dst = grad_base + 12 * (size_t)__float_as_uint(q2s[j].w);
+            if ((lane & 3) == 0) {
+                const int k = lane >> 2;
+                float val = v[0];
+                if (k == 0) val *= ddelx_dx;
+                if (k == 1) val *= ddely_dy;
+                atomicAdd(dst + k, val);
+            } else if (lane == 1) {
+                atomicAdd(dst + 8, v[8]);
+            }
+        }
+    }
+}
+
 // exhaustive check kernel: exp1_exact / exp2_exact against expf on every float in [lo_bits, hi_bits]
 __global__ void exp_check_kernel(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches) {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -221,6 +428,16 @@ int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
     { GsrProfScope prof_("blend_fwd", stream);
     if (np == 2) blend_fwd_v2_kernel<2><<<grid, 64, 0, stream>>>(a);
     else blend_fwd_v2_kernel<1><<<grid, 128, 0, stream>>>(a); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+
+int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream) {
+    dim3 grid(a.grid_x, a.grid_y, 1);
+    static const int np = env_int_v2("GSR_BWD_NP", 2);
+    { GsrProfScope prof_("blend_bwd", stream);
+    if (np == 2) blend_bwd_v2_kernel<2><<<grid, 64, 0, stream>>>(a);
+    else blend_bwd_v2_kernel<1><<<grid, 128, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

@@ -120,6 +120,7 @@ struct BlendBwdArgs {
     float4* grad_recs;       // [P,3], zero-initialised by the caller
 };
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream);
+int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream);   // blend_v2.cu
 
 // ---- fused per-Gaussian backward ------------------------------------------
 struct PreprocessBwdArgs {
