@@ -232,11 +232,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // Per pixel, back to front (backward.cu:443-548).  With d_j = colour_j . dL/dpixel the reference's
-// three-channel "accumulated colour behind j" recurrence collapses to one scalar per pixel:
-//   a_j = alpha_{j+1} d_{j+1} + (1 - alpha_{j+1}) a_{j+1},   dL/dalpha_j = T_j (d_j - a_j)
+// three-channel "accumulated colour behind j" recurrence (with its pending last_alpha/last_color)
+// collapses to one scalar per pixel, updated right after use:
+//   dL/dalpha_j = T_j (d_j - a_j),   a_{j-1} = alpha_j d_j + (1 - alpha_j) a_j = fma(alpha_j, d_j - a_j, a_j)
 // (same sum, associated per pixel instead of per channel; gradients carry a 1e-4 tolerance).
-// A half of a pair that does not blend Gaussian j runs with alpha = G = 0: T, a and every sum are
-// then unchanged exactly, so no per-half branches are needed.
+// A pixel that does not blend Gaussian j runs with alpha = G = 0: T, a and every sum are then
+// unchanged exactly, so the loop body is straight-line code behind two warp-uniform skips.
 template <int NP>
 __global__ void __launch_bounds__(128 / NP) blend_bwd_v2_kernel(BlendBwdArgs a) {
     constexpr int NW = 4 / NP;
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(128 / NP) blend_bwd_v2_kernel(BlendBwdArgs a) 
     const bool has_bg = (a.bg[0] != 0.0f) || (a.bg[1] != 0.0f) || (a.bg[2] != 0.0f);
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
 
-    f32x2 npy[NP], T[NP], nTfin[NP], dp0[NP], dp1[NP], dp2[NP], bgdot[NP], acc[NP], la[NP], ld[NP];
+    f32x2 npy[NP], T[NP], nTfin[NP], dp0[NP], dp1[NP], dp2[NP], bgdot[NP], acc[NP];
     uint32_t lastA[NP], lastB[NP];
     uint32_t wlast = 0;
 #pragma unroll
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(128 / NP) blend_bwd_v2_kernel(BlendBwdArgs a) 
         T[q] = pk(TA, TB); nTfin[q] = pk(-TA, -TB);
         dp0[q] = pk(d[0], d[1]); dp1[q] = pk(d[2], d[3]); dp2[q] = pk(d[4], d[5]);
         bgdot[q] = pk(a.bg[0] * d[0] + a.bg[1] * d[2] + a.bg[2] * d[4], a.bg[0] * d[1] + a.bg[1] * d[3] + a.bg[2] * d[5]);
-        acc[q] = la[q] = ld[q] = pk1(0.0f);
+        acc[q] = pk1(0.0f);
         wlast = max(wlast, max(lastA[q], lastB[q]));
     }
     // nothing behind the region's deepest contributor matters to any of its pixels
@@ -318,71 +319,89 @@ __global__ void __launch_bounds__(128 / NP) blend_bwd_v2_kernel(BlendBwdArgs a) 
             const uint32_t pos_j = __float_as_uint(g1.w);
             const float dx = g0.x - pxf;
             const float s1 = FMUL(dx, g0.z), s2 = FMUL(dx, g0.w);
-            f32x2 V[9];
+            // Every branch below is warp-uniform: a lane whose pixels do not blend Gaussian j runs the
+            // same straight-line code with alpha = G = 0 (a per-lane branch would save no issue slot).
+            f32x2 dy[NP], pw[NP];
+            bool okA[NP], okB[NP];
+            bool any_ok = false;
 #pragma unroll
-            for (int k = 0; k < 9; k++) V[k] = pk1(0.0f);
+            for (int q = 0; q < NP; q++) {
+                dy[q] = add2(pk1(g0.y), npy[q]);
+                pw[q] = power2_exact(dx, s1, s2, dy[q], g1.x);
+                float pA, pB;
+                upk(pw[q], pA, pB);
+                okA[q] = pos_j < lastA[q] && !(pA > 0.0f || pA < g1.z);
+                okB[q] = pos_j < lastB[q] && !(pB > 0.0f || pB < g1.z);
+                any_ok = any_ok || okA[q] || okB[q];
+            }
+            if (!__any_sync(FULL, any_ok)) continue;
+            f32x2 G[NP], alpha[NP];
             bool any_act = false;
 #pragma unroll
             for (int q = 0; q < NP; q++) {
-                const f32x2 dy = add2(pk1(g0.y), npy[q]);
-                const f32x2 pw = power2_exact(dx, s1, s2, dy, g1.x);
-                float pA, pB;
-                upk(pw, pA, pB);
-                const bool okA = pos_j < lastA[q] && !(pA > 0.0f || pA < g1.z);
-                const bool okB = pos_j < lastB[q] && !(pB > 0.0f || pB < g1.z);
-                if (!(okA || okB)) continue;
-                const f32x2 Gp = exp2_exact(pw);
+                const f32x2 Gp = exp2_exact(pw[q]);
                 float GA, GB, aA, aB;
                 upk(Gp, GA, GB);
                 upk(mul2(pk1(g1.y), Gp), aA, aB);
                 aA = fminf(0.99f, aA); aB = fminf(0.99f, aB);
-                const bool actA = okA && !(aA < 1.0f / 255.0f);
-                const bool actB = okB && !(aB < 1.0f / 255.0f);
-                if (!(actA || actB)) continue;
-                any_act = true;
-                const f32x2 G = pk(actA ? GA : 0.0f, actB ? GB : 0.0f);
-                const f32x2 alpha = pk(actA ? aA : 0.0f, actB ? aB : 0.0f);
-                const float4 col = q2s[j];
+                const bool actA = okA[q] && !(aA < 1.0f / 255.0f);
+                const bool actB = okB[q] && !(aB < 1.0f / 255.0f);
+                any_act = any_act || actA || actB;
+                G[q] = pk(actA ? GA : 0.0f, actB ? GB : 0.0f);
+                alpha[q] = pk(actA ? aA : 0.0f, actB ? aB : 0.0f);
+            }
+            if (!__any_sync(FULL, any_act)) continue;
+            const float4 col = q2s[j];
+            f32x2 V[9];
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
                 // T_j = T_{j+1} / (1 - alpha): MUFU.RCP + one Newton step
-                const f32x2 om = rsub2(alpha, 1.0f);
+                const f32x2 om = rsub2(alpha[q], 1.0f);
                 float o0, o1;
                 upk(om, o0, o1);
                 const float r0 = rcp_approx(o0), r1 = rcp_approx(o1);
                 const f32x2 r = pk(r0, r1);
                 const f32x2 inv = fma2(r, fma2(om, pk(-r0, -r1), pk1(1.0f)), r);
                 T[q] = mul2(T[q], inv);
-                const f32x2 dcd = mul2(alpha, T[q]);                     // dchannel_dcolor
+                const f32x2 dcd = mul2(alpha[q], T[q]);                   // dchannel_dcolor
                 const f32x2 d = fma2(pk1(col.z), dp2[q], fma2(pk1(col.y), dp1[q], mul2(pk1(col.x), dp0[q])));
-                float ac0, ac1;
-                upk(acc[q], ac0, ac1);
-                const f32x2 nacc = pk(-ac0, -ac1);
-                acc[q] = fma2(la[q], add2(ld[q], nacc), acc[q]);          // a = la*ld + (1-la)*a
-                la[q] = alpha; ld[q] = d;
-                upk(acc[q], ac0, ac1);
-                f32x2 dL_dalpha = mul2(add2(d, pk(-ac0, -ac1)), T[q]);
+                const f32x2 diff = fma2(acc[q], pk1(-1.0f), d);           // d_j - a_j
+                f32x2 dL_dalpha = mul2(diff, T[q]);
+                acc[q] = fma2(alpha[q], diff, acc[q]);                    // a_{j-1} = alpha_j d_j + (1 - alpha_j) a_j
                 if (has_bg) dL_dalpha = fma2(mul2(nTfin[q], inv), bgdot[q], dL_dalpha);
                 const f32x2 dL_dG = mul2(pk1(g1.y), dL_dalpha);
-                const f32x2 gdx = mul2(G, pk1(dx)), gdy = mul2(G, dy);
+                const f32x2 gdx = mul2(G[q], pk1(dx)), gdy = mul2(G[q], dy[q]);
                 const f32x2 dG_ddelx = fma2(gdx, pk1(-g0.z), mul2(gdy, pk1(g0.w)));
                 const f32x2 dG_ddely = fma2(gdy, pk1(-g1.x), mul2(gdx, pk1(g0.w)));
                 const f32x2 h = mul2(dL_dG, pk1(-0.5f));
                 const f32x2 hgdx = mul2(h, gdx), hgdy = mul2(h, gdy);
-                V[0] = fma2(dL_dG, dG_ddelx, V[0]);
-                V[1] = fma2(dL_dG, dG_ddely, V[1]);
-                V[2] = fma2(hgdx, pk1(dx), V[2]);
-                V[3] = fma2(hgdx, dy, V[3]);
-                V[4] = fma2(hgdy, dy, V[4]);
-                V[5] = fma2(G, dL_dalpha, V[5]);
-                V[6] = fma2(dcd, dp0[q], V[6]);
-                V[7] = fma2(dcd, dp1[q], V[7]);
-                V[8] = fma2(dcd, dp2[q], V[8]);
+                if (q == 0) {
+                    V[0] = mul2(dL_dG, dG_ddelx);
+                    V[1] = mul2(dL_dG, dG_ddely);
+                    V[2] = mul2(hgdx, pk1(dx));
+                    V[3] = mul2(hgdx, dy[q]);
+                    V[4] = mul2(hgdy, dy[q]);
+                    V[5] = mul2(G[q], dL_dalpha);
+                    V[6] = mul2(dcd, dp0[q]);
+                    V[7] = mul2(dcd, dp1[q]);
+                    V[8] = mul2(dcd, dp2[q]);
+                } else {
+                    V[0] = fma2(dL_dG, dG_ddelx, V[0]);
+                    V[1] = fma2(dL_dG, dG_ddely, V[1]);
+                    V[2] = fma2(hgdx, pk1(dx), V[2]);
+                    V[3] = fma2(hgdx, dy[q], V[3]);
+                    V[4] = fma2(hgdy, dy[q], V[4]);
+                    V[5] = fma2(G[q], dL_dalpha, V[5]);
+                    V[6] = fma2(dcd, dp0[q], V[6]);
+                    V[7] = fma2(dcd, dp1[q], V[7]);
+                    V[8] = fma2(dcd, dp2[q], V[8]);
+                }
             }
-            if (!__any_sync(FULL, any_act)) continue;
             float v[9];
 #pragma unroll
             for (int k = 0; k < 9; k++) { float x0, x1; upk(V[k], x0, x1); v[k] = x0 + x1; }
             warp_reduce9_v2(v, lane);
-            float* dst = grad_base + 12 * (size_t)__float_as_uint(q2s[j].w);
+            float* dst = grad_base + 12 * (size_t)__float_as_uint(col.w);
             if ((lane & 3) == 0) {
                 const int k = lane >> 2;
                 float val = v[0];
@@ -434,7 +453,7 @@ int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
 
 int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
-    static const int np = env_int_v2("GSR_BWD_NP", 2);
+    static const int np = env_int_v2("GSR_BWD_NP", 1);
     { GsrProfScope prof_("blend_bwd", stream);
     if (np == 2) blend_bwd_v2_kernel<2><<<grid, 64, 0, stream>>>(a);
     else blend_bwd_v2_kernel<1><<<grid, 128, 0, stream>>>(a); }
