@@ -63,8 +63,8 @@ __device__ __forceinline__ f32x2 power2_exact(float dx, float s1, float s2, f32x
 // ---------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------
-template <int NP>
-__global__ void __launch_bounds__(128 / NP) blend_fwd_v2_kernel(BlendFwdArgs a) {
+template <int NP, int MINB>
+__global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdArgs a) {
     constexpr int NW = 4 / NP;                       // warps (regions) per tile
     __shared__ float4 s_q0[NW][32];                  // x, y, conic.x, -conic.y
     __shared__ float4 s_q1[NW][32];                  // conic.z, opacity, cut, (list position + 1) as bits
@@ -238,8 +238,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // (same sum, associated per pixel instead of per channel; gradients carry a 1e-4 tolerance).
 // A pixel that does not blend Gaussian j runs with alpha = G = 0: T, a and every sum are then
 // unchanged exactly, so the loop body is straight-line code behind two warp-uniform skips.
-template <int NP>
-__global__ void __launch_bounds__(128 / NP) blend_bwd_v2_kernel(BlendBwdArgs a) {
+template <int NP, int MINB>
+__global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdArgs a) {
     constexpr int NW = 4 / NP;
     __shared__ float4 s_q0[NW][32];                  // x, y, conic.x, -conic.y
     __shared__ float4 s_q1[NW][32];                  // conic.z, opacity, cut, list position as bits
@@ -445,8 +445,10 @@ int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int np = env_int_v2("GSR_FWD_NP", 1);
     { GsrProfScope prof_("blend_fwd", stream);
-    if (np == 2) blend_fwd_v2_kernel<2><<<grid, 64, 0, stream>>>(a);
-    else blend_fwd_v2_kernel<1><<<grid, 128, 0, stream>>>(a); }
+    static const int minb = env_int_v2("GSR_FWD_MINB", 1);
+    if (np == 2) blend_fwd_v2_kernel<2, 0><<<grid, 64, 0, stream>>>(a);
+    else if (minb >= 8) blend_fwd_v2_kernel<1, 8><<<grid, 128, 0, stream>>>(a);
+    else blend_fwd_v2_kernel<1, 0><<<grid, 128, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -455,8 +457,10 @@ int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int np = env_int_v2("GSR_BWD_NP", 1);
     { GsrProfScope prof_("blend_bwd", stream);
-    if (np == 2) blend_bwd_v2_kernel<2><<<grid, 64, 0, stream>>>(a);
-    else blend_bwd_v2_kernel<1><<<grid, 128, 0, stream>>>(a); }
+    static const int minb = env_int_v2("GSR_BWD_MINB", 8);
+    if (np == 2) blend_bwd_v2_kernel<2, 0><<<grid, 64, 0, stream>>>(a);
+    else if (minb >= 8) blend_bwd_v2_kernel<1, 8><<<grid, 128, 0, stream>>>(a);
+    else blend_bwd_v2_kernel<1, 0><<<grid, 128, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

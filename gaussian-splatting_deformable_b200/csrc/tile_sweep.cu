@@ -112,6 +112,34 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_sweep_kernel(const 
     }
 }
 
+// Up-sweep, order-free variant: counting does not care in which order the Gaussians of a chunk
+// are visited, so one THREAD takes a Gaussian and bumps a CTA-wide counter array covering the whole
+// tile grid (4 B x tiles of shared memory; 32 KB at 1080p, 127 KB at 4K).  The warp-per-stripe sweep
+// above spends 17 warps re-scanning every chunk with 7 of 32 lanes busy; this does the same
+// counting in a tenth of the instructions.  The rank-producing down-sweep keeps the ordered sweep.
+__global__ void __launch_bounds__(1024) tile_count_kernel(const uint32_t* __restrict__ n_emit_p,
+                                                          const uint4* __restrict__ srec, GsrTileBinPlan pl, int grid_x,
+                                                          uint32_t* __restrict__ matrix) {
+    extern __shared__ uint32_t s_cnt_all[];
+    const int chunk = blockIdx.x;
+    for (int i = threadIdx.x; i < pl.num_tiles; i += blockDim.x) s_cnt_all[i] = 0u;
+    __syncthreads();
+    const uint32_t n_emit = *n_emit_p;
+    const uint32_t G = (((n_emit + pl.chunks - 1) / pl.chunks) + 31u) & ~31u;   // same chunking as the sweep
+    const uint32_t g_begin = chunk * G, g_end = min(n_emit, g_begin + G);
+    for (uint32_t g = g_begin + threadIdx.x; g < g_end; g += blockDim.x) {
+        const uint4 rec = srec[g];
+        const uint32_t x0 = rec.y & 0xffffu, y0 = rec.y >> 16, x1 = rec.z & 0xffffu, y1 = rec.z >> 16;
+        for (uint32_t y = y0; y < y1; y++) {
+            uint32_t* row = s_cnt_all + y * (uint32_t)grid_x;
+            for (uint32_t x = x0; x < x1; x++) atomicAdd(row + x, 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t* mrow = matrix + (size_t)chunk * pl.num_tiles;
+    for (int i = threadIdx.x; i < pl.num_tiles; i += blockDim.x) mrow[i] = s_cnt_all[i];
+}
+
 // Column scan of the chunk x tile count matrix: in place, counts -> exclusive prefix over the
 // chunks; totals[tile] = column sum.  CTA = 32 tiles x 8 row segments: every thread sums its
 // segment, the 8 partial sums are scanned in shared memory, then the segment is rewritten.
@@ -249,8 +277,20 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order
     gather_rects_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(n_emit, order, rects, srec); }
     GSR_CHECK_LAUNCH();
     const dim3 grid(pl.chunks, pl.groups, 1);
-    { GsrProfScope prof_("tile_sweep_count", stream);
-    tile_sweep_kernel<false><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list); }
+    static const int count_v = env_int2("GSR_SWEEP_COUNT_V", 2);
+    const size_t cnt_smem = (size_t)pl.num_tiles * sizeof(uint32_t);
+    if (count_v == 2 && cnt_smem <= 200 * 1024) {
+        static bool cattr_done = false;
+        if (!cattr_done) {
+            GSR_CHECK(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            cattr_done = true;
+        }
+        GsrProfScope prof_("tile_count", stream);
+        tile_count_kernel<<<pl.chunks, cnt_smem <= 48 * 1024 ? 256 : 1024, cnt_smem, stream>>>(n_emit, srec, pl, grid_x, matrix);
+    } else {
+        GsrProfScope prof_("tile_sweep_count", stream);
+        tile_sweep_kernel<false><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list);
+    }
     GSR_CHECK_LAUNCH();
     { GsrProfScope prof_("tile_column_scan", stream);
     tile_column_scan_kernel<<<gsr_div_up(pl.num_tiles, 32), 256, 0, stream>>>(pl.chunks, pl.num_tiles, matrix, totals); }
