@@ -140,6 +140,93 @@ __global__ void __launch_bounds__(1024) tile_count_kernel(const uint32_t* __rest
     for (int i = threadIdx.x; i < pl.num_tiles; i += blockDim.x) mrow[i] = s_cnt_all[i];
 }
 
+// Down-sweep, second generation.  CTA = (chunk, group of GSR_SWEEP_WARPS stripes).  The chunk is taken
+// in sub-batches of GSR_SCATTER_SUB Gaussians: (1) all warps stage the sub-batch's rect records in
+// shared memory and, with one ballot per stripe, write a bitmap "Gaussian i touches stripe s";
+// (2) warp s walks the set bits of ITS bitmap in order (= depth order) and ranks/scatters the cells of
+// each Gaussian with one returning shared atomic per lane, as in tile_sweep_kernel.  A stripe warp
+// thus only ever visits the Gaussians that reach its stripe (1 in 9 at 1080p) instead of scanning
+// the whole chunk, and the rect arrives by one broadcast LDS.128 instead of three shuffles.
+#define GSR_SCATTER_SUB 1024
+__global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(const uint32_t* __restrict__ n_emit_p,
+                                                                           const uint4* __restrict__ srec, GsrTileBinPlan pl,
+                                                                           int grid_x, int grid_y,
+                                                                           const uint32_t* __restrict__ matrix,
+                                                                           const uint32_t* __restrict__ tile_base,
+                                                                           uint32_t* __restrict__ point_list) {
+    constexpr int ROWS = GSR_SWEEP_ROWS, CW = 32 / ROWS;
+    extern __shared__ uint32_t s_cnt_all[];                                   // [warps][stripe_tiles]
+    __shared__ uint4 s_rec[GSR_SCATTER_SUB];
+    __shared__ uint32_t s_bits[GSR_SWEEP_WARPS][GSR_SCATTER_SUB / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stripe = blockIdx.y * GSR_SWEEP_WARPS + warp;
+    const bool live = stripe < pl.stripes;
+    uint32_t* cnt = s_cnt_all + warp * pl.stripe_tiles;
+    const int row0 = stripe * ROWS;
+    const int row1 = min(grid_y, row0 + ROWS);
+    const int tile0 = row0 * grid_x, ntile = live ? (row1 - row0) * grid_x : 0;
+    const int chunk = blockIdx.x;
+    const uint32_t n_emit = *n_emit_p;
+    const uint32_t G = (((n_emit + pl.chunks - 1) / pl.chunks) + 31u) & ~31u;
+    const uint32_t g_begin = chunk * G, g_end = min(n_emit, g_begin + G);
+    if (g_begin >= g_end) return;
+    const uint32_t* mrow = matrix + (size_t)chunk * pl.num_tiles + tile0;
+    for (int i = lane; i < ntile; i += 32) cnt[i] = tile_base[tile0 + i] + mrow[i];
+    const int grow0 = blockIdx.y * GSR_SWEEP_WARPS * ROWS;                    // first tile row of this CTA's stripes
+    const int lrow = lane / CW, lcol = lane % CW;
+    uint32_t* const cnt_lane = cnt + (lrow - row0) * grid_x + lcol;
+
+    for (uint32_t sb = g_begin; sb < g_end; sb += GSR_SCATTER_SUB) {
+        const uint32_t sn = min((uint32_t)GSR_SCATTER_SUB, g_end - sb);
+        __syncthreads();                                                      // previous sub-batch fully consumed
+        // (1) stage + bitmaps: warp w takes Gaussians w*32 + lane, + 256, ...
+        for (uint32_t i0 = warp * 32; i0 < sn; i0 += 32 * GSR_SWEEP_WARPS) {
+            const uint32_t i = i0 + lane;
+            uint4 rec = make_uint4(0, 0, 0, 0);
+            if (i < sn) rec = srec[sb + i];
+            s_rec[i0 + lane] = rec;
+            const int y0 = rec.y >> 16, y1 = rec.z >> 16;
+            const bool any = (rec.z & 0xffffu) > (rec.y & 0xffffu);
+#pragma unroll
+            for (int s = 0; s < GSR_SWEEP_WARPS; s++) {
+                const int r0 = grow0 + s * ROWS;
+                const unsigned m = __ballot_sync(FULL, any && y0 < r0 + ROWS && y1 > r0);
+                if (lane == 0) s_bits[s][i0 >> 5] = m;
+            }
+        }
+        __syncthreads();
+        if (!live) continue;
+        // (2) ordered walk over this stripe's Gaussians
+        const int nwords = (int)((sn + 31) >> 5);
+        for (int k = 0; k < nwords; k++) {
+            uint32_t m = s_bits[warp][k];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const uint4 rec = s_rec[32 * k + b];
+                const int x0 = rec.y & 0xffffu, y0 = rec.y >> 16, x1 = rec.z & 0xffffu, y1 = rec.z >> 16;
+                const int cy0 = max(y0, row0), cy1 = min(y1, row1);
+                const int gw = x1 - x0, gh = cy1 - cy0;
+                const bool rowok = lrow < gh;
+                uint32_t* cell = cnt_lane + cy0 * grid_x + x0;          // this lane's cell of the first 4 x 8 window
+                if (rowok && lcol < gw) {
+                    const uint32_t pos = atomicAdd(cell, 1u);
+                    point_list[pos] = rec.x;
+                }
+                if (gw > CW) {                                           // wider than the window: rare, warp-uniform
+#pragma unroll 1
+                    for (int c = CW; c < gw; c += CW) {
+                        if (rowok && lcol + c < gw) {
+                            const uint32_t pos = atomicAdd(cell + c, 1u);
+                            point_list[pos] = rec.x;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Column scan of the chunk x tile count matrix: in place, counts -> exclusive prefix over the
 // chunks; totals[tile] = column sum.  CTA = 32 tiles x 8 row segments: every thread sums its
 // segment, the 8 partial sums are scanned in shared memory, then the segment is rewritten.
@@ -247,7 +334,7 @@ GsrTileBinPlan gsr_make_tile_bin_plan(int grid_x, int grid_y) {
     if (forced || grid_x <= 0 || grid_y <= 0 || grid_x * GSR_SWEEP_ROWS > GSR_SWEEP_MAX_STRIPE_TILES) { pl.feasible = 0; return pl; }
     pl.feasible = 1;
     static const int c_env = env_int2("GSR_SWEEP_CHUNKS", 0);
-    pl.chunks = (c_env > 0 && c_env <= GSR_SWEEP_MAX_CHUNKS) ? c_env : 512;
+    pl.chunks = (c_env > 0 && c_env <= GSR_SWEEP_MAX_CHUNKS) ? c_env : 768;
     pl.stripes = (grid_y + GSR_SWEEP_ROWS - 1) / GSR_SWEEP_ROWS;
     pl.groups = (pl.stripes + GSR_SWEEP_WARPS - 1) / GSR_SWEEP_WARPS;
     pl.stripe_tiles = GSR_SWEEP_ROWS * grid_x;
@@ -298,8 +385,20 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order
     { GsrProfScope prof_("tile_base_scan", stream);
     tile_base_kernel<<<1, 1024, 0, stream>>>(pl.num_tiles, totals, tile_base, ranges); }
     GSR_CHECK_LAUNCH();
-    { GsrProfScope prof_("tile_sweep_scatter", stream);
-    tile_sweep_kernel<true><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list); }
+    static const int scatter_v = env_int2("GSR_SWEEP_SCATTER_V", 2);
+    if (scatter_v == 2) {
+        static bool sattr_done = false;
+        if (!sattr_done) {
+            GSR_CHECK(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           GSR_SWEEP_WARPS * GSR_SWEEP_MAX_STRIPE_TILES * (int)sizeof(uint32_t)));
+            sattr_done = true;
+        }
+        GsrProfScope prof_("tile_scatter", stream);
+        tile_scatter_kernel<<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list);
+    } else {
+        GsrProfScope prof_("tile_sweep_scatter", stream);
+        tile_sweep_kernel<true><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list);
+    }
     GSR_CHECK_LAUNCH();
     return 0;
 }
