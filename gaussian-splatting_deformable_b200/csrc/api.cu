@@ -439,6 +439,8 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
     }
     a.scales = scales; a.rotations = rotations; a.shs = shs; a.cov3D_precomp = cov3D_precomp; a.colors_precomp = colors_precomp;
     a.radii = radii; a.clamped = reinterpret_cast<const uint8_t*>(gw + L.clamped); a.grad_recs = grad_recs;
+    a.grad_moments = (R > 0) ? gsr_blend_bwd_writes_moments() : 0;
+    a.recs = reinterpret_cast<const float4*>(gw + L.recs); a.half_W = 0.5f * v.W; a.half_H = 0.5f * v.H;
     a.dL_dmeans3D = dL_dmeans3D; a.dL_dmeans2D = dL_dmeans2D; a.dL_dopacity = dL_dopacity; a.dL_dcolors = dL_dcolors;
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = scales ? dL_dscales : nullptr;
     a.dL_drots = scales ? dL_drots : nullptr;

@@ -95,8 +95,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
     if (visible) {
         // ================= (2) all loads =================
         const float4* gr = a.grad_recs + 3 * (size_t)idx;
-        const float4 g0 = gr[0], g1 = gr[1];
+        float4 g0 = gr[0], g1 = gr[1];
         const float g2x = reinterpret_cast<const float*>(gr + 2)[0];
+        float4 sp0 = make_float4(0, 0, 0, 0);
+        float2 sp1 = make_float2(0, 0);
+        if (a.grad_moments) {
+            const float4* sp = a.recs + 3 * (size_t)idx;
+            sp0 = sp[0]; sp1 = *reinterpret_cast<const float2*>(sp + 1);
+        }
         const float* mp = (a.means_deformed ? a.means_deformed : a.means) + 3 * (size_t)idx;
         const float3 mean = make_float3(mp[0], mp[1], mp[2]);
         float cov6[6];
@@ -161,6 +167,16 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         const float ca = cov.x, cb = cov.y, cc = cov.z;
         const float denom = ca * cc - cb * cb;
         const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        if (a.grad_moments) {
+            // moments -> (dL_dmean2D.xy, dL_dconic.xyz, dL_dopacity); common.cuh, backward.cu:504-528
+            const float M0 = g0.x, Mx = g0.y, My = g0.z, Mxx = g0.w, Mxy = g1.x, Myy = g1.y;
+            const float cx = sp0.z, cy = sp0.w, cz = sp1.x, op = sp1.y;
+            const float hop = -0.5f * op;
+            g0.x = -op * a.half_W * (cx * Mx + cy * My);
+            g0.y = -op * a.half_H * (cz * My + cy * Mx);
+            g0.z = hop * Mxx; g0.w = hop * Mxy; g1.x = hop * Myy;
+            g1.y = M0;
+        }
         const float dcx = g0.z, dcy = g0.w, dcz = g1.x;   // dL_dconic (xx, xy, yy)
         float dL_da = 0, dL_db = 0, dL_dc = 0;
         // glm column-major T[c][r]: T[0][*] = (T00,T01,T02), T[1][*] = (T10,T11,T12)

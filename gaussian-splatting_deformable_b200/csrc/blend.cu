@@ -584,6 +584,11 @@ int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream) {
     return 0;
 }
 
+int gsr_blend_bwd_writes_moments() {
+    static const int ver = env_int("GSR_BLEND_BWD_V", 2);
+    return ver == 2 ? 1 : 0;
+}
+
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int ver = env_int("GSR_BLEND_BWD_V", 2);   // 2: blend_v2.cu, 1: this file

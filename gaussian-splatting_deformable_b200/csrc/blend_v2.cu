@@ -255,7 +255,6 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
     const float rx1 = fminf(rx0 + 7.0f, (float)(a.W - 1)), ry1 = fminf(ry0 + (float)(8 * NP - 1), (float)(a.H - 1));
     const size_t HW = (size_t)a.H * a.W;
     const bool has_bg = (a.bg[0] != 0.0f) || (a.bg[1] != 0.0f) || (a.bg[2] != 0.0f);
-    const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
 
     f32x2 npy[NP], T[NP], nTfin[NP], dp0[NP], dp1[NP], dp2[NP], bgdot[NP], acc[NP];
     uint32_t lastA[NP], lastB[NP];
@@ -369,29 +368,22 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
                 f32x2 dL_dalpha = mul2(diff, T[q]);
                 acc[q] = fma2(alpha[q], diff, acc[q]);                    // a_{j-1} = alpha_j d_j + (1 - alpha_j) a_j
                 if (has_bg) dL_dalpha = fma2(mul2(nTfin[q], inv), bgdot[q], dL_dalpha);
-                const f32x2 dL_dG = mul2(pk1(g1.y), dL_dalpha);
-                const f32x2 gdx = mul2(G[q], pk1(dx)), gdy = mul2(G[q], dy[q]);
-                const f32x2 dG_ddelx = fma2(gdx, pk1(-g0.z), mul2(gdy, pk1(g0.w)));
-                const f32x2 dG_ddely = fma2(gdy, pk1(-g1.x), mul2(gdx, pk1(g0.w)));
-                const f32x2 h = mul2(dL_dG, pk1(-0.5f));
-                const f32x2 hgdx = mul2(h, gdx), hgdy = mul2(h, gdy);
+                // moment form of the per-Gaussian sums (common.cuh): w = G dL/dalpha
+                const f32x2 w = mul2(G[q], dL_dalpha);
+                const f32x2 wx = mul2(w, pk1(dx)), wy = mul2(w, dy[q]);
                 if (q == 0) {
-                    V[0] = mul2(dL_dG, dG_ddelx);
-                    V[1] = mul2(dL_dG, dG_ddely);
-                    V[2] = mul2(hgdx, pk1(dx));
-                    V[3] = mul2(hgdx, dy[q]);
-                    V[4] = mul2(hgdy, dy[q]);
-                    V[5] = mul2(G[q], dL_dalpha);
+                    V[0] = w; V[1] = wx; V[2] = wy;
+                    V[3] = mul2(wx, pk1(dx));
+                    V[4] = mul2(wx, dy[q]);
+                    V[5] = mul2(wy, dy[q]);
                     V[6] = mul2(dcd, dp0[q]);
                     V[7] = mul2(dcd, dp1[q]);
                     V[8] = mul2(dcd, dp2[q]);
                 } else {
-                    V[0] = fma2(dL_dG, dG_ddelx, V[0]);
-                    V[1] = fma2(dL_dG, dG_ddely, V[1]);
-                    V[2] = fma2(hgdx, pk1(dx), V[2]);
-                    V[3] = fma2(hgdx, dy[q], V[3]);
-                    V[4] = fma2(hgdy, dy[q], V[4]);
-                    V[5] = fma2(G[q], dL_dalpha, V[5]);
+                    V[0] = add2(V[0], w); V[1] = add2(V[1], wx); V[2] = add2(V[2], wy);
+                    V[3] = fma2(wx, pk1(dx), V[3]);
+                    V[4] = fma2(wx, dy[q], V[4]);
+                    V[5] = fma2(wy, dy[q], V[5]);
                     V[6] = fma2(dcd, dp0[q], V[6]);
                     V[7] = fma2(dcd, dp1[q], V[7]);
                     V[8] = fma2(dcd, dp2[q], V[8]);
@@ -402,15 +394,8 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
             for (int k = 0; k < 9; k++) { float x0, x1; upk(V[k], x0, x1); v[k] = x0 + x1; }
             warp_reduce9_v2(v, lane);
             float* dst = grad_base + 12 * (size_t)__float_as_uint(col.w);
-            if ((lane & 3) == 0) {
-                const int k = lane >> 2;
-                float val = v[0];
-                if (k == 0) val *= ddelx_dx;
-                if (k == 1) val *= ddely_dy;
-                atomicAdd(dst + k, val);
-            } else if (lane == 1) {
-                atomicAdd(dst + 8, v[8]);
-            }
+            if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), v[0]);
+            else if (lane == 1) atomicAdd(dst + 8, v[8]);
         }
     }
 }

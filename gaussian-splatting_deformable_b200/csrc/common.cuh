@@ -43,6 +43,13 @@ struct GsrView {
 //   g0 = (dL_dmean2D.x, dL_dmean2D.y, dL_dconic.x, dL_dconic.y)
 //   g1 = (dL_dconic.w(zz), dL_dopacity, dL_dcolor.r, dL_dcolor.g)
 //   g2 = (dL_dcolor.b, 0, 0, 0)
+// Moment form (blend_v2.cu): with w = G * dL/dalpha per blended (pixel, Gaussian) pair and
+// d = mean2D - pixel, the record accumulates
+//   g0 = (sum w, sum w dx, sum w dy, sum w dx^2)   g1 = (sum w dx dy, sum w dy^2, dL_dcolor.r, dL_dcolor.g)
+//   g2 = (dL_dcolor.b, 0, 0, 0)
+// and the per-Gaussian backward turns the six moments into dL_dopacity, dL_dmean2D and dL_dconic
+// with the Gaussian's own opacity and conic (linear, so it commutes with the sum over pixels):
+// ten fewer instructions per pair in the issue-bound blend loop.
 #define GSR_GRAD_F4 3
 
 // Deformation modes fused into preprocess (scene/rigid_body.py:86-93 + the

@@ -121,6 +121,7 @@ struct BlendBwdArgs {
 };
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream);
 int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream);   // blend_v2.cu
+int gsr_blend_bwd_writes_moments();   // 1 when the selected blend backward writes the moment form of the gradient record
 
 // ---- fused per-Gaussian backward ------------------------------------------
 struct PreprocessBwdArgs {
@@ -132,6 +133,9 @@ struct PreprocessBwdArgs {
     int deform_mode; const float* twist_S; const float* twist_theta; const int* body_id; int num_bodies;
     const int* radii; const uint8_t* clamped;
     const float4* grad_recs;     // [P,3] from blend backward
+    int grad_moments;            // 1: records hold the moment form written by blend_v2.cu (see common.cuh)
+    const float4* recs;          // [P,3] splat records (conic + opacity; read only when grad_moments)
+    float half_W, half_H;        // d(pixel)/d(ndc) = 0.5 W, 0.5 H (applied here in the moment form)
     // outputs (every element written, zeros for culled Gaussians)
     float* dL_dmeans3D;          // [P,3]  w.r.t. the un-deformed means
     float* dL_dmeans2D;          // [P,3]
