@@ -128,17 +128,25 @@ def flat_buffer(leaves):
     return _FLAT["buf"]
 
 
+_STREAMS = {}
+
+
 def step_ours(leaves, cams, bg, grad, args):
+    """One view-batched step: forward+backward of every local view, gradients summed in the flat buffer.
+    The views of a step are independent, so they are issued round-robin on `--streams` CUDA streams:
+    one view's latency-bound binning kernels, launch gaps and kernel tails overlap another view's
+    issue-bound blend kernels (view_parallel.render_views)."""
     import synthetic
+    import view_parallel
     from diff_gaussian_rasterization import GaussianRasterizer
     buf = flat_buffer(leaves)
     buf.zero_()
     sinks = {"means3D": leaves["means3D"].grad, "opacities": leaves["opacities"].grad, "shs": leaves["shs"].grad,
              "scales": leaves["scales"].grad, "rotations": leaves["rotations"].grad,
              "se3_S": leaves["S"].grad, "se3_theta": leaves["theta"].grad}
-    loss_total = None
-    for cam in cams:
-        rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+
+    def render_view(i):
+        rs = synthetic.raster_settings(cams[i], bg, sh_degree=3)
         ras = GaussianRasterizer(rs)
         means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
         color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
@@ -146,8 +154,9 @@ def step_ours(leaves, cams, bg, grad, args):
                            se3_S=leaves["S"], se3_theta=leaves["theta"], accumulate_grads=sinks)
         loss = (color * grad).sum()
         loss.backward()
-        loss_total = loss.detach() if loss_total is None else loss_total + loss.detach()
-    return loss_total
+        return loss.detach()
+
+    return view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams)
 
 
 def step_reference(leaves, cams, bg, grad, args):
@@ -217,6 +226,7 @@ def main():
     ap.add_argument("--P", type=int, default=1000000)
     ap.add_argument("--W", type=int, default=1920)
     ap.add_argument("--H", type=int, default=1080)
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are spread over (ours)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -337,7 +347,9 @@ def main():
         from diff_gaussian_rasterization import _RasterizeGaussians
         rt.profile_enable(True)
         zero_grads(leaves)
+        n_streams, args.streams = args.streams, 1       # kernels timed one at a time, not overlapping another view's
         step_fn(leaves, cams, bg, grad, args)          # rank-local: NO collective here (other ranks are done)
+        args.streams = n_streams
         torch.cuda.synchronize()
         prof = rt.profile_dump()
         rt.profile_enable(False)
@@ -400,7 +412,7 @@ def main():
         "impl": args.impl,
         "config": {"workload": "C2: %d Gaussians, SH degree 3, %dx%d, SE3 exp-map deform + rasterize fwd+bwd; "
                                "%d views/GPU/step on a camera circle (C5's 64 cameras at 8 GPUs)" % (args.P, args.W, args.H, args.views),
-                   "P": args.P, "width": args.W, "height": args.H, "views_per_gpu_per_step": args.views,
+                   "P": args.P, "width": args.W, "height": args.H, "views_per_gpu_per_step": args.views, "streams": args.streams,
                    "parallelism": "view-parallel x%d, per-Gaussian grad all-reduce (NCCL)" % world if world > 1 else "single GPU",
                    "l2": "inputs (264 MB params+twists, 85 MB geometry state, 190 MB keys) exceed the 126 MB L2 every view"},
         "clocks": clocks,

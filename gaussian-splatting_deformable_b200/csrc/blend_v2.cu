@@ -238,9 +238,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // (same sum, associated per pixel instead of per channel; gradients carry a 1e-4 tolerance).
 // A pixel that does not blend Gaussian j runs with alpha = G = 0: T, a and every sum are then
 // unchanged exactly, so the loop body is straight-line code behind two warp-uniform skips.
-template <int NP, int MINB>
+// SMEM_RED: the nine per-lane sums of up to four consecutive Gaussians are parked in a warp-private
+// shared buffer and reduced together - lane (e, o) = (entry, octant) adds the 32 lane values of sum o of
+// entry e with eight LDS.128 - instead of a 14-shuffle butterfly per Gaussian (33 vs 59 instructions
+// per blended (region, Gaussian)).
+constexpr int RED_E = 4, RED_STRIDE = 36;             // entries per flush; padded row (conflict-free LDS.128)
+
+template <int NP, int MINB, bool SMEM_RED>
 __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdArgs a) {
     constexpr int NW = 4 / NP;
+    __shared__ __align__(16) float s_red[SMEM_RED ? NW : 1][SMEM_RED ? RED_E * 9 * RED_STRIDE : 1];
+    __shared__ uint32_t s_rid[NW][RED_E];
     __shared__ float4 s_q0[NW][32];                  // x, y, conic.x, -conic.y
     __shared__ float4 s_q1[NW][32];                  // conic.z, opacity, cut, list position as bits
     __shared__ float4 s_q2[NW][32];                  // r, g, b, Gaussian id as bits
@@ -295,6 +303,36 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
             const float4* r = a.recs + 3 * (size_t)nid;
             n0 = __ldg(r); n1 = __ldg(r + 1); n2 = __ldg(r + 2);
         }
+    };
+    float* const red = s_red[SMEM_RED ? warp : 0];
+    int ne = 0;
+    auto flush = [&](int count) {
+        __syncwarp();
+        const int e = lane >> 3, o = lane & 7;
+        if (e < count) {
+            const float* rows = red + e * (9 * RED_STRIDE);
+            const float4* r4 = reinterpret_cast<const float4*>(rows + o * RED_STRIDE);
+            f32x2 s0 = pk1(0.0f), s1 = pk1(0.0f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float4 x = r4[i];
+                s0 = add2(s0, pk(x.x, x.y));
+                s1 = add2(s1, pk(x.z, x.w));
+            }
+            float a0, a1, b0, b1;
+            upk(s0, a0, a1); upk(s1, b0, b1);
+            const float sum = (a0 + a1) + (b0 + b1);
+            // ninth sum: each octant lane adds four of its 32 values, then three shuffles
+            const float4 y = reinterpret_cast<const float4*>(rows + 8 * RED_STRIDE)[o];
+            float s8 = (y.x + y.y) + (y.z + y.w);
+            s8 += __shfl_xor_sync(0xffu << (lane & 24), s8, 4);
+            s8 += __shfl_xor_sync(0xffu << (lane & 24), s8, 2);
+            s8 += __shfl_xor_sync(0xffu << (lane & 24), s8, 1);
+            float* dst = grad_base + 12 * (size_t)s_rid[warp][e];
+            atomicAdd(dst + o, sum);
+            if (o == 0) atomicAdd(dst + 8, s8);
+        }
+        __syncwarp();
     };
     if (wlast > 0) fetch((int)wlast);
     for (int start = (int)wlast; start > 0; start -= 32) {
@@ -392,12 +430,21 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
             float v[9];
 #pragma unroll
             for (int k = 0; k < 9; k++) { float x0, x1; upk(V[k], x0, x1); v[k] = x0 + x1; }
-            warp_reduce9_v2(v, lane);
-            float* dst = grad_base + 12 * (size_t)__float_as_uint(col.w);
-            if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), v[0]);
-            else if (lane == 1) atomicAdd(dst + 8, v[8]);
+            if (SMEM_RED) {
+                float* slot = red + ne * (9 * RED_STRIDE) + lane;
+#pragma unroll
+                for (int k = 0; k < 9; k++) slot[k * RED_STRIDE] = v[k];
+                if (lane == 0) s_rid[warp][ne] = __float_as_uint(col.w);
+                if (++ne == RED_E) { flush(ne); ne = 0; }
+            } else {
+                warp_reduce9_v2(v, lane);
+                float* dst = grad_base + 12 * (size_t)__float_as_uint(col.w);
+                if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), v[0]);
+                else if (lane == 1) atomicAdd(dst + 8, v[8]);
+            }
         }
     }
+    if (SMEM_RED && ne) flush(ne);
 }
 
 // exhaustive check kernel: exp1_exact / exp2_exact against expf on every float in [lo_bits, hi_bits]
@@ -442,10 +489,18 @@ int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int np = env_int_v2("GSR_BWD_NP", 1);
     { GsrProfScope prof_("blend_bwd", stream);
-    static const int minb = env_int_v2("GSR_BWD_MINB", 8);
-    if (np == 2) blend_bwd_v2_kernel<2, 0><<<grid, 64, 0, stream>>>(a);
-    else if (minb >= 8) blend_bwd_v2_kernel<1, 8><<<grid, 128, 0, stream>>>(a);
-    else blend_bwd_v2_kernel<1, 0><<<grid, 128, 0, stream>>>(a); }
+    static const int minb = env_int_v2("GSR_BWD_MINB", 0);
+    static const int sred = env_int_v2("GSR_BWD_SMEM_RED", 1);
+    if (np == 2) {
+        if (sred) blend_bwd_v2_kernel<2, 0, true><<<grid, 64, 0, stream>>>(a);
+        else blend_bwd_v2_kernel<2, 0, false><<<grid, 64, 0, stream>>>(a);
+    } else if (minb >= 8) {
+        if (sred) blend_bwd_v2_kernel<1, 8, true><<<grid, 128, 0, stream>>>(a);
+        else blend_bwd_v2_kernel<1, 8, false><<<grid, 128, 0, stream>>>(a);
+    } else {
+        if (sred) blend_bwd_v2_kernel<1, 0, true><<<grid, 128, 0, stream>>>(a);
+        else blend_bwd_v2_kernel<1, 0, false><<<grid, 128, 0, stream>>>(a);
+    } }
     GSR_CHECK_LAUNCH();
     return 0;
 }

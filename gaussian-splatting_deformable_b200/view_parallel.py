@@ -71,6 +71,45 @@ def reduce_densification_stats(xyz_gradient_accum, denom, max_radii2D, group=Non
     dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)
 
 
+_streams = {}
+
+
+def render_views(render_view, views, num_streams=2):
+    """Run `render_view(i)` (forward + backward of local view i, accumulating into shared gradient
+    buffers) for every i in `views`, spreading the views round-robin over `num_streams` CUDA streams.
+    The views of one step only meet in the gradient sums (atomic adds), so they may overlap: the
+    latency-bound part of one view (depth sort passes, scans, launch gaps, kernel tails) runs under
+    the issue-bound blend kernels of another.  Returns the summed loss (tensor on the current stream).
+    `render_view` must allocate per-view state itself (the rasterizer does) and return a detached loss."""
+    views = list(views)
+    if num_streams <= 1 or len(views) <= 1 or not torch.cuda.is_available():
+        total = None
+        for i in views:
+            loss = render_view(i)
+            total = loss if total is None else total + loss
+        return total
+    dev = torch.cuda.current_device()
+    key = (dev, num_streams)
+    if key not in _streams:
+        _streams[key] = [torch.cuda.Stream(device=dev) for _ in range(num_streams)]
+    side = _streams[key]
+    main = torch.cuda.current_stream(dev)
+    for s in side:
+        s.wait_stream(main)                 # parameters / zeroed gradient buffer are ready
+    losses = []
+    for n, i in enumerate(views):
+        with torch.cuda.stream(side[n % num_streams]):
+            losses.append(render_view(i))
+    for s in side:
+        main.wait_stream(s)
+    total = losses[0]
+    for l in losses[1:]:
+        total = total + l
+    for l in losses:
+        l.record_stream(main)
+    return total
+
+
 def render_step(render_view, views, buffer, group=None):
     """One view-parallel step: `render_view(i)` must run forward+backward for local view
     i (accumulating into the parameters' .grad, i.e. into `buffer`) and return the loss.

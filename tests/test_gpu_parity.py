@@ -403,3 +403,43 @@ def test_packed_expf_is_cudas_expf_on_every_float():
     rc = rt.load().gsr_debug_exp_check(80.0, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0, rt.last_error()
     assert out.tolist() == [0, 0]
+
+
+def test_render_views_on_several_streams_matches_one_stream():
+    """view_parallel.render_views spreads the views of a step over CUDA streams; the views only meet in the
+    accumulated gradient sums, so the result must equal the sequential loop (up to the order of float adds)."""
+    import synthetic
+    import view_parallel
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from _gpu_util import make_view_settings, rel_to_max
+    P, W, H = 50000, 400, 300
+    sc, _, _ = make_view_settings(P, W, H)
+    S, th = synthetic.make_twists(P, device="cuda")
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    cams = [synthetic.make_camera(k, 6, W, H, device="cuda") for k in range(6)]
+    out = {}
+    for ns in (1, 3):
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+        leaves["S"], leaves["theta"] = S.clone().requires_grad_(True), th.clone().requires_grad_(True)
+        buf = view_parallel.FlatGradBuffer(list(leaves.values()))
+        buf.zero_()
+        sinks = {"means3D": leaves["means3D"].grad, "opacities": leaves["opacities"].grad, "shs": leaves["shs"].grad,
+                 "scales": leaves["scales"].grad, "rotations": leaves["rotations"].grad,
+                 "se3_S": leaves["S"].grad, "se3_theta": leaves["theta"].grad}
+
+        def render_view(i):
+            ras = GaussianRasterizer(synthetic.raster_settings(cams[i], bg))
+            m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+            color, _ = ras(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
+                           scales=leaves["scales"], rotations=leaves["rotations"], se3_S=leaves["S"],
+                           se3_theta=leaves["theta"], accumulate_grads=sinks)
+            loss = (color * grad).sum()
+            loss.backward()
+            return loss.detach()
+
+        total = view_parallel.render_views(render_view, range(len(cams)), num_streams=ns)
+        torch.cuda.synchronize()
+        out[ns] = (float(total), buf.flat.clone())
+    assert abs(out[1][0] - out[3][0]) <= 1e-4 * abs(out[1][0])
+    assert rel_to_max(out[3][1], out[1][1]) <= 1e-4
