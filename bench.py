@@ -366,13 +366,16 @@ def main():
         alg = {  # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x units per launch; R = last view's)
             "preprocess_fwd": 316.0 * args.P,
             "preprocess_bwd": 572.0 * args.P,
+            "depth_sort_onesweep_pass": 16.0 * args.P,     # depth order of the Gaussians: (u32 key, u32 id), 4 passes
+            # radix fallback path (GSR_BINNING_RADIX=1)
             "duplicate_with_keys": 8.0 * R + 28.0 * args.P,
-            "depth_sort_histogram": 4.0 * args.P,          # depth order of the Gaussians: (u32 key, u32 id), 4 passes
-            "depth_sort_onesweep_pass": 16.0 * args.P,
-            "tile_sort_histogram": 4.0 * R,                # duplicates by tile id: (u32 tile, u32 id), 2 passes
             "tile_sort_onesweep_pass": 16.0 * R,
             "tile_ranges": 4.0 * R + 8.0 * tiles,
         }
+        # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload
+        # (profiles/r01_ncu_full_metrics.csv); only valid for P = 1 M @ 1920x1080, SH 3, per-Gaussian twists
+        ncu_traffic = {"preprocess_bwd": 679.9e6, "preprocess_fwd": 285.1e6}
+        default_workload = (args.P, args.W, args.H) == (1000000, 1920, 1080)
         kernels = {}
         for name, (cnt, tot) in prof.items():
             avg = tot / max(cnt, 1)
@@ -381,14 +384,27 @@ def main():
                 k["alg_GBps"] = round(alg[name] / avg / 1e6, 1)
                 k["frac_of_hbm_peak"] = round(alg[name] / avg / 1e6 / peak, 4)
             kernels[name] = k
+        # the whole binning stage against the reference scheme's traffic model (12 B/dup
+        # duplicate + 152 B/dup 6-pass pair sort + 8 B/dup ranges); an implementation that moves fewer bytes
+        # reads above what HBM could deliver to that scheme
+        bin_names = ("scan_block_sums", "sort_scan_hist", "depth_sort_onesweep_pass", "gather_rects", "tile_count",
+                     "tile_sweep_count", "tile_column_scan", "tile_base_scan", "tile_scatter", "tile_sweep_scatter",
+                     "sorted_block_sums", "duplicate_with_keys", "tile_sort_onesweep_pass", "tile_ranges")
+        bin_ms = sum(kernels[n]["total_ms"] for n in bin_names if n in kernels) / max(len(cams), 1)
+        if bin_ms > 0 and R > 0:
+            kernels["binning_stage"] = {"launches": 1, "avg_ms": round(bin_ms, 5), "total_ms": round(bin_ms * len(cams), 4),
+                                        "alg_GBps": round(172.0 * R / bin_ms / 1e6, 1),
+                                        "frac_of_hbm_peak": round(172.0 * R / bin_ms / 1e6 / peak, 4),
+                                        "note": "sum of the binning kernels of one view vs the reference scheme's 172 B/duplicate"}
         hbm_kernels = [n for n in kernels if n in alg]
         dom = max(hbm_kernels, key=lambda n: kernels[n]["total_ms"]) if hbm_kernels else None
         if dom:
             a = alg[dom] / kernels[dom]["avg_ms"] / 1e6
             roofline = {"kernel": dom, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(a / peak, 4), "traffic": None, "peak_source": peak_src,
-                        "note": "dominant HBM-bound kernel; the blend kernels (largest time share) are FP32-issue/"
-                                "shared-memory bound, see `kernels` and profiles/"}
+                        "frac": round(a / peak, 4),
+                        "traffic": ncu_traffic.get(dom) if default_workload else None, "peak_source": peak_src,
+                        "note": "dominant HBM-bound kernel; achieved = 572 B x P / CUDA-event time; the blend kernels "
+                                "(largest time share) are instruction-issue / FMA-pipe bound (DRAM < 2 %), see `kernels` and profiles/"}
         counters = {"num_rendered_last_view": R, "sort_passes": passes, "tiles": tiles}
 
     if rank != 0:
