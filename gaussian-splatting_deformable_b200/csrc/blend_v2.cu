@@ -63,7 +63,7 @@ __device__ __forceinline__ f32x2 power2_exact(float dx, float s1, float s2, f32x
 // ---------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------
-template <int NP, int MINB>
+template <int NP, int MINB, bool TMUL, bool STRAIGHT>
 __global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdArgs a) {
     constexpr int NW = 4 / NP;                       // warps (regions) per tile
     __shared__ float4 s_q0[NW][32];                  // x, y, conic.x, -conic.y
@@ -79,17 +79,22 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdAr
     const float rx0 = (float)X0, ry0 = (float)Y0;
     const float rx1 = fminf(rx0 + 7.0f, (float)(a.W - 1)), ry1 = fminf(ry0 + (float)(8 * NP - 1), (float)(a.H - 1));
 
+    // A pixel that is done (T (1 - alpha) < 1e-4, forward.cu:345-350) - or lies outside the image - is
+    // parked FAR_Y pixels away: -power = d^T Q d / 2 >= FAR_Y^2 / (2 sigma_max^2) then exceeds every cut
+    // (|cut| <= 80) for any Gaussian with sigma_max < 7e7 pixels, and FAR_Y^2 lambda_max stays finite up to
+    // lambda_max = 3e20 (the 0.3-pixel dilation bounds it by 3.4), so the pixel rejects every later Gaussian
+    // in the ordinary power test and needs no flag in the loop.
+    constexpr float FAR_Y = 1.0e9f;
     int pyi[NP];
     f32x2 npy[NP], T[NP], C0[NP], C1[NP], C2[NP];
     uint32_t lastA[NP], lastB[NP];
-    bool doneA[NP], doneB[NP], inA[NP], inB[NP];
+    bool inA[NP], inB[NP];
 #pragma unroll
     for (int q = 0; q < NP; q++) {
         pyi[q] = Y0 + 8 * q + 2 * (lane >> 3);
-        npy[q] = pk(-(float)pyi[q], -(float)(pyi[q] + 1));
         inA[q] = px < a.W && pyi[q] < a.H;
         inB[q] = px < a.W && pyi[q] + 1 < a.H;
-        doneA[q] = !inA[q]; doneB[q] = !inB[q];
+        npy[q] = pk(inA[q] ? -(float)pyi[q] : -FAR_Y, inB[q] ? -(float)(pyi[q] + 1) : -FAR_Y);
         T[q] = pk1(1.0f); C0[q] = C1[q] = C2[q] = pk1(0.0f);
         lastA[q] = lastB[q] = 0;
     }
@@ -111,7 +116,11 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdAr
     for (int base = 0; base < todo; base += 32) {
         bool all_done = true;
 #pragma unroll
-        for (int q = 0; q < NP; q++) all_done = all_done && doneA[q] && doneB[q];
+        for (int q = 0; q < NP; q++) {
+            float yA, yB;
+            upk(npy[q], yA, yB);
+            all_done = all_done && yA < -0.5f * FAR_Y && yB < -0.5f * FAR_Y;
+        }
         if (__all_sync(FULL, all_done)) break;
         const float4 c0 = n0, c1 = n1, c2 = n2;
         const bool keep = nvalid && rect_may_contribute(c0.x, c0.y, c0.z, c0.w, c1.x, c2.y, rx0, ry0, rx1, ry1);
@@ -137,28 +146,36 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdAr
                 const f32x2 pw = power2_exact(dx, s1, s2, dy, g1.x);
                 float pA, pB;
                 upk(pw, pA, pB);
-                const bool okA = !doneA[q] && !(pA > 0.0f || pA < g1.z);
-                const bool okB = !doneB[q] && !(pB > 0.0f || pB < g1.z);
-                if (!(okA || okB)) continue;
+                const bool okA = !(pA > 0.0f || pA < g1.z);
+                const bool okB = !(pB > 0.0f || pB < g1.z);
+                // warp-uniform skips: a lane whose pixels reject runs the same straight-line code with alpha 0
+                if (!STRAIGHT) { if (!__any_sync(FULL, okA || okB)) continue; }
                 const f32x2 al = mul2(pk1(g1.y), exp2_exact(pw));
-                float aA, aB, tA, tB, TA, TB;
+                float aA, aB, tA, tB;
                 upk(al, aA, aB);
                 aA = fminf(0.99f, aA); aB = fminf(0.99f, aB);
-                bool cA = okA && !(aA < 1.0f / 255.0f);
-                bool cB = okB && !(aB < 1.0f / 255.0f);
-                const f32x2 test_T = mul2(T[q], rsub2(pk(aA, aB), 1.0f));
-                upk(test_T, tA, tB);
-                upk(T[q], TA, TB);
-                if (cA && tA < 0.0001f) { doneA[q] = true; cA = false; }
-                if (cB && tB < 0.0001f) { doneB[q] = true; cB = false; }
-                if (!(cA || cB)) continue;
-                // a pixel that does not blend this Gaussian adds T * (0 * colour) = +-0
+                const bool bA = okA && !(aA < 1.0f / 255.0f);
+                const bool bB = okB && !(aB < 1.0f / 255.0f);
+                upk(mul2(T[q], rsub2(pk(aA, aB), 1.0f)), tA, tB);      // test_T
+                const bool dA = bA && tA < 0.0001f, dB = bB && tB < 0.0001f;   // done now: park the pixel
+                const bool cA = bA && !dA, cB = bB && !dB;
+                float yA, yB;
+                upk(npy[q], yA, yB);
+                npy[q] = pk(dA ? -FAR_Y : yA, dB ? -FAR_Y : yB);
+                if (!STRAIGHT) { if (!__any_sync(FULL, cA || cB)) continue; }
+                // a pixel that does not blend this Gaussian runs with alpha 0: T * 1, C + T * (0 * colour)
                 const f32x2 w = pk(cA ? aA : 0.0f, cB ? aB : 0.0f);
                 const float4 col = q2s[j];
                 C0[q] = fma2(T[q], mul2(w, pk1(col.x)), C0[q]);
                 C1[q] = fma2(T[q], mul2(w, pk1(col.y)), C1[q]);
                 C2[q] = fma2(T[q], mul2(w, pk1(col.z)), C2[q]);
-                T[q] = pk(cA ? tA : TA, cB ? tB : TB);
+                if (TMUL) {
+                    T[q] = mul2(T[q], rsub2(w, 1.0f));
+                } else {
+                    float TA, TB;
+                    upk(T[q], TA, TB);
+                    T[q] = pk(cA ? tA : TA, cB ? tB : TB);
+                }
                 const uint32_t pos1 = __float_as_uint(g1.w);
                 lastA[q] = cA ? pos1 : lastA[q];
                 lastB[q] = cB ? pos1 : lastB[q];
@@ -244,7 +261,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // per blended (region, Gaussian)).
 constexpr int RED_E = 4, RED_STRIDE = 36;             // entries per flush; padded row (conflict-free LDS.128)
 
-template <int NP, int MINB, bool SMEM_RED>
+template <int NP, int MINB, bool SMEM_RED, bool STRAIGHT>
 __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdArgs a) {
     constexpr int NW = 4 / NP;
     __shared__ __align__(16) float s_red[SMEM_RED ? NW : 1][SMEM_RED ? RED_E * 9 * RED_STRIDE : 1];
@@ -309,25 +326,26 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
     auto flush = [&](int count) {
         __syncwarp();
         const int e = lane >> 3, o = lane & 7;
-        if (e < count) {
-            const float* rows = red + e * (9 * RED_STRIDE);
-            const float4* r4 = reinterpret_cast<const float4*>(rows + o * RED_STRIDE);
-            f32x2 s0 = pk1(0.0f), s1 = pk1(0.0f);
+        // every lane computes (rows of entries >= count hold stale values); only the atomics are predicated
+        const float* rows = red + e * (9 * RED_STRIDE);
+        const float4* r4 = reinterpret_cast<const float4*>(rows + o * RED_STRIDE);
+        f32x2 s0 = pk1(0.0f), s1 = pk1(0.0f);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float4 x = r4[i];
-                s0 = add2(s0, pk(x.x, x.y));
-                s1 = add2(s1, pk(x.z, x.w));
-            }
-            float a0, a1, b0, b1;
-            upk(s0, a0, a1); upk(s1, b0, b1);
-            const float sum = (a0 + a1) + (b0 + b1);
-            // ninth sum: each octant lane adds four of its 32 values, then three shuffles
-            const float4 y = reinterpret_cast<const float4*>(rows + 8 * RED_STRIDE)[o];
-            float s8 = (y.x + y.y) + (y.z + y.w);
-            s8 += __shfl_xor_sync(0xffu << (lane & 24), s8, 4);
-            s8 += __shfl_xor_sync(0xffu << (lane & 24), s8, 2);
-            s8 += __shfl_xor_sync(0xffu << (lane & 24), s8, 1);
+        for (int i = 0; i < 8; i++) {
+            const float4 x = r4[i];
+            s0 = add2(s0, pk(x.x, x.y));
+            s1 = add2(s1, pk(x.z, x.w));
+        }
+        float a0, a1, b0, b1;
+        upk(s0, a0, a1); upk(s1, b0, b1);
+        const float sum = (a0 + a1) + (b0 + b1);
+        // ninth sum: each octant lane adds four of its 32 values, then three shuffles inside the octet
+        const float4 y = reinterpret_cast<const float4*>(rows + 8 * RED_STRIDE)[o];
+        float s8 = (y.x + y.y) + (y.z + y.w);
+        s8 += __shfl_xor_sync(FULL, s8, 4);
+        s8 += __shfl_xor_sync(FULL, s8, 2);
+        s8 += __shfl_xor_sync(FULL, s8, 1);
+        if (e < count) {
             float* dst = grad_base + 12 * (size_t)s_rid[warp][e];
             atomicAdd(dst + o, sum);
             if (o == 0) atomicAdd(dst + 8, s8);
@@ -371,7 +389,7 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
                 okB[q] = pos_j < lastB[q] && !(pB > 0.0f || pB < g1.z);
                 any_ok = any_ok || okA[q] || okB[q];
             }
-            if (!__any_sync(FULL, any_ok)) continue;
+            if (!STRAIGHT) { if (!__any_sync(FULL, any_ok)) continue; }
             f32x2 G[NP], alpha[NP];
             bool any_act = false;
 #pragma unroll
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
                 G[q] = pk(actA ? GA : 0.0f, actB ? GB : 0.0f);
                 alpha[q] = pk(actA ? aA : 0.0f, actB ? aB : 0.0f);
             }
-            if (!__any_sync(FULL, any_act)) continue;
+            if (!STRAIGHT) { if (!__any_sync(FULL, any_act)) continue; }
             const float4 col = q2s[j];
             f32x2 V[9];
 #pragma unroll
@@ -477,10 +495,13 @@ int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int np = env_int_v2("GSR_FWD_NP", 1);
     { GsrProfScope prof_("blend_fwd", stream);
-    static const int minb = env_int_v2("GSR_FWD_MINB", 1);
-    if (np == 2) blend_fwd_v2_kernel<2, 0><<<grid, 64, 0, stream>>>(a);
-    else if (minb >= 8) blend_fwd_v2_kernel<1, 8><<<grid, 128, 0, stream>>>(a);
-    else blend_fwd_v2_kernel<1, 0><<<grid, 128, 0, stream>>>(a); }
+    static const int tmul = env_int_v2("GSR_FWD_TMUL", 0);   // T *= (1 - w) instead of a select: measured 1 % slower
+    static const int straight = env_int_v2("GSR_FWD_STRAIGHT", 1);
+    if (np == 2) blend_fwd_v2_kernel<2, 0, false, false><<<grid, 64, 0, stream>>>(a);
+    else if (straight && tmul) blend_fwd_v2_kernel<1, 0, true, true><<<grid, 128, 0, stream>>>(a);
+    else if (straight) blend_fwd_v2_kernel<1, 0, false, true><<<grid, 128, 0, stream>>>(a);
+    else if (tmul) blend_fwd_v2_kernel<1, 0, true, false><<<grid, 128, 0, stream>>>(a);
+    else blend_fwd_v2_kernel<1, 0, false, false><<<grid, 128, 0, stream>>>(a); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -491,15 +512,17 @@ int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream) {
     { GsrProfScope prof_("blend_bwd", stream);
     static const int minb = env_int_v2("GSR_BWD_MINB", 0);
     static const int sred = env_int_v2("GSR_BWD_SMEM_RED", 1);
+    static const int straight = env_int_v2("GSR_BWD_STRAIGHT", 1);
     if (np == 2) {
-        if (sred) blend_bwd_v2_kernel<2, 0, true><<<grid, 64, 0, stream>>>(a);
-        else blend_bwd_v2_kernel<2, 0, false><<<grid, 64, 0, stream>>>(a);
+        if (sred) blend_bwd_v2_kernel<2, 0, true, false><<<grid, 64, 0, stream>>>(a);
+        else blend_bwd_v2_kernel<2, 0, false, false><<<grid, 64, 0, stream>>>(a);
     } else if (minb >= 8) {
-        if (sred) blend_bwd_v2_kernel<1, 8, true><<<grid, 128, 0, stream>>>(a);
-        else blend_bwd_v2_kernel<1, 8, false><<<grid, 128, 0, stream>>>(a);
+        blend_bwd_v2_kernel<1, 8, false, false><<<grid, 128, 0, stream>>>(a);
+    } else if (straight && sred) {
+        blend_bwd_v2_kernel<1, 0, true, true><<<grid, 128, 0, stream>>>(a);
     } else {
-        if (sred) blend_bwd_v2_kernel<1, 0, true><<<grid, 128, 0, stream>>>(a);
-        else blend_bwd_v2_kernel<1, 0, false><<<grid, 128, 0, stream>>>(a);
+        if (sred) blend_bwd_v2_kernel<1, 0, true, false><<<grid, 128, 0, stream>>>(a);
+        else blend_bwd_v2_kernel<1, 0, false, false><<<grid, 128, 0, stream>>>(a);
     } }
     GSR_CHECK_LAUNCH();
     return 0;
