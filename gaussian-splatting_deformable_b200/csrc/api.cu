@@ -361,6 +361,36 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
 }
 
 // Debug: workload counters of the blend stage for a finished forward (see blend.cu).
+int gsr_ssim_l1_loss_forward(const float* image, const float* gt, int channels, int height, int width,
+                             const float* window11, float lambda_dssim, float* dmaps, float* out8, void* stream_) {
+    if (!image || !gt || !window11 || !dmaps || !out8) return gsr_set_error_msg(-1, "ssim_l1_loss: NULL pointer");
+    if (channels != 3) return gsr_set_error_msg(-1, "ssim_l1_loss: images must be [3,H,W]");
+    if (height <= 0 || width <= 0) return gsr_set_error_msg(-1, "ssim_l1_loss: empty image");
+    return gsr_launch_ssim_l1_fwd(image, gt, height, width, window11, lambda_dssim, dmaps, out8, (cudaStream_t)stream_);
+}
+
+int gsr_ssim_l1_loss_backward(const float* image, const float* gt, int channels, int height, int width,
+                              const float* window11, float lambda_dssim, const float* dmaps, const float* upstream,
+                              float* dL_dimage, void* stream_) {
+    if (!image || !gt || !window11 || !dmaps || !dL_dimage) return gsr_set_error_msg(-1, "ssim_l1_loss: NULL pointer");
+    if (channels != 3) return gsr_set_error_msg(-1, "ssim_l1_loss: images must be [3,H,W]");
+    if (height <= 0 || width <= 0) return gsr_set_error_msg(-1, "ssim_l1_loss: empty image");
+    return gsr_launch_ssim_l1_bwd(image, gt, height, width, window11, lambda_dssim, dmaps, upstream, dL_dimage,
+                                  (cudaStream_t)stream_);
+}
+
+int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int num_groups,
+                  const unsigned long long* group_begin, const float* step_size, const float* bias_correction2_sqrt,
+                  const double* beta1, const double* beta2, const float* eps, void* stream_) {
+    if (num_groups < 0) return gsr_set_error_msg(-1, "adam: negative group count");
+    if (num_groups == 0) return 0;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !group_begin || !step_size || !bias_correction2_sqrt || !beta1 ||
+        !beta2 || !eps)
+        return gsr_set_error_msg(-1, "adam: NULL pointer");
+    return gsr_launch_adam(params, grads, exp_avg, exp_avg_sq, num_groups, group_begin, step_size, bias_correction2_sqrt,
+                           beta1, beta2, eps, (cudaStream_t)stream_);
+}
+
 int gsr_debug_exp_check(float x_max, unsigned long long* out2, void* stream_) {
     if (!out2 || !(x_max > 0.0f)) return gsr_set_error_msg(-1, "exp_check: bad arguments");
     return gsr_launch_exp_check(x_max, out2, (cudaStream_t)stream_);

@@ -83,6 +83,16 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order
                             uint32_t* tile_base, uint2* ranges, uint32_t* point_list, cudaStream_t stream);
 int gsr_launch_expand_tile_ids(int num_tiles, const uint2* ranges, uint32_t* tile_ids, cudaStream_t stream);
 
+// ---- training-step kernels either side of the rasterizer: loss.cu, adam.cu ----
+int gsr_launch_ssim_l1_fwd(const float* img, const float* gt, int H, int W, const float* window11, float lambda,
+                           float* dmaps, float* sums8, cudaStream_t stream);
+int gsr_launch_ssim_l1_bwd(const float* img, const float* gt, int H, int W, const float* window11, float lambda,
+                           const float* dmaps, const float* upstream, float* dL_dimg, cudaStream_t stream);
+#define GSR_ADAM_MAX_GROUPS 16
+int gsr_launch_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int num_groups,
+                    const unsigned long long* begin, const float* step_size, const float* bc2_sqrt,
+                    const double* beta1, const double* beta2, const float* eps, cudaStream_t stream);
+
 // ---- onesweep radix sort of (u64|u32 key, u32 value) pairs -----------------
 
 size_t gsr_sort_temp_bytes(uint32_t n, int begin_bit, int end_bit);

