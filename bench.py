@@ -191,6 +191,75 @@ def allreduce_grads(leaves, world):
         w.wait()
 
 
+# learning rates of arguments/__init__.py:73-80 in the group order of scene/gaussian_model.py:840-860 (+ the twists)
+TRAIN_LRS = {"means3D": 0.00016, "shs": 0.0025 / 20.0, "opacities": 0.05, "scales": 0.005, "rotations": 0.001,
+             "S": 0.00016, "theta": 0.00016}
+
+
+def make_train_state(host, dev, impl, n_views, W, H):
+    leaves = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
+    groups = [{"params": [leaves[k]], "lr": TRAIN_LRS[k], "name": k} for k in leaves]
+    if impl == "ours":
+        import fused_adam
+        opt = fused_adam.FusedAdam(groups, lr=0.0, eps=1e-15)        # re-homes params + grads into flat buffers
+    else:
+        opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)            # scene/gaussian_model.py:846
+    g = torch.Generator().manual_seed(7)
+    targets = [torch.rand((3, H, W), generator=g).to(dev) for _ in range(n_views)]
+    return leaves, opt, targets
+
+
+def train_step(leaves, opt, targets, cams, bg, args, world):
+    """One whole optimizer step over the rank's views (C5): render, loss, backward, all-reduce, Adam."""
+    import synthetic
+    if args.impl == "ours":
+        import loss_utils
+        import view_parallel
+        from diff_gaussian_rasterization import GaussianRasterizer
+        opt.zero_grad()
+        sinks = {"means3D": leaves["means3D"].grad, "opacities": leaves["opacities"].grad, "shs": leaves["shs"].grad,
+                 "scales": leaves["scales"].grad, "rotations": leaves["rotations"].grad,
+                 "se3_S": leaves["S"].grad, "se3_theta": leaves["theta"].grad}
+
+        def render_view(i):
+            ras = GaussianRasterizer(synthetic.raster_settings(cams[i], bg, sh_degree=3))
+            means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+            color, _ = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
+                           scales=leaves["scales"], rotations=leaves["rotations"], se3_S=leaves["S"],
+                           se3_theta=leaves["theta"], accumulate_grads=sinks)
+            loss = loss_utils.l1_ssim_loss(color, targets[i], 0.2)
+            loss.backward()
+            return loss.detach()
+
+        total = view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams)
+        if world > 1:
+            opt.grads.all_reduce()
+        opt.step()
+        return total
+    from oracle import loss_port, ref_driver, rigid_body_port
+    opt.zero_grad(set_to_none=True)
+    total = None
+    for i, cam in enumerate(cams):
+        rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+        y = rigid_body_port.deform_points(leaves["means3D"], leaves["S"], leaves["theta"])
+        yd = y.detach()
+        f = ref_driver.forward(rs, yd, leaves["opacities"].detach(), shs=leaves["shs"].detach(),
+                               scales=leaves["scales"].detach(), rotations=leaves["rotations"].detach())
+        img = f["color"].detach().requires_grad_(True)
+        loss = loss_port.training_loss(img, targets[i], 0.2)           # utils/loss_utils.py ops, train.py:529
+        loss.backward()
+        g = ref_driver.backward(rs, f, img.grad, yd, shs=leaves["shs"].detach(), scales=leaves["scales"].detach(),
+                                rotations=leaves["rotations"].detach())
+        y.backward(g["means3D"])
+        for k in ("opacities", "shs", "scales", "rotations"):
+            t = leaves[k]
+            t.grad = g[k].view_as(t) if t.grad is None else t.grad + g[k].view_as(t)
+        total = loss.detach() if total is None else total + loss.detach()
+    allreduce_grads(leaves, world)
+    opt.step()
+    return total
+
+
 def cpu_baseline(n=100000, iters=30):
     """Reference torch-CPU deformation stage (config C1): exp_se3 + apply, fwd+bwd."""
     import synthetic
@@ -227,6 +296,9 @@ def main():
     ap.add_argument("--W", type=int, default=1920)
     ap.add_argument("--H", type=int, default=1080)
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are spread over (ours)")
+    ap.add_argument("--train", action="store_true",
+                    help="also time the whole C5-style training step: per-view loss 0.8 L1 + 0.2 (1 - SSIM) against a fixed "
+                         "target, gradient all-reduce, Adam step (ours: fused kernels; reference: its torch ops)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -341,6 +413,30 @@ def main():
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
     e2e_val = args.P * views_total / (float(e2e_s.item()) / args.steps)
 
+    # ---------------- optional: the whole training step (C5) ----------------
+    train = None
+    if args.train:
+        del leaves
+        t_leaves, t_opt, t_targets = make_train_state(host, dev, args.impl, len(cams), args.W, args.H)
+        for _ in range(args.warmup):
+            train_step(t_leaves, t_opt, t_targets, cams, bg, args, world)
+        barrier()
+        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        te0.record()
+        for _ in range(args.steps):
+            t_loss = train_step(t_leaves, t_opt, t_targets, cams, bg, args, world)
+        te1.record()
+        barrier()
+        tms = torch.tensor([te0.elapsed_time(te1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+        t_ms = float(tms.item()) / args.steps
+        train = {"ms_per_step": t_ms, "ms_per_view": t_ms / args.views,
+                 "gaussian_views_per_s": args.P * views_total / (t_ms * 1e-3), "loss_last": float(t_loss),
+                 "what": "C5 step: %d views/GPU x (SE3 + rasterize fwd, 0.8 L1 + 0.2 (1-SSIM) vs a fixed random target, bwd) + "
+                         "gradient all-reduce + Adam (eps 1e-15, reference lrs) on all %d M parameters" % (args.views, 66 * args.P // 1000000)}
+        leaves = t_leaves
+
     # ---------------- per-kernel profile (ours) -> roofline ----------------
     roofline, kernels, counters = None, None, None
     if args.impl == "ours" and rank == 0:
@@ -435,6 +531,8 @@ def main():
         "e2e": {"value": e2e_val, "unit": "Gaussian-views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches if args.impl == "ours" else 0,
     }
+    if train is not None:
+        out["train_step"] = train
     if args.impl == "ours":
         out["roofline"] = roofline
         out["kernels"] = kernels

@@ -7,9 +7,10 @@
 // with w the 11x11 Gaussian window (sigma 1.5) applied with ZERO padding, per channel.  The window is an
 // outer product (loss_utils.py:27-31), so both kernels run it as two 11-tap passes through shared memory.
 //
-// Forward (ssim_l1_fwd_kernel): a CTA owns a 32x16 output tile of one channel, stages the (32+10)x(16+10)
-// halo of both images, runs the horizontal pass of the five moments into shared memory and the vertical
-// pass into registers, then evaluates the map and its three partial derivatives
+// Forward (ssim_l1_fwd_kernel): a CTA owns a 32x32 output tile of one channel, stages the 42x42 halo of both
+// images, runs the horizontal pass of the five moments into shared memory and the vertical pass into registers -
+// each thread filters 4 consecutive outputs from a 14-value sliding window in registers, which is what keeps the
+// kernel off the shared-memory bandwidth limit - then evaluates the map and its three partial derivatives
 //   dS/dmu1 (conv outputs P = w*x1^2, Q = w*x1x2 held fixed), dS/dP, dS/dQ
 // which are written out (12 B/pixel/channel) for the backward; |x1 - x2| and the map are block-reduced and
 // leave as two atomics; the last CTA turns the two sums into the loss.
@@ -20,12 +21,14 @@
 
 namespace {
 
-constexpr int TX = 32, TY = 16, HALO = 5, WIN = 11;
-constexpr int SX = TX + 2 * HALO, SY = TY + 2 * HALO;       // 42 x 26 staged pixels
+constexpr int TX = 32, TY = 32, HALO = 5, WIN = 11, NT = 256;
+constexpr int SX = TX + 2 * HALO, SY = TY + 2 * HALO;       // 42 x 42 staged pixels
+constexpr int SEG = 4;                                       // consecutive outputs per thread along the filtered axis:
+                                                             // 14 shared loads feed 4 outputs (a sliding window in registers)
 
 struct SsimWindow { float w[WIN]; };
 
-__device__ __forceinline__ float block_sum_256(float v, float* s_part) {
+__device__ __forceinline__ float block_sum(float v, float* s_part) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -33,22 +36,21 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_part) {
     __syncthreads();
     float t = 0.0f;
     if (warp == 0) {
-        t = lane < (TX * TY / 64) ? s_part[lane] : 0.0f;
+        t = lane < NT / 32 ? s_part[lane] : 0.0f;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     }
     __syncthreads();
     return t;        // valid in thread 0
 }
 
-__global__ void __launch_bounds__(TX * TY / 2) ssim_l1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ gt, int H, int W,
-                                                                  SsimWindow win, float lambda, float* __restrict__ dmaps,
-                                                                  float* __restrict__ sums /*[2] + counter + out[3]*/) {
-    // thread (tx, ty2) computes output pixels (tx, 2*ty2) and (tx, 2*ty2 + 1) of the tile
+__global__ void __launch_bounds__(NT) ssim_l1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ gt, int H, int W,
+                                                         SsimWindow win, float lambda, float* __restrict__ dmaps,
+                                                         float* __restrict__ sums /*[2] + counter + out[3]*/) {
     __shared__ float s_x1[SY][SX + 1];
     __shared__ float s_x2[SY][SX + 1];
     __shared__ float s_h[5][SY][TX + 1];           // horizontal pass of x1, x2, x1^2, x2^2, x1 x2
-    __shared__ float s_part[8];
+    __shared__ float s_part[NT / 32];
     __shared__ bool s_last;
     const int c = blockIdx.z;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(TX * TY / 2) ssim_l1_fwd_kernel(const float* _
     const float* p1 = img + c * plane;
     const float* p2 = gt + c * plane;
     const int tid = threadIdx.x;
-    for (int i = tid; i < SX * SY; i += TX * TY / 2) {
+    for (int i = tid; i < SX * SY; i += NT) {
         const int sx = i % SX, sy = i / SX;
         const int gx = x0 + sx - HALO, gy = y0 + sy - HALO;
         const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
@@ -64,33 +66,50 @@ __global__ void __launch_bounds__(TX * TY / 2) ssim_l1_fwd_kernel(const float* _
         s_x2[sy][sx] = in ? p2[(size_t)gy * W + gx] : 0.0f;
     }
     __syncthreads();
-    for (int i = tid; i < TX * SY; i += TX * TY / 2) {
-        const int ox = i % TX, sy = i / TX;
-        float a = 0, b = 0, aa = 0, bb = 0, ab = 0;
+    // horizontal pass: task = (row, segment of SEG output columns)
+    for (int i = tid; i < SY * (TX / SEG); i += NT) {
+        const int seg = i % (TX / SEG), sy = i / (TX / SEG);
+        const int ox = seg * SEG;
+        float u[SEG + WIN - 1], v[SEG + WIN - 1];
 #pragma unroll
-        for (int k = 0; k < WIN; k++) {
-            const float u = s_x1[sy][ox + k], v = s_x2[sy][ox + k], w = win.w[k];
-            a = fmaf(w, u, a); b = fmaf(w, v, b);
-            aa = fmaf(w, u * u, aa); bb = fmaf(w, v * v, bb); ab = fmaf(w, u * v, ab);
+        for (int k = 0; k < SEG + WIN - 1; k++) { u[k] = s_x1[sy][ox + k]; v[k] = s_x2[sy][ox + k]; }
+#pragma unroll
+        for (int o = 0; o < SEG; o++) {
+            float a = 0, b = 0, aa = 0, bb = 0, ab = 0;
+#pragma unroll
+            for (int k = 0; k < WIN; k++) {
+                const float w = win.w[k], uu = u[o + k], vv = v[o + k];
+                a = fmaf(w, uu, a); b = fmaf(w, vv, b);
+                aa = fmaf(w, uu * uu, aa); bb = fmaf(w, vv * vv, bb); ab = fmaf(w, uu * vv, ab);
+            }
+            s_h[0][sy][ox + o] = a; s_h[1][sy][ox + o] = b; s_h[2][sy][ox + o] = aa; s_h[3][sy][ox + o] = bb;
+            s_h[4][sy][ox + o] = ab;
         }
-        s_h[0][sy][ox] = a; s_h[1][sy][ox] = b; s_h[2][sy][ox] = aa; s_h[3][sy][ox] = bb; s_h[4][sy][ox] = ab;
     }
     __syncthreads();
-    const int tx = tid % TX, ty2 = tid / TX;
+    // vertical pass: thread = (column, segment of SEG output rows)
+    const int tx = tid % TX, oy0 = (tid / TX) * SEG;
+    float acc[5][SEG];
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        float col[SEG + WIN - 1];
+#pragma unroll
+        for (int k = 0; k < SEG + WIN - 1; k++) col[k] = s_h[q][oy0 + k][tx];
+#pragma unroll
+        for (int o = 0; o < SEG; o++) {
+            float a = 0;
+#pragma unroll
+            for (int k = 0; k < WIN; k++) a = fmaf(win.w[k], col[o + k], a);
+            acc[q][o] = a;
+        }
+    }
     float l1_acc = 0.0f, ssim_acc = 0.0f;
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const int oy = 2 * ty2 + r;
-        float mu1 = 0, mu2 = 0, e11 = 0, e22 = 0, e12 = 0;
-#pragma unroll
-        for (int k = 0; k < WIN; k++) {
-            const float w = win.w[k];
-            mu1 = fmaf(w, s_h[0][oy + k][tx], mu1); mu2 = fmaf(w, s_h[1][oy + k][tx], mu2);
-            e11 = fmaf(w, s_h[2][oy + k][tx], e11); e22 = fmaf(w, s_h[3][oy + k][tx], e22);
-            e12 = fmaf(w, s_h[4][oy + k][tx], e12);
-        }
+    for (int o = 0; o < SEG; o++) {
+        const int oy = oy0 + o;
         const int gx = x0 + tx, gy = y0 + oy;
         if (gx < W && gy < H) {
+            const float mu1 = acc[0][o], mu2 = acc[1][o], e11 = acc[2][o], e22 = acc[3][o], e12 = acc[4][o];
             const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
             const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
             const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
@@ -102,15 +121,15 @@ __global__ void __launch_bounds__(TX * TY / 2) ssim_l1_fwd_kernel(const float* _
             const float dS_dmu1 = 2.0f * mu2 * (A2 - A1) * inv - S * 2.0f * mu1 * (1.0f / B1 - 1.0f / B2);
             const float dS_dP = -S / B2;
             const float dS_dQ = 2.0f * A1 * inv;
-            const size_t o = c * plane + (size_t)gy * W + gx;
+            const size_t o_ = c * plane + (size_t)gy * W + gx;
             const size_t CHW = 3 * plane;
-            dmaps[o] = dS_dmu1; dmaps[CHW + o] = dS_dP; dmaps[2 * CHW + o] = dS_dQ;
+            dmaps[o_] = dS_dmu1; dmaps[CHW + o_] = dS_dP; dmaps[2 * CHW + o_] = dS_dQ;
             ssim_acc += S;
             l1_acc += fabsf(s_x1[oy + HALO][tx + HALO] - s_x2[oy + HALO][tx + HALO]);
         }
     }
-    const float bl1 = block_sum_256(l1_acc, s_part);
-    const float bss = block_sum_256(ssim_acc, s_part);
+    const float bl1 = block_sum(l1_acc, s_part);
+    const float bss = block_sum(ssim_acc, s_part);
     if (tid == 0) {
         atomicAdd(&sums[0], bl1);
         atomicAdd(&sums[1], bss);
@@ -130,16 +149,16 @@ __global__ void __launch_bounds__(TX * TY / 2) ssim_l1_fwd_kernel(const float* _
     }
 }
 
-__global__ void __launch_bounds__(TX * TY / 2) ssim_l1_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gt, int H, int W,
-                                                                  SsimWindow win, float lambda, const float* __restrict__ dmaps,
-                                                                  const float* __restrict__ upstream, float* __restrict__ dL_dimg) {
+__global__ void __launch_bounds__(NT) ssim_l1_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gt, int H, int W,
+                                                         SsimWindow win, float lambda, const float* __restrict__ dmaps,
+                                                         const float* __restrict__ upstream, float* __restrict__ dL_dimg) {
     __shared__ float s_d[3][SY][SX + 1];
     __shared__ float s_h[3][SY][TX + 1];
     const int c = blockIdx.z;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const size_t plane = (size_t)H * W, CHW = 3 * plane;
     const int tid = threadIdx.x;
-    for (int i = tid; i < SX * SY; i += TX * TY / 2) {
+    for (int i = tid; i < SX * SY; i += NT) {
         const int sx = i % SX, sy = i / SX;
         const int gx = x0 + sx - HALO, gy = y0 + sy - HALO;
         const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
@@ -148,37 +167,51 @@ __global__ void __launch_bounds__(TX * TY / 2) ssim_l1_bwd_kernel(const float* _
         for (int m = 0; m < 3; m++) s_d[m][sy][sx] = in ? dmaps[m * CHW + o] : 0.0f;
     }
     __syncthreads();
-    for (int i = tid; i < TX * SY; i += TX * TY / 2) {
-        const int ox = i % TX, sy = i / TX;
-        float a = 0, b = 0, d = 0;
+    for (int i = tid; i < SY * (TX / SEG); i += NT) {
+        const int seg = i % (TX / SEG), sy = i / (TX / SEG);
+        const int ox = seg * SEG;
 #pragma unroll
-        for (int k = 0; k < WIN; k++) {
-            const float w = win.w[k];
-            a = fmaf(w, s_d[0][sy][ox + k], a); b = fmaf(w, s_d[1][sy][ox + k], b); d = fmaf(w, s_d[2][sy][ox + k], d);
+        for (int m = 0; m < 3; m++) {
+            float u[SEG + WIN - 1];
+#pragma unroll
+            for (int k = 0; k < SEG + WIN - 1; k++) u[k] = s_d[m][sy][ox + k];
+#pragma unroll
+            for (int o = 0; o < SEG; o++) {
+                float a = 0;
+#pragma unroll
+                for (int k = 0; k < WIN; k++) a = fmaf(win.w[k], u[o + k], a);
+                s_h[m][sy][ox + o] = a;
+            }
         }
-        s_h[0][sy][ox] = a; s_h[1][sy][ox] = b; s_h[2][sy][ox] = d;
     }
     __syncthreads();
     const float up = upstream ? upstream[0] : 1.0f;
     const float n = (float)(3.0 * (double)plane);
     const float gS = -lambda / n * up, gL = (1.0f - lambda) / n * up;
-    const int tx = tid % TX, ty2 = tid / TX;
+    const int tx = tid % TX, oy0 = (tid / TX) * SEG;
+    float acc[3][SEG];
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const int oy = 2 * ty2 + r;
-        const int gx = x0 + tx, gy = y0 + oy;
+    for (int m = 0; m < 3; m++) {
+        float col[SEG + WIN - 1];
+#pragma unroll
+        for (int k = 0; k < SEG + WIN - 1; k++) col[k] = s_h[m][oy0 + k][tx];
+#pragma unroll
+        for (int o = 0; o < SEG; o++) {
+            float a = 0;
+#pragma unroll
+            for (int k = 0; k < WIN; k++) a = fmaf(win.w[k], col[o + k], a);
+            acc[m][o] = a;
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < SEG; o++) {
+        const int gx = x0 + tx, gy = y0 + oy0 + o;
         if (gx < W && gy < H) {
-            float a = 0, b = 0, d = 0;
-#pragma unroll
-            for (int k = 0; k < WIN; k++) {
-                const float w = win.w[k];
-                a = fmaf(w, s_h[0][oy + k][tx], a); b = fmaf(w, s_h[1][oy + k][tx], b); d = fmaf(w, s_h[2][oy + k][tx], d);
-            }
-            const size_t o = c * plane + (size_t)gy * W + gx;
-            const float x1 = img[o], x2 = gt[o];
+            const size_t o_ = c * plane + (size_t)gy * W + gx;
+            const float x1 = img[o_], x2 = gt[o_];
             const float diff = x1 - x2;
             const float sgn = diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f);      // torch.abs backward: sign, 0 at 0
-            dL_dimg[o] = gS * (a + 2.0f * x1 * b + x2 * d) + gL * sgn;
+            dL_dimg[o_] = gS * (acc[0][o] + 2.0f * x1 * acc[1][o] + x2 * acc[2][o]) + gL * sgn;
         }
     }
 }
@@ -193,7 +226,7 @@ int gsr_launch_ssim_l1_fwd(const float* img, const float* gt, int H, int W, cons
     GSR_CHECK(cudaMemsetAsync(sums, 0, 8 * sizeof(float), stream));
     dim3 grid(gsr_div_up(W, TX), gsr_div_up(H, TY), 3);
     { GsrProfScope prof_("ssim_l1_fwd", stream);
-    ssim_l1_fwd_kernel<<<grid, TX * TY / 2, 0, stream>>>(img, gt, H, W, win, lambda, dmaps, sums); }
+    ssim_l1_fwd_kernel<<<grid, NT, 0, stream>>>(img, gt, H, W, win, lambda, dmaps, sums); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -204,7 +237,7 @@ int gsr_launch_ssim_l1_bwd(const float* img, const float* gt, int H, int W, cons
     for (int k = 0; k < WIN; k++) win.w[k] = window11[k];
     dim3 grid(gsr_div_up(W, TX), gsr_div_up(H, TY), 3);
     { GsrProfScope prof_("ssim_l1_bwd", stream);
-    ssim_l1_bwd_kernel<<<grid, TX * TY / 2, 0, stream>>>(img, gt, H, W, win, lambda, dmaps, upstream, dL_dimg); }
+    ssim_l1_bwd_kernel<<<grid, NT, 0, stream>>>(img, gt, H, W, win, lambda, dmaps, upstream, dL_dimg); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
