@@ -124,7 +124,12 @@ def flat_buffer(leaves):
     key = tuple(id(t) for t in leaves.values())
     if _FLAT.get("key") != key:
         _FLAT["key"] = key
-        _FLAT["buf"] = view_parallel.FlatGradBuffer(list(leaves.values()))
+        shapes = [tuple(t.shape) for t in leaves.values()]
+        if _FLAT.get("shapes") == shapes and _FLAT["buf"].flat.device == next(iter(leaves.values())).device:
+            _FLAT["buf"].rebind(list(leaves.values()))          # a step's freshly staged parameters: reuse the buffer
+        else:
+            _FLAT["buf"] = view_parallel.FlatGradBuffer(list(leaves.values()))
+            _FLAT["shapes"] = shapes
     return _FLAT["buf"]
 
 

@@ -10,6 +10,7 @@
 // HBM-bound: ~280 B read + ~236 B written per Gaussian.
 #include "geom_exact.cuh"
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -53,7 +54,8 @@ __device__ __forceinline__ void emit(float* p, float val, bool accumulate) {
 // quaternion, clamp bits, the 192-byte SH record as 6 x LDG.256, twist) BEFORE the first store -
 // a store to a non-restrict pointer would otherwise pin all later loads behind it; (3) math;
 // (4) all stores.  Accumulate mode uses vector reductions (RED.ADD.F32x4 for the SH gradient).
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a, GsrView v) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) preprocess_bwd_kernel(PreprocessBwdArgs a, GsrView v) {
     extern __shared__ float s_body[];   // [num_bodies][7] when accumulating rigid-body twists in smem
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const bool body_smem = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) && a.dL_dtwist_S && (a.num_bodies * 7 * 4 <= 32768);
@@ -535,7 +537,9 @@ int gsr_launch_preprocess_bwd(const PreprocessBwdArgs& a, const GsrView& v, cuda
     if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && a.dL_dtwist_S && a.num_bodies * 7 * 4 <= 32768)
         smem = (size_t)a.num_bodies * 7 * 4;
     { GsrProfScope prof_("preprocess_bwd", stream);
-    preprocess_bwd_kernel<<<gsr_div_up(a.P, 256), 256, smem, stream>>>(a, v); }
+    static const int minb = getenv("GSR_PRE_BWD_MINB") ? atoi(getenv("GSR_PRE_BWD_MINB")) : 2;
+    if (minb >= 3) preprocess_bwd_kernel<3><<<gsr_div_up(a.P, 256), 256, smem, stream>>>(a, v);
+    else preprocess_bwd_kernel<2><<<gsr_div_up(a.P, 256), 256, smem, stream>>>(a, v); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

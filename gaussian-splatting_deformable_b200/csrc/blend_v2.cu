@@ -497,8 +497,11 @@ int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
     { GsrProfScope prof_("blend_fwd", stream);
     static const int tmul = env_int_v2("GSR_FWD_TMUL", 0);   // T *= (1 - w) instead of a select: measured 1 % slower
     static const int straight = env_int_v2("GSR_FWD_STRAIGHT", 1);
+    static const int minb = env_int_v2("GSR_FWD_MINB", 7);   // 72 regs: 7 CTAs/SM
     if (np == 2) blend_fwd_v2_kernel<2, 0, false, false><<<grid, 64, 0, stream>>>(a);
     else if (straight && tmul) blend_fwd_v2_kernel<1, 0, true, true><<<grid, 128, 0, stream>>>(a);
+    else if (straight && minb == 7) blend_fwd_v2_kernel<1, 7, false, true><<<grid, 128, 0, stream>>>(a);
+    else if (straight && minb == 8) blend_fwd_v2_kernel<1, 8, false, true><<<grid, 128, 0, stream>>>(a);
     else if (straight) blend_fwd_v2_kernel<1, 0, false, true><<<grid, 128, 0, stream>>>(a);
     else if (tmul) blend_fwd_v2_kernel<1, 0, true, false><<<grid, 128, 0, stream>>>(a);
     else blend_fwd_v2_kernel<1, 0, false, false><<<grid, 128, 0, stream>>>(a); }

@@ -40,6 +40,20 @@ class FlatGradBuffer:
             p.grad = self.flat[off:off + n].view_as(p)
             off += n
 
+    def rebind(self, params):
+        """Attach the same flat buffer to a new set of parameter tensors of identical shapes (e.g. a step's freshly
+        staged copies): no allocation, no fill."""
+        params = list(params)
+        if [tuple(p.shape) for p in params] != [tuple(p.shape) for p in self.params]:
+            raise ValueError("rebind: parameter shapes differ")
+        self.params = params
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+        return self
+
     def zero_(self):
         self.flat.zero_()
         off = 0
