@@ -158,3 +158,47 @@ def test_rigid_body_helpers_match_port():
     assert torch.equal(rigid_body.to_homogenous(p), port.to_homogenous(p))
     h = port.to_homogenous(p) * 2.0
     assert torch.equal(rigid_body.from_homogenous(h), port.from_homogenous(h))
+
+
+def test_loss_and_optimizer_modules_mirror_the_reference_surface_and_refuse_cpu():
+    """same names/signatures as utils/loss_utils.py; no CPU fallback behind them."""
+    import fused_adam
+    import loss_utils
+    for name in ("l1_loss", "l2_loss", "gaussian", "create_window", "ssim"):          # utils/loss_utils.py:17-42
+        assert callable(getattr(loss_utils, name))
+    assert list(inspect.signature(loss_utils.ssim).parameters) == ["img1", "img2", "window_size", "size_average"]
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "loss_golden.pt"), weights_only=False)
+    c = gold["cases"][0]
+    # the window the kernels receive is the reference's own (loss_utils.py:23-25), value for value
+    w = loss_utils.gaussian(11, 1.5)
+    assert w.shape == (11,) and abs(float(w.sum()) - 1.0) < 1e-6 and torch.equal(w, w.flip(0))
+    assert torch.equal(loss_utils.create_window(11, 3)[1, 0], torch.outer(w, w))
+    # l1/l2 are the reference's torch one-liners and work anywhere; ssim / the fused loss / Adam need the GPU library
+    assert torch.equal(loss_utils.l1_loss(c["image"], c["gt"]), c["l1"])
+    with pytest.raises(rt.GsrError):
+        loss_utils.ssim(c["image"], c["gt"])
+    with pytest.raises(rt.GsrError):
+        loss_utils.l1_ssim_loss(c["image"], c["gt"], 0.2)
+    with pytest.raises(NotImplementedError):
+        loss_utils.ssim(c["image"], c["gt"], window_size=7)
+    with pytest.raises(rt.GsrError):
+        fused_adam.FusedAdam([{"params": [torch.zeros(4, requires_grad=True)], "lr": 0.1}], lr=0.0, eps=1e-15)
+    with pytest.raises(ValueError):
+        fused_adam.FusedAdam([])
+
+
+def test_flat_grad_buffer_rebind_and_sequential_render_views():
+    import view_parallel
+    a = [torch.zeros(5, 3, requires_grad=True), torch.zeros(7, requires_grad=True)]
+    buf = view_parallel.FlatGradBuffer(a)
+    assert buf.flat.numel() == 22 and a[1].grad.data_ptr() == buf.flat[15:].data_ptr()
+    a[0].grad += 2.0
+    b = [torch.zeros(5, 3, requires_grad=True), torch.zeros(7, requires_grad=True)]
+    buf.rebind(b)                                               # same memory, new owners, nothing cleared
+    assert float(b[0].grad.sum()) == 30.0 and b[0].grad.data_ptr() == buf.flat.data_ptr()
+    with pytest.raises(ValueError):
+        buf.rebind([torch.zeros(4, 3), torch.zeros(7)])
+    # without CUDA render_views degrades to the plain sequential loop (host logic only; no rasterizer involved)
+    seen = []
+    total = view_parallel.render_views(lambda i: (seen.append(i), torch.tensor(float(i)))[1], [3, 1, 2], num_streams=4)
+    assert seen == [3, 1, 2] and float(total) == 6.0
