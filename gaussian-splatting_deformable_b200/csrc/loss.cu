@@ -17,6 +17,7 @@
 // Backward (ssim_l1_bwd_kernel): dL/dx1 = gS (w * dS/dmu1 + 2 x1 (w * dS/dP) + x2 (w * dS/dQ)) + gL sign(x1 - x2),
 // gS = -lambda / N, gL = (1 - lambda) / N, times the upstream gradient (a device scalar) - the adjoint of a
 // zero-padded convolution with a symmetric window is the same convolution.
+#include "f32x2.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -47,9 +48,12 @@ __device__ __forceinline__ float block_sum(float v, float* s_part) {
 __global__ void __launch_bounds__(NT) ssim_l1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ gt, int H, int W,
                                                          SsimWindow win, float lambda, float* __restrict__ dmaps,
                                                          float* __restrict__ sums /*[2] + counter + out[3]*/) {
-    __shared__ float s_x1[SY][SX + 1];
-    __shared__ float s_x2[SY][SX + 1];
-    __shared__ float s_h[5][SY][TX + 1];           // horizontal pass of x1, x2, x1^2, x2^2, x1 x2
+    // (x1, x2) and the moment pairs (w*x1, w*x2), (w*x1^2, w*x2^2) live interleaved so that one LDS.64 feeds one
+    // packed FFMA2 (f32x2.cuh); w*x1x2 stays scalar.  5 FMA + 3 MUL per tap become 3 packed + 2 scalar.
+    __shared__ float2 s_x[SY][SX + 1];
+    __shared__ float2 s_hm[SY][TX + 1];            // horizontal pass of (x1, x2)
+    __shared__ float2 s_hs[SY][TX + 1];            //                    (x1^2, x2^2)
+    __shared__ float s_hc[SY][TX + 1];             //                    x1 x2
     __shared__ float s_part[NT / 32];
     __shared__ bool s_last;
     const int c = blockIdx.z;
@@ -62,45 +66,64 @@ __global__ void __launch_bounds__(NT) ssim_l1_fwd_kernel(const float* __restrict
         const int sx = i % SX, sy = i / SX;
         const int gx = x0 + sx - HALO, gy = y0 + sy - HALO;
         const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
-        s_x1[sy][sx] = in ? p1[(size_t)gy * W + gx] : 0.0f;
-        s_x2[sy][sx] = in ? p2[(size_t)gy * W + gx] : 0.0f;
+        s_x[sy][sx] = in ? make_float2(p1[(size_t)gy * W + gx], p2[(size_t)gy * W + gx]) : make_float2(0.0f, 0.0f);
     }
     __syncthreads();
-    // horizontal pass: task = (row, segment of SEG output columns)
+    // horizontal pass: task = (row, segment of SEG output columns); consecutive lanes take consecutive ROWS
+    // (row stride 43 float2 -> conflict-free 64-bit shared accesses)
     for (int i = tid; i < SY * (TX / SEG); i += NT) {
-        const int seg = i % (TX / SEG), sy = i / (TX / SEG);
+        const int sy = i % SY, seg = i / SY;
         const int ox = seg * SEG;
-        float u[SEG + WIN - 1], v[SEG + WIN - 1];
+        f32x2 u[SEG + WIN - 1];
 #pragma unroll
-        for (int k = 0; k < SEG + WIN - 1; k++) { u[k] = s_x1[sy][ox + k]; v[k] = s_x2[sy][ox + k]; }
+        for (int k = 0; k < SEG + WIN - 1; k++) { const float2 t = s_x[sy][ox + k]; u[k] = pk(t.x, t.y); }
 #pragma unroll
         for (int o = 0; o < SEG; o++) {
-            float a = 0, b = 0, aa = 0, bb = 0, ab = 0;
+            f32x2 m = pk1(0.0f), q = pk1(0.0f);
+            float ab = 0.0f;
 #pragma unroll
             for (int k = 0; k < WIN; k++) {
-                const float w = win.w[k], uu = u[o + k], vv = v[o + k];
-                a = fmaf(w, uu, a); b = fmaf(w, vv, b);
-                aa = fmaf(w, uu * uu, aa); bb = fmaf(w, vv * vv, bb); ab = fmaf(w, uu * vv, ab);
+                const f32x2 w2 = pk1(win.w[k]);
+                const f32x2 uv = u[o + k];
+                float a1, a2;
+                upk(uv, a1, a2);
+                m = fma2(w2, uv, m);
+                q = fma2(w2, mul2(uv, uv), q);
+                ab = fmaf(win.w[k], a1 * a2, ab);
             }
-            s_h[0][sy][ox + o] = a; s_h[1][sy][ox + o] = b; s_h[2][sy][ox + o] = aa; s_h[3][sy][ox + o] = bb;
-            s_h[4][sy][ox + o] = ab;
+            float m1, m2, q1, q2;
+            upk(m, m1, m2); upk(q, q1, q2);
+            s_hm[sy][ox + o] = make_float2(m1, m2);
+            s_hs[sy][ox + o] = make_float2(q1, q2);
+            s_hc[sy][ox + o] = ab;
         }
     }
     __syncthreads();
     // vertical pass: thread = (column, segment of SEG output rows)
     const int tx = tid % TX, oy0 = (tid / TX) * SEG;
     float acc[5][SEG];
+    {
+        f32x2 cm[SEG + WIN - 1], cs[SEG + WIN - 1];
+        float cc[SEG + WIN - 1];
 #pragma unroll
-    for (int q = 0; q < 5; q++) {
-        float col[SEG + WIN - 1];
-#pragma unroll
-        for (int k = 0; k < SEG + WIN - 1; k++) col[k] = s_h[q][oy0 + k][tx];
+        for (int k = 0; k < SEG + WIN - 1; k++) {
+            const float2 a = s_hm[oy0 + k][tx], b = s_hs[oy0 + k][tx];
+            cm[k] = pk(a.x, a.y); cs[k] = pk(b.x, b.y); cc[k] = s_hc[oy0 + k][tx];
+        }
 #pragma unroll
         for (int o = 0; o < SEG; o++) {
-            float a = 0;
+            f32x2 m = pk1(0.0f), q = pk1(0.0f);
+            float ab = 0.0f;
 #pragma unroll
-            for (int k = 0; k < WIN; k++) a = fmaf(win.w[k], col[o + k], a);
-            acc[q][o] = a;
+            for (int k = 0; k < WIN; k++) {
+                const f32x2 w2 = pk1(win.w[k]);
+                m = fma2(w2, cm[o + k], m);
+                q = fma2(w2, cs[o + k], q);
+                ab = fmaf(win.w[k], cc[o + k], ab);
+            }
+            upk(m, acc[0][o], acc[1][o]);
+            upk(q, acc[2][o], acc[3][o]);
+            acc[4][o] = ab;
         }
     }
     float l1_acc = 0.0f, ssim_acc = 0.0f;
@@ -125,7 +148,8 @@ __global__ void __launch_bounds__(NT) ssim_l1_fwd_kernel(const float* __restrict
             const size_t CHW = 3 * plane;
             dmaps[o_] = dS_dmu1; dmaps[CHW + o_] = dS_dP; dmaps[2 * CHW + o_] = dS_dQ;
             ssim_acc += S;
-            l1_acc += fabsf(s_x1[oy + HALO][tx + HALO] - s_x2[oy + HALO][tx + HALO]);
+            const float2 xc = s_x[oy + HALO][tx + HALO];
+            l1_acc += fabsf(xc.x - xc.y);
         }
     }
     const float bl1 = block_sum(l1_acc, s_part);
@@ -152,8 +176,10 @@ __global__ void __launch_bounds__(NT) ssim_l1_fwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(NT) ssim_l1_bwd_kernel(const float* __restrict__ img, const float* __restrict__ gt, int H, int W,
                                                          SsimWindow win, float lambda, const float* __restrict__ dmaps,
                                                          const float* __restrict__ upstream, float* __restrict__ dL_dimg) {
-    __shared__ float s_d[3][SY][SX + 1];
-    __shared__ float s_h[3][SY][TX + 1];
+    __shared__ float2 s_d01[SY][SX + 1];           // (dS/dmu1, dS/dP) interleaved: one LDS.64 per packed FFMA2
+    __shared__ float s_d2[SY][SX + 1];             // dS/dQ
+    __shared__ float2 s_h01[SY][TX + 1];
+    __shared__ float s_h2[SY][TX + 1];
     const int c = blockIdx.z;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const size_t plane = (size_t)H * W, CHW = 3 * plane;
@@ -163,25 +189,27 @@ __global__ void __launch_bounds__(NT) ssim_l1_bwd_kernel(const float* __restrict
         const int gx = x0 + sx - HALO, gy = y0 + sy - HALO;
         const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
         const size_t o = c * plane + (size_t)gy * W + gx;
-#pragma unroll
-        for (int m = 0; m < 3; m++) s_d[m][sy][sx] = in ? dmaps[m * CHW + o] : 0.0f;
+        s_d01[sy][sx] = in ? make_float2(dmaps[o], dmaps[CHW + o]) : make_float2(0.0f, 0.0f);
+        s_d2[sy][sx] = in ? dmaps[2 * CHW + o] : 0.0f;
     }
     __syncthreads();
     for (int i = tid; i < SY * (TX / SEG); i += NT) {
-        const int seg = i % (TX / SEG), sy = i / (TX / SEG);
+        const int sy = i % SY, seg = i / SY;
         const int ox = seg * SEG;
+        f32x2 u[SEG + WIN - 1];
+        float v[SEG + WIN - 1];
 #pragma unroll
-        for (int m = 0; m < 3; m++) {
-            float u[SEG + WIN - 1];
+        for (int k = 0; k < SEG + WIN - 1; k++) { const float2 t = s_d01[sy][ox + k]; u[k] = pk(t.x, t.y); v[k] = s_d2[sy][ox + k]; }
 #pragma unroll
-            for (int k = 0; k < SEG + WIN - 1; k++) u[k] = s_d[m][sy][ox + k];
+        for (int o = 0; o < SEG; o++) {
+            f32x2 a = pk1(0.0f);
+            float d = 0.0f;
 #pragma unroll
-            for (int o = 0; o < SEG; o++) {
-                float a = 0;
-#pragma unroll
-                for (int k = 0; k < WIN; k++) a = fmaf(win.w[k], u[o + k], a);
-                s_h[m][sy][ox + o] = a;
-            }
+            for (int k = 0; k < WIN; k++) { a = fma2(pk1(win.w[k]), u[o + k], a); d = fmaf(win.w[k], v[o + k], d); }
+            float a0, a1;
+            upk(a, a0, a1);
+            s_h01[sy][ox + o] = make_float2(a0, a1);
+            s_h2[sy][ox + o] = d;
         }
     }
     __syncthreads();
@@ -190,17 +218,19 @@ __global__ void __launch_bounds__(NT) ssim_l1_bwd_kernel(const float* __restrict
     const float gS = -lambda / n * up, gL = (1.0f - lambda) / n * up;
     const int tx = tid % TX, oy0 = (tid / TX) * SEG;
     float acc[3][SEG];
+    {
+        f32x2 c01[SEG + WIN - 1];
+        float c2[SEG + WIN - 1];
 #pragma unroll
-    for (int m = 0; m < 3; m++) {
-        float col[SEG + WIN - 1];
-#pragma unroll
-        for (int k = 0; k < SEG + WIN - 1; k++) col[k] = s_h[m][oy0 + k][tx];
+        for (int k = 0; k < SEG + WIN - 1; k++) { const float2 t = s_h01[oy0 + k][tx]; c01[k] = pk(t.x, t.y); c2[k] = s_h2[oy0 + k][tx]; }
 #pragma unroll
         for (int o = 0; o < SEG; o++) {
-            float a = 0;
+            f32x2 a = pk1(0.0f);
+            float d = 0.0f;
 #pragma unroll
-            for (int k = 0; k < WIN; k++) a = fmaf(win.w[k], col[o + k], a);
-            acc[m][o] = a;
+            for (int k = 0; k < WIN; k++) { a = fma2(pk1(win.w[k]), c01[o + k], a); d = fmaf(win.w[k], c2[o + k], d); }
+            upk(a, acc[0][o], acc[1][o]);
+            acc[2][o] = d;
         }
     }
 #pragma unroll
