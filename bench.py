@@ -475,7 +475,7 @@ def main():
         }
         # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload
         # (profiles/r01_ncu_full_metrics.csv); only valid for P = 1 M @ 1920x1080, SH 3, per-Gaussian twists
-        ncu_traffic = {"preprocess_bwd": 679.9e6, "preprocess_fwd": 285.1e6}
+        ncu_traffic = {"preprocess_bwd": 677.3e6, "preprocess_fwd": 274.4e6}
         default_workload = (args.P, args.W, args.H) == (1000000, 1920, 1080)
         kernels = {}
         for name, (cnt, tot) in prof.items():
