@@ -258,10 +258,12 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* mean
     // preprocess kernel accumulates the digit histograms of its depth keys
     a.depth_hist = reinterpret_cast<uint32_t*>(ws + L.dsort_temp);
     a.rects = reinterpret_cast<uint2*>(ws + L.rects);
+    // num_rendered accumulates in a spare word of the (zeroed) sort state: tickets are words [0, 8), the error
+    // flag is word 63, words 61 and 62 serve the forward (tile-scan ticket, num_rendered)
+    uint32_t* d_total = a.depth_hist + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 62;
+    a.total = d_total;
     GSR_CHECK(cudaMemsetAsync(ws + L.dsort_temp, 0, L.dsort_temp_bytes, stream));
     if (int rc = gsr_launch_preprocess_fwd(a, v, stream)) return rc;
-    uint32_t* d_total = reinterpret_cast<uint32_t*>(ws + L.total);
-    if (int rc = gsr_launch_scan_block_sums(a.block_sums, gsr_div_up(P, 256), d_total, stream)) return rc;
     GSR_CHECK(cudaMemcpyAsync(host_num_rendered, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GSR_CHECK(cudaStreamSynchronize(stream));
     return 0;
@@ -310,7 +312,8 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
                                                  reinterpret_cast<uint4*>(gw + L.srec), pl, v.grid_x, v.grid_y,
                                                  reinterpret_cast<uint32_t*>(bw + BL.matrix),
                                                  reinterpret_cast<uint32_t*>(bw + BL.totals),
-                                                 reinterpret_cast<uint32_t*>(bw + BL.tile_base), ranges, plist, stream))
+                                                 reinterpret_cast<uint32_t*>(bw + BL.tile_base), ranges, plist,
+                                                 reinterpret_cast<uint32_t*>(gw + L.dsort_temp) + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 61, stream))
                 return rc;
             point_list = plist;
             if (materialize_keys) {

@@ -38,6 +38,7 @@ struct PreprocessArgs {
     uint32_t* depth_keys;        // [P] float bits of the view depth (0xffffffff when the Gaussian emits nothing)
     uint32_t* depth_vals;        // [P] = idx (payload of the depth sort)
     uint32_t* depth_hist;        // [4][256] digit histograms of depth_keys (pre-zeroed), accumulated here
+    uint32_t* total;             // running sum of tiles_touched = num_rendered (pre-zeroed; one atomic per block)
     uint2* rects;                // [P] tile rect (rmin.x | rmin.y << 16, rmax.x | rmax.y << 16); (0,0) when nothing is emitted
 };
 
@@ -80,7 +81,8 @@ size_t gsr_tile_matrix_bytes(int grid_x, int grid_y);
 // n_emit (device) = number of Gaussians that emit duplicates (the depth sort puts them first).
 int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
                             const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
-                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, cudaStream_t stream);
+                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, uint32_t* scan_ticket /* zeroed word */,
+                            cudaStream_t stream);
 int gsr_launch_expand_tile_ids(int num_tiles, const uint2* ranges, uint32_t* tile_ids, cudaStream_t stream);
 
 // ---- training-step kernels either side of the rasterizer: loss.cu, adam.cu ----

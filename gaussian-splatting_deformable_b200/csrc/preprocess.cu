@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
 #pragma unroll
         for (int k = 0; k < 8; k++) t += wsum[k];
         a.block_sums[blockIdx.x] = t;
+        if (t) atomicAdd(a.total, t);           // num_rendered without a scan launch in front of the host read-back
     }
     for (int k = threadIdx.x; k < 4 * 256; k += 256) {
         const uint32_t c = s_hist[k];

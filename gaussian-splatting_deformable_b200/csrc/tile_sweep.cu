@@ -231,8 +231,10 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(cons
 // chunks; totals[tile] = column sum.  CTA = 32 tiles x 8 row segments: every thread sums its
 // segment, the 8 partial sums are scanned in shared memory, then the segment is rewritten.
 __global__ void __launch_bounds__(256) tile_column_scan_kernel(int chunks, int num_tiles, uint32_t* __restrict__ matrix,
-                                                               uint32_t* __restrict__ totals) {
+                                                               uint32_t* __restrict__ totals, uint32_t* __restrict__ ticket,
+                                                               uint32_t* __restrict__ base, uint2* __restrict__ ranges) {
     __shared__ uint32_t s_part[8][33];
+    __shared__ bool s_last;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int t = blockIdx.x * 32 + tx;
     const int seg = (chunks + 7) / 8;
@@ -269,6 +271,59 @@ __global__ void __launch_bounds__(256) tile_column_scan_kernel(int chunks, int n
             run += v;
         }
         if (ty == 7) totals[t] = run;
+    }
+    // The CTA that finishes last scans the tile totals: base[tile] and the reference's `ranges`
+    // (identifyTileRanges + its memset, rasterizer_impl.cu:116-138,310) without another launch.
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) + 1u == gridDim.x);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0u;                     // ready for the next call
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0u;
+    __syncthreads();
+    // 2048 tiles per round: a thread owns 8 consecutive tiles (two 16-byte L2 loads), block scan with a carry
+    for (int c0 = 0; c0 < num_tiles; c0 += 2048) {
+        const int i0 = c0 + threadIdx.x * 8;
+        uint32_t v[8];
+        if (i0 + 8 <= num_tiles && (num_tiles & 3) == 0) {
+            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(totals + i0));
+            const uint4 b = __ldcg(reinterpret_cast<const uint4*>(totals + i0) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (i0 + k < num_tiles) ? __ldcg(totals + i0 + k) : 0u;
+        }
+        uint32_t sum8 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum8 += v[k];
+        uint32_t incl = sum8;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = s_carry, all = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { wbase += (w < warp) ? warp_tot[w] : 0u; all += warp_tot[w]; }
+        uint32_t ex = wbase + incl - sum8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (i0 + k < num_tiles) {
+                base[i0 + k] = ex;
+                ranges[i0 + k] = v[k] ? make_uint2(ex, ex + v[k]) : make_uint2(0u, 0u);
+            }
+            ex += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += all;
+        __syncthreads();
     }
 }
 
@@ -348,7 +403,7 @@ size_t gsr_tile_matrix_bytes(int grid_x, int grid_y) {
 
 int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
                             const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
-                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, cudaStream_t stream) {
+                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, uint32_t* scan_ticket, cudaStream_t stream) {
     if (P <= 0) return 0;
     if (!pl.feasible) return gsr_set_error_msg(-2, "tile sweep: plan not feasible");
     const size_t smem = (size_t)GSR_SWEEP_WARPS * pl.stripe_tiles * sizeof(uint32_t);
@@ -380,10 +435,8 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order
     }
     GSR_CHECK_LAUNCH();
     { GsrProfScope prof_("tile_column_scan", stream);
-    tile_column_scan_kernel<<<gsr_div_up(pl.num_tiles, 32), 256, 0, stream>>>(pl.chunks, pl.num_tiles, matrix, totals); }
-    GSR_CHECK_LAUNCH();
-    { GsrProfScope prof_("tile_base_scan", stream);
-    tile_base_kernel<<<1, 1024, 0, stream>>>(pl.num_tiles, totals, tile_base, ranges); }
+    tile_column_scan_kernel<<<gsr_div_up(pl.num_tiles, 32), 256, 0, stream>>>(pl.chunks, pl.num_tiles, matrix, totals, scan_ticket,
+                                                                             tile_base, ranges); }
     GSR_CHECK_LAUNCH();
     static const int scatter_v = env_int2("GSR_SWEEP_SCATTER_V", 2);
     if (scatter_v == 2) {
