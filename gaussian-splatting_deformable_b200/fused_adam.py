@@ -8,11 +8,33 @@ all-reduce buffer; moments: two more flat buffers) and runs the whole step as on
 Arithmetic is torch.optim.Adam's (torch 2.11; no amsgrad, weight decay or maximize).
 """
 import ctypes
+import math
 
 import torch
 
 import gsr_runtime as _rt
 import view_parallel
+
+
+def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+    """Learning-rate schedule of utils/general_utils.py:29-62 (same name, signature and values): log-linear
+    interpolation from lr_init (step 0) to lr_final (step max_steps), optionally eased in by a quarter sine that
+    starts at lr_delay_mult; 0 for negative steps or when both rates are 0.  The reference writes the result into
+    `param_group['lr']` every iteration (scene/gaussian_model.py:875-886); FusedAdam reads it from there."""
+    log_init = math.log(lr_init) if lr_init > 0 else None
+    log_final = math.log(lr_final) if lr_final > 0 else None
+
+    def schedule(step):
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        ease = 1.0
+        if lr_delay_steps > 0:
+            frac = min(max(step / lr_delay_steps, 0.0), 1.0)
+            ease = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * frac)
+        t = min(max(step / max_steps, 0.0), 1.0)
+        return ease * math.exp(log_init * (1 - t) + log_final * t)
+
+    return schedule
 
 
 class FusedAdam:

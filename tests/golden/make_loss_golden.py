@@ -50,5 +50,16 @@ for s in range(5):
     opt.step()
 out["adam"] = {"params": ps, "lrs": lrs, "grads": grads, "lr0_from_step3": 0.00008, "final": [p.detach().clone() for p in params],
                "torch": torch.__version__}
+# learning-rate schedule (utils/general_utils.py:29-62) with the two configurations scene/gaussian_model.py:857-864 uses
+spec2 = importlib.util.spec_from_file_location("ref_general_utils", "/root/reference/utils/general_utils.py")
+gu = importlib.util.module_from_spec(spec2)
+spec2.loader.exec_module(gu)
+steps = [-1, 0, 1, 10, 100, 999, 1000, 5000, 20000, 39999, 40000, 50000]
+cfgs = {"xyz": dict(lr_init=0.00016 * 5.0, lr_final=0.0000016 * 5.0, lr_delay_mult=0.01, max_steps=40000),
+        "offset": dict(lr_init=8e-4, lr_final=1.6e-6, max_steps=40000),
+        "delayed": dict(lr_init=1e-2, lr_final=1e-4, lr_delay_steps=500, lr_delay_mult=0.1, max_steps=3000),
+        "disabled": dict(lr_init=0.0, lr_final=0.0)}
+out["lr_schedule"] = {"steps": steps, "cfgs": cfgs,
+                      "values": {k: [float(gu.get_expon_lr_func(**c)(s)) for s in steps] for k, c in cfgs.items()}}
 torch.save(out, os.path.join(HERE, "loss_golden.pt"))
 print("wrote", os.path.join(HERE, "loss_golden.pt"), [float(c["loss"]) for c in out["cases"]])

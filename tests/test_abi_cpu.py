@@ -202,3 +202,14 @@ def test_flat_grad_buffer_rebind_and_sequential_render_views():
     seen = []
     total = view_parallel.render_views(lambda i: (seen.append(i), torch.tensor(float(i)))[1], [3, 1, 2], num_streams=4)
     assert seen == [3, 1, 2] and float(total) == 6.0
+
+
+def test_lr_schedule_matches_the_reference_function():
+    import fused_adam
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "loss_golden.pt"), weights_only=False)["lr_schedule"]
+    for name, cfg in gold["cfgs"].items():
+        f = fused_adam.get_expon_lr_func(**cfg)
+        for s, want in zip(gold["steps"], gold["values"][name]):
+            assert abs(f(s) - want) <= 1e-12 * max(1.0, abs(want)) + 1e-18, (name, s)
+    assert list(inspect.signature(fused_adam.get_expon_lr_func).parameters) == [
+        "lr_init", "lr_final", "lr_delay_steps", "lr_delay_mult", "max_steps"]
