@@ -1,28 +1,28 @@
-// Tile blending, forward and backward.
+// Tile blending, forward and backward - FIRST-GENERATION kernels (CTA-cooperative staging), kept as the
+// selectable fallback/baseline of blend_v2.cu (GSR_BLEND_FWD_V=1 / GSR_BLEND_BWD_V=1) and as the home of the
+// TMA-staged variant (GSR_BLEND_TMA=1) and of the workload counters (gsr_debug_blend_stats).
 //
 // Replaces cuda_rasterizer/forward.cu:261-374 (renderCUDA fwd) and
-// backward.cu:399-557 (renderCUDA bwd).  One CTA per 16x16 tile, one thread per
-// pixel; a warp owns an 8x4 pixel patch (compact patches diverge less than the
-// reference's 16x2 rows).  FP32-pipe / shared-memory bound, not HBM bound.
+// backward.cu:399-557 (renderCUDA bwd).  One CTA per 16x16 tile; a warp owns PPT 8x4 pixel
+// patches (compact patches diverge less than the reference's 16x2 rows).
 //
 // What is kept bit-identical to the reference: the exponent `power`, expf, alpha,
 // the three reject tests and the T recurrence - every decision a pixel takes is
 // the reference's decision (a flipped 1/255 test would move a pixel by ~4e-3).
 // What is redesigned:
-//   * each 256-entry batch of the tile's list is CULLED while it is staged: an
+//   * each batch of the tile's list is CULLED while it is staged: an
 //     entry whose Gaussian cannot reach alpha >= 1/255 anywhere inside this tile
 //     (closed-form minimum of the conic form over the tile rectangle, with a
 //     rounding-safe margin) is dropped by a stable ballot compaction, so the
-//     256 pixel threads never loop over it.  The reference's lists come from a
+//     pixel threads never loop over it.  The reference's lists come from a
 //     3-sigma circle's bounding square and are mostly such entries;
 //   * surviving pixels reject with `power < cut` (cut = log(1/(255 opacity)) minus a
 //     margin, precomputed per Gaussian) before paying for expf;
 //   * colours ride in the staged record (no global load in the inner loop);
 //   * the next batch's gathers are issued before the current batch is blended;
 //   * backward: per-Gaussian gradients are reduced across the warp with a
-//     transposing butterfly (14 shuffles for 9 values instead of 45), summed
-//     across the CTA's warps in shared memory, and leave the SM as two 128-bit
-//     vector reductions + one scalar per (tile, Gaussian) - the reference issues
+//     transposing butterfly (14 shuffles for 9 values instead of 45) and leave the SM as
+//     nine native RED.ADD.F32 per (warp, Gaussian) - the reference issues
 //     9 scalar atomics per (pixel, Gaussian).
 #include "geom_exact.cuh"
 #include "kernels.cuh"

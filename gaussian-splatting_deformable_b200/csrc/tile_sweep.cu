@@ -10,7 +10,8 @@
 //   order" = a STABLE partition of the duplicate stream by tile id.  A stable partition
 //   is a counting sort:
 //     up-sweep    count[chunk][tile]   (chunk = G consecutive Gaussians of the depth order)
-//     scan        start[chunk][tile] = base[tile] + sum_{c' < chunk} count[c'][tile]
+//     scan        start[chunk][tile] = base[tile] + sum_{c' < chunk} count[c'][tile]   (tile_column_scan_kernel;
+//                 its last CTA also scans the tile totals)
 //                 (base = exclusive scan of the tile totals = the reference's `ranges`)
 //     down-sweep  every duplicate goes straight to point_list[start + rank-in-chunk]
 //   HBM traffic: 16 B x P (sorted rect records, read twice) + the chunk x tile matrix
@@ -324,43 +325,6 @@ __global__ void __launch_bounds__(256) tile_column_scan_kernel(int chunks, int n
         __syncthreads();
         if (threadIdx.x == 0) s_carry += all;
         __syncthreads();
-    }
-}
-
-// Exclusive scan of the tile totals by one CTA -> base[tile]; ranges[tile] = [base, base+total)
-// or (0,0) for an empty tile (what identifyTileRanges + its memset leave, rasterizer_impl.cu:116-138,310).
-__global__ void __launch_bounds__(1024) tile_base_kernel(int num_tiles, const uint32_t* __restrict__ totals,
-                                                         uint32_t* __restrict__ base, uint2* __restrict__ ranges) {
-    __shared__ uint32_t warp_tot[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = (num_tiles + 1023) / 1024;             // consecutive tiles per thread
-    const int i0 = threadIdx.x * per, i1 = min(num_tiles, i0 + per);
-    uint32_t v = 0;
-    for (int i = i0; i < i1; i++) v += totals[i];
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_tot[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, w, o);
-            if (lane >= o) w += t;
-        }
-        warp_tot[lane] = w;
-    }
-    __syncthreads();
-    uint32_t ex = (warp ? warp_tot[warp - 1] : 0u) + incl - v;
-    for (int i = i0; i < i1; i++) {
-        const uint32_t c = totals[i];
-        base[i] = ex;
-        ranges[i] = c ? make_uint2(ex, ex + c) : make_uint2(0u, 0u);
-        ex += c;
     }
 }
 
