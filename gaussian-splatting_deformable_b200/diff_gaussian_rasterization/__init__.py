@@ -98,6 +98,9 @@ def rasterize_gaussians(
     )
 
 
+_BUCKET = 64 << 20
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(
@@ -151,7 +154,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _rt.ptr(radii), _rt.ptr(geom), geom.numel(), mailbox.data_ptr(),
                     1 if raster_settings.debug else 0, stream))
                 num_rendered = int(mailbox.item()) & 0xFFFFFFFF
-            binning = torch.empty(lib.gsr_binning_bytes(num_rendered, W, H), dtype=torch.uint8, device=dev)
+            # num_rendered differs from view to view: round the workspace up to a 64 MB bucket so that the caching
+            # allocator can hand the same block to every view (exact sizes make it split and re-cudaMalloc blocks,
+            # which stalls the GPU for milliseconds once several streams' pools fragment)
+            nbytes = lib.gsr_binning_bytes(num_rendered, W, H)
+            binning = torch.empty(((nbytes + _BUCKET - 1) // _BUCKET) * _BUCKET, dtype=torch.uint8, device=dev)
             _rt.check(lib.gsr_forward_render(view, P, num_rendered, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
                                              binning.numel(), _rt.ptr(img), _rt.ptr(color),
                                              1 if raster_settings.debug else 0, stream))
