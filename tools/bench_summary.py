@@ -8,7 +8,8 @@ print("ms_per_view %.4f  value %.1f M/s  e2e %.1f M/s  launches %s" % (d["ms_per
 tot = 0.0
 for k, x in (d.get("kernels") or {}).items():
     per_view = x["total_ms"] / v
-    tot += per_view
+    if k != "binning_stage":          # a derived entry (sum of the binning kernels), not a kernel
+        tot += per_view
     print("  %-28s x%-3d avg %.4f ms  per-view %.4f ms  %s" % (k, x["launches"] // v, x["avg_ms"], per_view,
           ("%.0f GB/s (%.0f%%)" % (x["alg_GBps"], 100 * x["frac_of_hbm_peak"])) if "alg_GBps" in x else ""))
 print("  kernel sum per view %.4f ms" % tot)
