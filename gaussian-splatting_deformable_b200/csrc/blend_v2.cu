@@ -14,8 +14,13 @@
 //     FFMA2/FMUL2/FADD2 (f32x2.cuh): same IEEE roundings as the reference's scalar
 //     sequence, half the issue slots.  expf is CUDA's own algorithm restated on packed
 //     values.  These kernels are issue-bound (profiles/), so issue slots are the currency.
-//   * backward: the per-Gaussian sums leave a warp as before (transposing butterfly + 9
-//     native RED.ADD.F32), once per (region, Gaussian).
+//   * the loop bodies are STRAIGHT-LINE code: after the region cull 92 % of the iterations blend, so a
+//     pixel that does not blend simply runs with alpha = 0 (and a finished pixel is parked far away so
+//     that the ordinary power test rejects everything) - no skips, no phi copies, 31 of 32 threads active.
+//   * backward: per-Gaussian sums are accumulated as six moments (common.cuh) plus the colour
+//     gradient, parked for four consecutive Gaussians in a warp-private shared buffer and reduced
+//     together (8 x LDS.128 + FADD2 per lane), then leave the SM as 9 native RED.ADD.F32 per
+//     (region, Gaussian).  Template switches keep the measured alternatives selectable.
 #include "f32x2.cuh"
 #include "geom_exact.cuh"
 #include "kernels.cuh"
