@@ -16,26 +16,30 @@ import gsr_runtime as _rt
 
 
 def l1_loss(network_output, gt):
-    # utils/loss_utils.py:17-18
-    return torch.abs((network_output - gt)).mean()
+    """Mean absolute error (utils/loss_utils.py:17-18)."""
+    return (network_output - gt).abs().mean()
 
 
 def l2_loss(network_output, gt):
-    # utils/loss_utils.py:20-21
-    return ((network_output - gt) ** 2).mean()
+    """Mean squared error (utils/loss_utils.py:20-21)."""
+    diff = network_output - gt
+    return (diff * diff).mean()
 
 
 def gaussian(window_size, sigma):
-    # utils/loss_utils.py:23-25 (values computed exactly as the reference computes them)
-    gauss = torch.Tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
-    return gauss / gauss.sum()
+    """Normalised 1-D Gaussian taps as a float32 tensor - the values utils/loss_utils.py:23-25 produces
+    (double-precision exp per tap, rounded to float32, then normalised in float32)."""
+    centre = window_size // 2
+    denom = float(2 * sigma ** 2)
+    taps = torch.tensor([exp(-((x - centre) ** 2) / denom) for x in range(window_size)], dtype=torch.float32)
+    return taps / taps.sum()
 
 
 def create_window(window_size, channel):
-    # utils/loss_utils.py:27-31
-    _1D_window = gaussian(window_size, 1.5).unsqueeze(1)
-    _2D_window = _1D_window.mm(_1D_window.t()).float().unsqueeze(0).unsqueeze(0)
-    return _2D_window.expand(channel, 1, window_size, window_size).contiguous()
+    """[channel, 1, k, k] window = outer product of the 1-D taps (sigma 1.5), utils/loss_utils.py:27-31."""
+    w1 = gaussian(window_size, 1.5)
+    w2 = torch.outer(w1, w1).float()
+    return w2.expand(channel, 1, window_size, window_size).contiguous()
 
 
 _WINDOW11 = None
