@@ -162,3 +162,37 @@ def test_adam_port_matches_torch_adam_as_the_reference_configures_it(loss_gold):
         opt.step()
     for p, f in zip(ps, a["final"]):
         assert torch.allclose(p.detach(), f, rtol=0, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------
+# Deformation network (oracle only so far): the port against outputs of the REAL classes
+# ---------------------------------------------------------------------------
+def test_deformation_mlp_port_matches_the_reference_classes():
+    from oracle import deform_mlp_port as port
+    g = torch.load(os.path.join(GOLD, "mlp_golden.pt"), weights_only=False)
+
+    def same_digest(t, d):
+        f = t.detach().double().reshape(-1)
+        return (tuple(t.shape) == d["shape"] and abs(float(f.sum()) - d["sum"]) <= 1e-9 * max(1.0, d["abs_sum"]) and
+                torch.equal(t.detach().reshape(-1)[:16], d["head"]) and torch.equal(t.detach().reshape(-1)[-16:], d["tail"]))
+
+    assert torch.equal(port.embed(g["x"]), g["embed_x"]) and g["embed_dim"] == 63
+    torch.manual_seed(g["seed"])
+    net = port.DeformMLP()
+    assert sum(p.numel() for p in net.parameters()) == 513338
+    for k, p in net.named_parameters():                      # same names, same initial values as the reference module
+        assert same_digest(p, g["params"][k]), k
+    x = g["x"].clone().requires_grad_(True)
+    outs = net(x, g["ts"], g["iteration"])
+    for o, want in zip(outs, g["outs"]):
+        assert torch.equal(o.detach(), want)
+    sum((o * p).sum() for o, p in zip(outs, g["proj"])).backward()
+    assert torch.equal(x.grad, g["dx"])
+    for k, p in net.named_parameters():
+        assert same_digest(p.grad, g["dparams"][k]), k
+    for o, want in zip(net(g["x"], g["ts"], 100), g["outs_early"]):     # iteration < 3000: zeros of the right shapes
+        assert torch.equal(o, want) and float(o.abs().sum()) == 0.0
+    S, th = port.screw_from_raw(g["se3"]["w_raw"], g["se3"]["v_raw"])
+    assert torch.equal(S, g["se3"]["S"]) and torch.equal(th, g["se3"]["theta"])
+    from oracle import rigid_body_port
+    assert torch.allclose(rigid_body_port.exp_se3(S, th), g["se3"]["transform"], rtol=0, atol=1e-6)
