@@ -106,6 +106,82 @@ class FusedAdam:
                                         self.exp_avg_sq.data_ptr(), n, begin, arr(ss), arr(bc), darr(b1s), darr(b2s), arr(es),
                                         _rt.stream_ptr(dev)))
 
+    # -- optimizer-state surgery of densification (scene/gaussian_model.py:1027-1100) on the flat buffers --
+    def _group_views(self, buf):
+        """Per group: list of views of `buf` shaped like the group's parameters."""
+        out, off = [], 0
+        for g in self.param_groups:
+            vs = []
+            for p in g["params"]:
+                n = p.numel()
+                vs.append(buf[off:off + n].view_as(p))
+                off += n
+            out.append(vs)
+        return out
+
+    def _rebuild(self, new_p, new_m, new_v):
+        """Re-home every parameter (same Python objects, possibly new shapes) into fresh flat buffers."""
+        dev = self.flat_params.device
+        total = sum(t.numel() for grp in new_p for t in grp)
+        flat_p = torch.empty(total + ((-total) % 4), dtype=torch.float32, device=dev)
+        flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        off, begin, params = 0, [], []
+        for g, ps, ms, vs in zip(self.param_groups, new_p, new_m, new_v):
+            begin.append(off)
+            for p, val, m, v in zip(g["params"], ps, ms, vs):
+                n = val.numel()
+                flat_p[off:off + n].copy_(val.reshape(-1))
+                flat_m[off:off + n].copy_(m.reshape(-1))
+                flat_v[off:off + n].copy_(v.reshape(-1))
+                p.grad = None
+                p.data = flat_p[off:off + n].view(val.shape)
+                params.append(p)
+                off += n
+        begin.append(off)
+        self.flat_params, self.exp_avg, self.exp_avg_sq, self._begin, self._params = flat_p, flat_m, flat_v, begin, params
+        self.grads = view_parallel.FlatGradBuffer(params)
+        return {g.get("name", str(i)): g["params"][0] for i, g in enumerate(self.param_groups) if len(g["params"]) == 1}
+
+    def _per_point(self, g, n):
+        return len(g["params"]) == 1 and g["params"][0].dim() >= 1 and g["params"][0].shape[0] == n
+
+    def prune(self, valid_mask):
+        """`_prune_optimizer` (gaussian_model.py:1042-1063): keep rows `valid_mask` of every single-tensor group whose
+        first dimension is the point count, together with their moments.  Returns {group name: parameter}."""
+        n = valid_mask.numel()
+        P, M, V = self._group_views(self.flat_params), self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        if not any(self._per_point(g, n) for g in self.param_groups):
+            raise ValueError("prune: no parameter group has %d rows" % n)
+        keep = lambda grp, g: [t[valid_mask] if self._per_point(g, n) else t for t in grp]
+        return self._rebuild([keep(a, g) for a, g in zip(P, self.param_groups)], [keep(a, g) for a, g in zip(M, self.param_groups)],
+                             [keep(a, g) for a, g in zip(V, self.param_groups)])
+
+    def append(self, tensors_dict):
+        """`cat_tensors_to_optimizer` (gaussian_model.py:1084-1107): append rows to the groups named in `tensors_dict`;
+        the new rows start with zero moments.  Returns {group name: parameter}."""
+        P, M, V = self._group_views(self.flat_params), self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        np_, nm, nv = [], [], []
+        for g, ps, ms, vs in zip(self.param_groups, P, M, V):
+            ext = tensors_dict.get(g.get("name")) if len(g["params"]) == 1 else None
+            if ext is None:
+                np_.append(ps); nm.append(ms); nv.append(vs)
+            else:
+                ext = ext.detach().to(ps[0].device, torch.float32)
+                np_.append([torch.cat((ps[0], ext), dim=0)])
+                nm.append([torch.cat((ms[0], torch.zeros_like(ext)), dim=0)])
+                nv.append([torch.cat((vs[0], torch.zeros_like(ext)), dim=0)])
+        return self._rebuild(np_, nm, nv)
+
+    def replace(self, name, tensor):
+        """`replace_tensor_to_optimizer` (gaussian_model.py:1027-1040): new values for one group, moments reset to zero."""
+        P, M, V = self._group_views(self.flat_params), self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        for i, g in enumerate(self.param_groups):
+            if g.get("name") == name and len(g["params"]) == 1:
+                t = tensor.detach().to(P[i][0].device, torch.float32)
+                P[i], M[i], V[i] = [t], [torch.zeros_like(t)], [torch.zeros_like(t)]
+        return self._rebuild(P, M, V)
+
     def state_dict(self):
         return {"step": self.state_step, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}

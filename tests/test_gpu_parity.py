@@ -583,3 +583,75 @@ def test_c3_training_loop_recovers_a_rigid_body_motion():
     assert losses[-1] < 0.8 * losses[0], (losses[0], losses[-1])
     assert err1 < err0, (err0, err1)
     assert torch.equal(S.detach(), S_true)                           # lr 0 group untouched
+
+
+def test_fused_adam_densification_surgery_vs_torch_adam():
+    """prune / append / replace on the flat buffers against torch.optim.Adam with the reference's own state surgery
+    (scene/gaussian_model.py:1027-1107: moments of kept rows survive, new rows start at zero, the step count stays)."""
+    import fused_adam
+    g = torch.Generator().manual_seed(9)
+    N = 1003
+    shapes = {"xyz": (N, 3), "f_rest": (N, 15, 3), "opacity": (N, 1), "twists": (64, 6)}
+    lrs = {"xyz": 1.6e-4, "f_rest": 1.25e-4, "opacity": 0.05, "twists": 1e-3}
+    base = {k: torch.randn(s, generator=g).cuda() for k, s in shapes.items()}
+    pa = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+    pb = {k: torch.nn.Parameter(v.clone()) for k, v in base.items()}
+    oa = fused_adam.FusedAdam([{"params": [pa[k]], "lr": lrs[k], "name": k} for k in shapes], lr=0.0, eps=1e-15)
+    ob = torch.optim.Adam([{"params": [pb[k]], "lr": lrs[k], "name": k} for k in shapes], lr=0.0, eps=1e-15)
+
+    def step():
+        oa.zero_grad()
+        for grp_a, grp_b in zip(oa.param_groups, ob.param_groups):
+            gr = torch.randn(grp_b["params"][0].shape, generator=g).cuda() * 0.1
+            grp_a["params"][0].grad.copy_(gr)
+            grp_b["params"][0].grad = gr.clone()
+        oa.step(); ob.step()
+
+    def ref_surgery(fn):          # the reference's pattern: swap the parameter, carry the state dict over
+        for grp in ob.param_groups:
+            old = grp["params"][0]
+            st = ob.state.pop(old)
+            new = fn(grp["name"], old.detach(), st)
+            grp["params"][0] = torch.nn.Parameter(new)
+            ob.state[grp["params"][0]] = st
+
+    def check():
+        for grp_a, grp_b in zip(oa.param_groups, ob.param_groups):
+            a, b = grp_a["params"][0], grp_b["params"][0]
+            assert a.shape == b.shape and torch.allclose(a.detach(), b.detach(), rtol=1e-6, atol=1e-7), grp_a["name"]
+
+    step(); step()
+    mask = (torch.rand(N, generator=g) > 0.3).cuda()
+    oa.prune(mask)
+
+    def prune_fn(name, old, st):
+        if old.shape[0] != N:
+            return old
+        st["exp_avg"], st["exp_avg_sq"] = st["exp_avg"][mask], st["exp_avg_sq"][mask]
+        return old[mask]
+    ref_surgery(prune_fn)
+    check(); step(); check()
+    n1 = int(mask.sum())
+    ext = {k: torch.randn((57,) + shapes[k][1:], generator=g).cuda() for k in ("xyz", "f_rest", "opacity")}
+    named = oa.append(ext)
+    assert named["xyz"].shape[0] == n1 + 57 and named["xyz"] is pa["xyz"] and pa["xyz"].grad.shape == pa["xyz"].shape
+
+    def cat_fn(name, old, st):
+        if name not in ext:
+            return old
+        st["exp_avg"] = torch.cat((st["exp_avg"], torch.zeros_like(ext[name])), 0)
+        st["exp_avg_sq"] = torch.cat((st["exp_avg_sq"], torch.zeros_like(ext[name])), 0)
+        return torch.cat((old, ext[name]), 0)
+    ref_surgery(cat_fn)
+    check(); step(); step(); check()
+    new_op = torch.full_like(pa["opacity"].detach(), -4.6)           # reset_opacity (gaussian_model.py:960-963)
+    oa.replace("opacity", new_op)
+
+    def rep_fn(name, old, st):
+        if name != "opacity":
+            return old
+        st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(new_op), torch.zeros_like(new_op)
+        return new_op.clone()
+    ref_surgery(rep_fn)
+    check(); step(); check()
+    assert pa["twists"].shape == (64, 6)
