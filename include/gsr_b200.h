@@ -30,6 +30,10 @@
  *   gsr_sort_pairs
  *       <- cub::DeviceRadixSort::SortPairs as called at rasterizer_impl.cu:303-308
  *          (exported so the sort can be tested and profiled on its own)
+ *   gsr_ssim_l1_loss_forward / gsr_ssim_l1_loss_backward
+ *       <- utils/loss_utils.py:17-64 (l1_loss, ssim) combined as in train.py:323,529
+ *   gsr_adam_step
+ *       <- torch.optim.Adam as configured at scene/gaussian_model.py:834-846
  */
 #ifndef GSR_B200_H
 #define GSR_B200_H
@@ -101,7 +105,7 @@ void gsr_image_layout(int width, int height, size_t out[3]);
 void gsr_binning_layout(uint32_t num_rendered, int width, int height, size_t out[4]);
 
 /* ---- forward -------------------------------------------------------------
- * Stage 1: deform + project + covariance + SH, offsets scan.  Writes radii[P]
+ * Stage 1: deform + project + covariance + SH (num_rendered is summed by the same kernel).  Writes radii[P]
  * (int32), optional means_out[P,3] (required when deform->mode != 0), fills the
  * geometry workspace, copies num_rendered to *host_num_rendered (pinned host
  * memory recommended) and synchronises the stream - the one host round trip of
@@ -117,8 +121,9 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M,
                            int32_t* radii, void* geom_ws, size_t geom_bytes,
                            uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream);
 
-/* Stage 2: depth-order the Gaussians (onesweep), duplicate (tile id, Gaussian id) pairs,
- * onesweep by tile id, tile ranges, blend.  out_color[3,H,W].  materialize_keys != 0 also
+/* Stage 2: depth-order the Gaussians (onesweep), then one stable counting sort of their tile duplicates into the
+ * per-tile lists (= the reference's sorted point_list and ranges; radix fallback: duplicate + onesweep by tile id +
+ * tile ranges), then blend.  out_color[3,H,W].  materialize_keys != 0 also
  * writes the reference-format sorted 64-bit keys (tile << 32 | depth bits) for parity checks. */
 int gsr_forward_render(const gsr_view* view, int P, uint32_t num_rendered,
                        const int32_t* radii, void* geom_ws, void* binning_ws, size_t binning_bytes,
