@@ -38,6 +38,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_deformable_b200"))
 
 PARAM_KEYS = ("means3D", "scales", "rotations", "opacities", "shs")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` at the default workload (profiles/)
+NCU_TRAFFIC = {"preprocess_bwd": 677.3e6, "preprocess_fwd": 274.4e6}
 
 
 # ---------------------------------------------------------------------------
@@ -91,11 +93,28 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
+CONFIGS = {
+    # BASELINE.json configs[1..4]; C2 is the configuration the metric is quoted on (the default)
+    "C2": dict(P=1000000, W=1920, H=1080, views=8, bodies=False,
+               what="C2: 1 M Gaussians, SH degree 3, 1920x1080, per-Gaussian SE3 exp-map deform + rasterize fwd+bwd"),
+    "C3": dict(P=500000, W=800, H=800, views=4, bodies=True,
+               what="C3: 500 k Gaussians in 64 rigid bodies (body twist table of frame f of 300, a new frame every step), "
+                    "800x800, fused SE3 + rasterize fwd+bwd"),
+    "C4": dict(P=6000000, W=3840, H=2160, views=1, bodies=False,
+               what="C4: 6 M Gaussians at 3840x2160 (tile/sort-heavy stress), per-Gaussian SE3 + rasterize fwd+bwd"),
+}
+
+
 def build_workload(args, rank, world, dev):
     import synthetic
     sc = synthetic.make_scene(args.P, seed=0, device="cpu")
-    S, theta = synthetic.make_twists(args.P, seed=2, device="cpu")
     host = {k: sc[k].pin_memory() for k in PARAM_KEYS}
+    if args.bodies:
+        body_id, S, theta = synthetic.make_bodies(sc["means3D"], frame=150, frames=300, device="cpu")
+        args.body_id = body_id.to(dev)
+    else:
+        S, theta = synthetic.make_twists(args.P, seed=2, device="cpu")
+        args.body_id = None
     host["S"], host["theta"] = S.pin_memory(), theta.pin_memory()
     total_views = args.views * world
     K = max(total_views, 64)
@@ -154,14 +173,29 @@ def step_ours(leaves, cams, bg, grad, args):
         rs = synthetic.raster_settings(cams[i], bg, sh_degree=3)
         ras = GaussianRasterizer(rs)
         means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-        color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
-                           shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
-                           se3_S=leaves["S"], se3_theta=leaves["theta"], accumulate_grads=sinks)
+        if getattr(args, "no_deform", False):
+            snk = {k: v for k, v in sinks.items() if not k.startswith("se3_")}
+            color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                               shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"], accumulate_grads=snk)
+        else:
+            color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                               shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                               se3_S=leaves["S"], se3_theta=leaves["theta"], body_id=args.body_id, accumulate_grads=sinks)
         loss = (color * grad).sum()
         loss.backward()
         return loss.detach()
 
     return view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams)
+
+
+def _ref_deform(leaves, args):
+    """The reference's torch op graph for the deformation: exp_se3 + the apply recipe (rigid bodies: the body's twist
+    gathered per Gaussian first, which is what the reference API shape S[N,6], theta[N] asks for)."""
+    from oracle import rigid_body_port
+    if args.body_id is not None:
+        idx = args.body_id.long()
+        return rigid_body_port.deform_points(leaves["means3D"], leaves["S"][idx], leaves["theta"][idx])
+    return rigid_body_port.deform_points(leaves["means3D"], leaves["S"], leaves["theta"])
 
 
 def step_reference(leaves, cams, bg, grad, args):
@@ -172,19 +206,84 @@ def step_reference(leaves, cams, bg, grad, args):
     loss_total = None
     for cam in cams:
         rs = synthetic.raster_settings(cam, bg, sh_degree=3)
-        y = rigid_body_port.deform_points(leaves["means3D"], leaves["S"], leaves["theta"])
+        no_deform = getattr(args, "no_deform", False)
+        y = leaves["means3D"] if no_deform else _ref_deform(leaves, args)
         yd = y.detach()
         f = ref_driver.forward(rs, yd, leaves["opacities"].detach(), shs=leaves["shs"].detach(),
                                scales=leaves["scales"].detach(), rotations=leaves["rotations"].detach())
         loss = (f["color"] * grad).sum()
         g = ref_driver.backward(rs, f, grad, yd, shs=leaves["shs"].detach(), scales=leaves["scales"].detach(),
                                 rotations=leaves["rotations"].detach())
-        y.backward(g["means3D"])
+        if no_deform:
+            y.grad = g["means3D"] if y.grad is None else y.grad + g["means3D"]
+        else:
+            y.backward(g["means3D"])
         for k, gk in (("opacities", "opacities"), ("shs", "shs"), ("scales", "scales"), ("rotations", "rotations")):
             t = leaves[k]
             t.grad = g[gk].view_as(t) if t.grad is None else t.grad + g[gk].view_as(t)
         loss_total = loss.detach() if loss_total is None else loss_total + loss.detach()
     return loss_total
+
+
+def counters_ours(leaves, cam, bg, args):
+    """Data-dependent counters of one view, read from the library's own workspaces after a
+    forward through the raw C ABI: visible Gaussians, num_rendered R, the sum of n_contrib (list entries every pixel
+    walks before it terminates; bit-equal to the reference's buffer, tests/test_gpu_parity.py), and the blend
+    stage's pair counts from gsr_debug_blend_stats (a replay of the forward loop)."""
+    import gsr_runtime as rt
+    import synthetic
+    lib = rt.load()
+    dev = leaves["means3D"].device
+    P, W, H = args.P, args.W, args.H
+    rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+    view = rt.make_view(rs)
+    d = {k: v.detach() for k, v in leaves.items()}
+    geom = torch.empty(lib.gsr_geom_bytes(P), dtype=torch.uint8, device=dev)
+    img = torch.empty(lib.gsr_image_bytes(W, H), dtype=torch.uint8, device=dev)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+    color = torch.empty((3, H, W), device=dev)
+    means_def = torch.empty((P, 3), device=dev)
+    mb = rt.pinned_u32(dev)
+    st = rt.stream_ptr(dev)
+    df = rt.gsr_deform()
+    df.mode = rt.DEFORM_RIGID_BODIES if args.body_id is not None else rt.DEFORM_PER_GAUSSIAN
+    df.num_bodies = int(d["S"].shape[0]) if args.body_id is not None else 0
+    df.S, df.theta = d["S"].data_ptr(), d["theta"].data_ptr()
+    df.body_id = args.body_id.data_ptr() if args.body_id is not None else None
+    rt.check(lib.gsr_forward_preprocess(view, P, 16, rt.ptr(d["means3D"]), rt.ptr(d["scales"]), rt.ptr(d["rotations"]),
+                                        rt.ptr(d["opacities"]), rt.ptr(d["shs"]), None, None, df, rt.ptr(means_def),
+                                        rt.ptr(radii), rt.ptr(geom), geom.numel(), mb.data_ptr(), 0, st))
+    R = int(mb.item()) & 0xFFFFFFFF
+    binning = torch.empty(lib.gsr_binning_bytes(R, W, H), dtype=torch.uint8, device=dev)
+    rt.check(lib.gsr_forward_render(view, P, R, rt.ptr(radii), rt.ptr(geom), rt.ptr(binning), binning.numel(),
+                                    rt.ptr(img), rt.ptr(color), 0, st))
+    out = torch.zeros(8, dtype=torch.int64, device=dev)
+    rt.check(lib.gsr_debug_blend_stats(view, P, R, rt.ptr(geom), rt.ptr(binning), rt.ptr(img), rt.ptr(out), st))
+    torch.cuda.synchronize()
+    il = rt.image_layout(W, H)
+    n_contrib = img[il["n_contrib"]:il["n_contrib"] + 4 * W * H].view(torch.int32)
+    o = out.tolist()
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    return {"P": P, "P_visible": int((radii > 0).sum()), "R": R, "sum_n_contrib": int(n_contrib.long().sum()),
+            "pairs_evaluated": o[5], "pairs_blended": o[6], "list_entries_after_cull": o[1], "tiles": tiles,
+            "sort_passes_reference_scheme": (32 + max(tiles, 1).bit_length() + 7) // 8,
+            "source": "libgsr_b200 workspaces of the step's last view (n_contrib / R / radii are bit-equal to the reference's, "
+                      "see tests); pairs_* from gsr_debug_blend_stats"}
+
+
+def counters_reference(leaves, cam, bg, args):
+    """The same counters from the reference rasterizer's own buffers (oracle/_ref)."""
+    import synthetic
+    from oracle import ref_driver
+    rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+    with torch.no_grad():
+        y = _ref_deform(leaves, args)
+        f = ref_driver.forward(rs, y, leaves["opacities"].detach(), shs=leaves["shs"].detach(),
+                               scales=leaves["scales"].detach(), rotations=leaves["rotations"].detach())
+    im = ref_driver.slice_img(f["img"], args.W, args.H)
+    return {"P": args.P, "P_visible": int((f["radii"] > 0).sum()), "R": f["num_rendered"],
+            "sum_n_contrib": int(im["n_contrib"].long().sum()),
+            "source": "reference rasterizer buffers (radii, num_rendered, ImageState::n_contrib) of the step's last view"}
 
 
 def allreduce_grads(leaves, world):
@@ -235,7 +334,7 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
             means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
             color, _ = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
                            scales=leaves["scales"], rotations=leaves["rotations"], se3_S=leaves["S"],
-                           se3_theta=leaves["theta"], accumulate_grads=sinks)
+                           se3_theta=leaves["theta"], body_id=args.body_id, accumulate_grads=sinks)
             loss = loss_utils.l1_ssim_loss(color, targets[i], 0.2)
             loss.backward()
             return loss.detach()
@@ -250,7 +349,7 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
     total = None
     for i, cam in enumerate(cams):
         rs = synthetic.raster_settings(cam, bg, sh_degree=3)
-        y = rigid_body_port.deform_points(leaves["means3D"], leaves["S"], leaves["theta"])
+        y = _ref_deform(leaves, args)
         yd = y.detach()
         f = ref_driver.forward(rs, yd, leaves["opacities"].detach(), shs=leaves["shs"].detach(),
                                scales=leaves["scales"].detach(), rotations=leaves["rotations"].detach())
@@ -300,10 +399,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--views", type=int, default=8, help="views per GPU per step")
-    ap.add_argument("--P", type=int, default=1000000)
-    ap.add_argument("--W", type=int, default=1920)
-    ap.add_argument("--H", type=int, default=1080)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: C2 (default, the one the metric is quoted on), C3 (500 k Gaussians in 64 rigid "
+                         "bodies, 800x800; add --train for the whole training step), C4 (6 M Gaussians at 3840x2160)")
+    ap.add_argument("--views", type=int, default=None, help="views per GPU per step (default: the config's)")
+    ap.add_argument("--P", type=int, default=None)
+    ap.add_argument("--W", type=int, default=None)
+    ap.add_argument("--H", type=int, default=None)
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are spread over (ours)")
     ap.add_argument("--train", action="store_true",
                     help="also time the whole C5-style training step: per-view loss 0.8 L1 + 0.2 (1 - SSIM) against a fixed "
@@ -311,6 +413,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
+    for k in ("P", "W", "H", "views"):
+        if getattr(args, k) is None:
+            setattr(args, k, cfg[k])
+    args.bodies = cfg["bodies"]
+    args.no_deform = False
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -383,6 +491,45 @@ def main():
     views_total = args.views * world
     value = args.P * views_total / (ms_per_step * 1e-3)
 
+    # ---------------- breakdown: the rasterizer alone (no deformation), and for the reference arm its torch SE3 graph ----
+    # north_star's target is ">= 2x the reference CUDA rasterizer's fwd+bwd throughput": both arms print
+    # `rasterizer_only_ms_per_view` for the same un-deformed scene, so the ratio can be read off the two driver records.
+    breakdown = None
+    if rank == 0 or world > 1:
+        def timed(fn, n):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        nb = max(2, min(args.steps, 5))
+        args.no_deform = True
+
+        def rast_only():
+            if args.impl != "ours":
+                zero_grads(leaves)
+            step_fn(leaves, cams, bg, grad, args)
+        t_rast = timed(rast_only, nb) / args.views
+        args.no_deform = False
+        breakdown = {"rasterizer_only_ms_per_view": round(t_rast, 4),
+                     "what": "fwd+bwd of the rasterizer on the un-deformed scene, same views, no SE3 stage"}
+        if args.impl == "reference":
+            def se3_only():
+                zero_grads(leaves)
+                y = _ref_deform(leaves, args)
+                y.backward(grad_y)
+            grad_y = torch.randn_like(leaves["means3D"])
+            t_se3 = timed(se3_only, nb)
+            breakdown["se3_graph_ms_per_view"] = round(t_se3, 4)
+            breakdown["what"] += "; se3_graph = torch exp_se3 + apply recipe fwd+bwd (scene/rigid_body.py op graph)"
+        if world > 1:
+            torch.distributed.barrier()
+
     # ---------------- end-to-end: host buffers in, loss out ----------------
     # Every step copies its own inputs from pinned host memory (264 MB of parameters + twists)
     # and reads its loss back.  As any input pipeline would, the copy for step i+1 is issued on
@@ -447,9 +594,10 @@ def main():
         leaves = t_leaves
 
     # ---------------- per-kernel profile (ours) -> roofline ----------------
-    roofline, kernels, counters = None, None, None
+    roofline, roofline_hbm, kernels, counters = None, None, None, None
+    if args.impl == "reference" and rank == 0:
+        counters = counters_reference(leaves, cams[-1], bg, args)
     if args.impl == "ours" and rank == 0:
-        from diff_gaussian_rasterization import _RasterizeGaussians
         rt.profile_enable(True)
         zero_grads(leaves)
         n_streams, args.streams = args.streams, 1       # kernels timed one at a time, not overlapping another view's
@@ -458,9 +606,9 @@ def main():
         torch.cuda.synchronize()
         prof = rt.profile_dump()
         rt.profile_enable(False)
-        R = getattr(_RasterizeGaussians, "last_num_rendered", 0)
-        tiles = ((args.W + 15) // 16) * ((args.H + 15) // 16)
-        passes = (32 + max(tiles, 1).bit_length() + 7) // 8
+        counters = counters_ours(leaves, cams[-1], bg, args)
+        R = counters["R"]
+        tiles = counters["tiles"]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -468,19 +616,20 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        twist_bytes = 28.0 if args.body_id is None else 4.0
         alg = {  # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x units per launch; R = last view's)
-            "preprocess_fwd": 316.0 * args.P,
-            "preprocess_bwd": 572.0 * args.P,
-            "depth_sort_onesweep_pass": 16.0 * args.P,     # depth order of the Gaussians: (u32 key, u32 id), 4 passes
+            "preprocess_fwd": (288.0 + twist_bytes) * args.P,
+            "preprocess_bwd": (516.0 + 2 * twist_bytes) * args.P,
+            "depth_sort_onesweep_pass": 16.0 * args.P,     # depth order of the Gaussians: (u32 key, u32 id)
             # radix fallback path (GSR_BINNING_RADIX=1)
             "duplicate_with_keys": 8.0 * R + 28.0 * args.P,
             "tile_sort_onesweep_pass": 16.0 * R,
             "tile_ranges": 4.0 * R + 8.0 * tiles,
         }
         # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload
-        # (profiles/r01_ncu_full_metrics.csv); only valid for P = 1 M @ 1920x1080, SH 3, per-Gaussian twists
-        ncu_traffic = {"preprocess_bwd": 677.3e6, "preprocess_fwd": 274.4e6}
-        default_workload = (args.P, args.W, args.H) == (1000000, 1920, 1080)
+        # (profiles/): only valid for P = 1 M @ 1920x1080, SH 3, per-Gaussian twists
+        ncu_traffic = NCU_TRAFFIC
+        default_workload = (args.P, args.W, args.H, args.bodies) == (1000000, 1920, 1080, False)
         kernels = {}
         for name, (cnt, tot) in prof.items():
             avg = tot / max(cnt, 1)
@@ -492,7 +641,7 @@ def main():
         # the whole binning stage against the reference scheme's traffic model (12 B/dup
         # duplicate + 152 B/dup 6-pass pair sort + 8 B/dup ranges); an implementation that moves fewer bytes
         # reads above what HBM could deliver to that scheme
-        bin_names = ("scan_block_sums", "sort_scan_hist", "depth_sort_onesweep_pass", "gather_rects", "tile_count",
+        bin_names = ("scan_block_sums", "sort_scan_hist", "depth_sort_onesweep_pass", "depth_sort_pass", "gather_rects", "tile_count",
                      "tile_sweep_count", "tile_column_scan", "tile_base_scan", "tile_scatter", "tile_sweep_scatter",
                      "sorted_block_sums", "duplicate_with_keys", "tile_sort_onesweep_pass", "tile_ranges")
         bin_ms = sum(kernels[n]["total_ms"] for n in bin_names if n in kernels) / max(len(cams), 1)
@@ -505,12 +654,34 @@ def main():
         dom = max(hbm_kernels, key=lambda n: kernels[n]["total_ms"]) if hbm_kernels else None
         if dom:
             a = alg[dom] / kernels[dom]["avg_ms"] / 1e6
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(a / peak, 4),
-                        "traffic": ncu_traffic.get(dom) if default_workload else None, "peak_source": peak_src,
-                        "note": "dominant HBM-bound kernel; achieved = 572 B x P / CUDA-event time; the blend kernels "
-                                "(largest time share) are instruction-issue / FMA-pipe bound (DRAM < 2 %), see `kernels` and profiles/"}
-        counters = {"num_rendered_last_view": R, "sort_passes": passes, "tiles": tiles}
+            roofline_hbm = {"kernel": dom, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(a / peak, 4),
+                            "traffic": ncu_traffic.get(dom) if default_workload else None, "peak_source": peak_src,
+                            "note": "largest HBM-bound kernel; achieved = SURVEY 8d bytes x P / CUDA-event time"}
+        # The time-dominant kernel is the blend backward: FP32-issue bound, not HBM or tensor bound (north_star: "FP32-pipe
+        # utilisation for blend").  Roofline per SURVEY 8d: the reference's SASS spends 72 FP32-pipe instructions per BLENDED
+        # (pixel, Gaussian) pair in the backward (28 in the forward); peak = 148 SMs x 128 FP32 lanes x SM clock thread-
+        # instructions/s at the clock sampled during the timed region.
+        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        fp32_peak = 148 * 128 * sm_mhz * 1e6
+        for kname, per_pair in (("blend_bwd", 72.0), ("blend_fwd", 28.0)):
+            if kname in kernels and kernels[kname]["avg_ms"] > 0:
+                ach = per_pair * counters["pairs_blended"] / (kernels[kname]["avg_ms"] * 1e-3)
+                kernels[kname]["alg_thread_instr_per_s"] = ach
+                kernels[kname]["frac_of_fp32_issue_peak"] = round(ach / fp32_peak, 4)
+        if "blend_bwd" in kernels and "frac_of_fp32_issue_peak" in kernels["blend_bwd"]:
+            ach = kernels["blend_bwd"]["alg_thread_instr_per_s"]
+            roofline = {"kernel": "blend_bwd", "bound": "fp32-issue", "achieved": round(ach / 1e12, 3), "peak": round(fp32_peak / 1e12, 3),
+                        "unit": "T thread-instr/s", "frac": round(ach / fp32_peak, 4),
+                        "traffic": ncu_traffic.get("blend_bwd") if default_workload else None,
+                        "peak_source": "148 SM x 128 lanes x %.0f MHz (clock sampled during the timed region)" % sm_mhz,
+                        "note": "time-dominant kernel (share = %.0f %% of the kernel sum); algorithmic work = 72 FP32 instr (SURVEY 8d, the "
+                                "reference's own SASS count) x %d blended pairs of this view; DRAM traffic of the kernel is < 2 %% of HBM peak. "
+                                "`roofline_hbm` is the largest HBM-bound kernel."
+                                % (100.0 * kernels["blend_bwd"]["total_ms"] / max(1e-9, sum(v["total_ms"] for n, v in kernels.items() if n != "binning_stage")),
+                                   counters["pairs_blended"])}
+        else:
+            roofline = roofline_hbm
 
     if rank != 0:
         if world > 1:
@@ -531,8 +702,8 @@ def main():
         "dtype": "f32",
         "data": "synthetic",
         "impl": args.impl,
-        "config": {"workload": "C2: %d Gaussians, SH degree 3, %dx%d, SE3 exp-map deform + rasterize fwd+bwd; "
-                               "%d views/GPU/step on a camera circle (C5's 64 cameras at 8 GPUs)" % (args.P, args.W, args.H, args.views),
+        "config": {"workload": "%s; %d views/GPU/step on a camera circle (C5's 64 cameras at 8 GPUs)" % (cfg["what"], args.views),
+                   "name": args.config,
                    "P": args.P, "width": args.W, "height": args.H, "views_per_gpu_per_step": args.views, "streams": args.streams,
                    "parallelism": "view-parallel x%d, per-Gaussian grad all-reduce (NCCL)" % world if world > 1 else "single GPU",
                    "l2": "inputs (264 MB params+twists, 85 MB geometry state, 190 MB keys) exceed the 126 MB L2 every view"},
@@ -542,16 +713,19 @@ def main():
     }
     if train is not None:
         out["train_step"] = train
+    out["breakdown"] = breakdown
+    out["counters"] = counters
     if args.impl == "ours":
         out["roofline"] = roofline
+        out["roofline_hbm"] = roofline_hbm
         out["kernels"] = kernels
-        out["counters"] = counters
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:
         try:
             out["cpu_baseline"] = cpu_baseline()
         except Exception as ex:  # pragma: no cover
             out["cpu_baseline"] = {"error": repr(ex)}
     if args.impl == "reference":
+        out["reference_breakdown"] = breakdown
         out["reference_arm"] = ("reference CUDA rasterizer (oracle/_ref, sm_100, unmodified sources) + torch-CUDA "
                                 "rigid_body op graph; the reference's torch-CPU deformation is `cpu_baseline`")
     print(json.dumps(out))

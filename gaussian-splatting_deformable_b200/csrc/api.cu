@@ -260,10 +260,24 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* mean
     a.rects = reinterpret_cast<uint2*>(ws + L.rects);
     // num_rendered accumulates in a spare word of the (zeroed) sort state: tickets are words [0, 8), the error
     // flag is word 63, words 61 and 62 serve the forward (tile-scan ticket, num_rendered)
+    // (word 60: prefiltered violation flag, read back together with num_rendered)
     uint32_t* d_total = a.depth_hist + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 62;
     a.total = d_total;
+    a.prefiltered = view->prefiltered ? 1 : 0;
+    a.flags = a.depth_hist + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 60;
     GSR_CHECK(cudaMemsetAsync(ws + L.dsort_temp, 0, L.dsort_temp_bytes, stream));
     if (int rc = gsr_launch_preprocess_fwd(a, v, stream)) return rc;
+    if (a.prefiltered) {
+        // rare path: one more 4-byte read-back before the sync
+        static thread_local uint32_t h_flags;
+        h_flags = 0;
+        GSR_CHECK(cudaMemcpyAsync(&h_flags, a.flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GSR_CHECK(cudaMemcpyAsync(host_num_rendered, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GSR_CHECK(cudaStreamSynchronize(stream));
+        if (h_flags & 1u)
+            return gsr_set_error_msg(-4, "Point is filtered although prefiltered is set. This shouldn't happen!");
+        return 0;
+    }
     GSR_CHECK(cudaMemcpyAsync(host_num_rendered, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GSR_CHECK(cudaStreamSynchronize(stream));
     return 0;

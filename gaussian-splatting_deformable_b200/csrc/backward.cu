@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256, MINB) preprocess_bwd_kernel(PreprocessBwd
             }
         }
         if (a.dL_dscales && !(acc & GSR_ACC_SCALES)) { a.dL_dscales[3 * idx] = 0.0f; a.dL_dscales[3 * idx + 1] = 0.0f; a.dL_dscales[3 * idx + 2] = 0.0f; }
-        if (a.dL_drots && !(acc & GSR_ACC_ROTS)) reinterpret_cast<float4*>(a.dL_drots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.dL_drots && !(acc & GSR_ACC_ROTS)) st_rec4(a.dL_drots, idx, make_float4(0.f, 0.f, 0.f, 0.f), false);
         if (a.dL_dtwist_S && a.deform_mode == GSR_DEFORM_PER_GAUSSIAN && !(acc & GSR_ACC_TWIST)) {
 #pragma unroll
             for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] = 0.0f;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256, MINB) preprocess_bwd_kernel(PreprocessBwd
             for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_precomp[6 * (size_t)idx + k];
         } else {
             s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-            q = reinterpret_cast<const float4*>(a.rotations)[idx];
+            q = ld_rec4(a.rotations, idx);
         }
         const int deg = v.sh_degree;
         float shv[48];
@@ -402,9 +402,7 @@ __global__ void __launch_bounds__(256, MINB) preprocess_bwd_kernel(PreprocessBwd
             for (int k = 0; k < 3; k++) emit(a.dL_dscales + 3 * idx + k, dscale[k], acc & GSR_ACC_SCALES);
         }
         if (a.dL_drots) {
-            float4* dr4 = reinterpret_cast<float4*>(a.dL_drots) + idx;
-            const float4 o = make_float4(drot[0], drot[1], drot[2], drot[3]);
-            if (acc & GSR_ACC_ROTS) atomicAdd(dr4, o); else *dr4 = o;
+            st_rec4(a.dL_drots, idx, make_float4(drot[0], drot[1], drot[2], drot[3]), (acc & GSR_ACC_ROTS) != 0);
         }
         if (a.dL_dtwist_S && a.deform_mode != GSR_DEFORM_NONE) {
             if (a.deform_mode == GSR_DEFORM_PER_GAUSSIAN) {

@@ -97,6 +97,25 @@ __device__ __forceinline__ void st256(float* p, const float* v) {
                  "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 
+// [P,4] records (quaternions and their gradients) move as one 128-bit access when the array is
+// 16-byte aligned and as four scalars otherwise: the caller's tensors may be views into a packed
+// flat buffer (fused_adam.FusedAdam / view_parallel.FlatGradBuffer) at any 4-byte offset.
+__device__ __forceinline__ float4 ld_rec4(const float* base, size_t idx) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) return reinterpret_cast<const float4*>(base)[idx];
+    const float* p = base + 4 * idx;
+    return make_float4(p[0], p[1], p[2], p[3]);
+}
+__device__ __forceinline__ void st_rec4(float* base, size_t idx, float4 o, bool accumulate) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        float4* d = reinterpret_cast<float4*>(base) + idx;
+        if (accumulate) atomicAdd(d, o); else *d = o;
+    } else {
+        float* p = base + 4 * idx;
+        if (accumulate) { atomicAdd(p, o.x); atomicAdd(p + 1, o.y); atomicAdd(p + 2, o.z); atomicAdd(p + 3, o.w); }
+        else { p[0] = o.x; p[1] = o.y; p[2] = o.z; p[3] = o.w; }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // SE3 exponential map applied to a point (closed form of rigid_body.exp_se3
 // followed by y = (T [x;1])[:3]):

@@ -39,6 +39,8 @@ struct PreprocessArgs {
     uint32_t* depth_vals;        // [P] = idx (payload of the depth sort)
     uint32_t* depth_hist;        // [4][256] digit histograms of depth_keys (pre-zeroed), accumulated here
     uint32_t* total;             // running sum of tiles_touched = num_rendered (pre-zeroed; one atomic per block)
+    int prefiltered;             // GaussianRasterizationSettings.prefiltered: a culled point is an error (auxiliary.h:156-160)
+    uint32_t* flags;             // bit 0 raised when prefiltered is set and a point fails the near-plane test
     uint2* rects;                // [P] tile rect (rmin.x | rmin.y << 16, rmax.x | rmax.y << 16); (0,0) when nothing is emitted
 };
 

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
             for (int k = 0; k < 6; k++) cov6[k] = a.cov3D_precomp[6 * (size_t)idx + k];
         } else {
             s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-            q = reinterpret_cast<const float4*>(a.rotations)[idx];
+            q = ld_rec4(a.rotations, idx);
         }
         const float op = a.opacities[idx];
         // ---- (2) geometry ----
@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
         const float depth = xform_row(v.view, 2, p);
         SplatGeom g;
         g.ok = false;
+        // auxiliary.h:154-160: with `prefiltered` the caller promises that no point fails this test; the reference
+        // printf()s and __trap()s (killing the context).  Here the violation raises a flag that the host turns into
+        // the same message as an error return, and the context survives.
+        if (a.prefiltered && !(depth > GSR_NEAR)) atomicOr(a.flags, 1u);
         if (depth > GSR_NEAR) {
             if (!a.cov3D_precomp) cov3d_exact(s, v.scale_modifier, q, cov6);
             g = splat_geometry_exact(p, cov6, v);

@@ -80,6 +80,7 @@ def rasterize_gaussians(
     se3_theta=None,
     body_id=None,
     accumulate_grads=None,
+    aux=None,
 ):
     return _RasterizeGaussians.apply(
         means3D,
@@ -95,10 +96,26 @@ def rasterize_gaussians(
         se3_theta,
         body_id,
         accumulate_grads,
+        aux,
     )
 
 
-_BUCKET = 64 << 20
+def cpu_deep_copy_tuple(input_tuple):
+    # diff_gaussian_rasterization/__init__.py:17-19
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+def _bucket(nbytes):
+    """Binning workspace size for `nbytes` of need: num_rendered differs from view to view, and exact sizes make the
+    caching allocator split and re-cudaMalloc blocks (milliseconds of stall once several streams' pools fragment).
+    Round up to a power of two below 64 MB (small scenes stay small) and to a multiple of 64 MB above."""
+    if nbytes >= (64 << 20):
+        return ((nbytes + (64 << 20) - 1) // (64 << 20)) * (64 << 20)
+    b = 1 << 20
+    while b < nbytes:
+        b <<= 1
+    return b
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -118,8 +135,34 @@ class _RasterizeGaussians(torch.autograd.Function):
         se3_theta=None,
         body_id=None,
         accumulate_grads=None,
+        aux=None,
     ):
         lib = _rt.load()
+        debug = bool(raster_settings.debug)
+        if debug:
+            # reference :83-90: copy the arguments before they can be corrupted; dumped if the forward fails
+            cpu_args = cpu_deep_copy_tuple((raster_settings.bg, means3D, colors_precomp, opacities, scales, rotations,
+                                            raster_settings.scale_modifier, cov3Ds_precomp, raster_settings.viewmatrix,
+                                            raster_settings.projmatrix, raster_settings.tanfovx, raster_settings.tanfovy,
+                                            raster_settings.image_height, raster_settings.image_width, sh,
+                                            raster_settings.sh_degree, raster_settings.campos, raster_settings.prefiltered,
+                                            raster_settings.debug, se3_S, se3_theta, body_id))
+            try:
+                out = _RasterizeGaussians._forward(ctx, lib, means3D, means2D, sh, colors_precomp, opacities, scales,
+                                                   rotations, cov3Ds_precomp, raster_settings, se3_S, se3_theta, body_id,
+                                                   accumulate_grads, aux)
+                torch.cuda.synchronize(means3D.device)    # CHECK_CUDA(.., debug) syncs after every launch (auxiliary.h:166-172)
+                return out
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        return _RasterizeGaussians._forward(ctx, lib, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                            cov3Ds_precomp, raster_settings, se3_S, se3_theta, body_id, accumulate_grads, aux)
+
+    @staticmethod
+    def _forward(ctx, lib, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                 raster_settings, se3_S, se3_theta, body_id, accumulate_grads, aux):
         if means3D.dim() != 2 or means3D.shape[1] != 3:
             # rasterize_points.cu:57-59
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -151,17 +194,12 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _rt.check(lib.gsr_forward_preprocess(
                     view, P, M, _rt.ptr(means3D_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c),
                     _rt.ptr(sh_c), _rt.ptr(cov_c), _rt.ptr(colors_c), dstruct, _rt.ptr(means_def),
-                    _rt.ptr(radii), _rt.ptr(geom), geom.numel(), mailbox.data_ptr(),
-                    1 if raster_settings.debug else 0, stream))
+                    _rt.ptr(radii), _rt.ptr(geom), geom.numel(), mailbox.data_ptr(), 0, stream))
                 num_rendered = int(mailbox.item()) & 0xFFFFFFFF
-            # num_rendered differs from view to view: round the workspace up to a 64 MB bucket so that the caching
-            # allocator can hand the same block to every view (exact sizes make it split and re-cudaMalloc blocks,
-            # which stalls the GPU for milliseconds once several streams' pools fragment)
             nbytes = lib.gsr_binning_bytes(num_rendered, W, H)
-            binning = torch.empty(((nbytes + _BUCKET - 1) // _BUCKET) * _BUCKET, dtype=torch.uint8, device=dev)
+            binning = torch.empty(_bucket(nbytes), dtype=torch.uint8, device=dev)
             _rt.check(lib.gsr_forward_render(view, P, num_rendered, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
-                                             binning.numel(), _rt.ptr(img), _rt.ptr(color),
-                                             1 if raster_settings.debug else 0, stream))
+                                             binning.numel(), _rt.ptr(img), _rt.ptr(color), 0, stream))
 
         acc = dict(accumulate_grads) if accumulate_grads else {}
         shapes = {"means3D": means3D, "opacities": opacities, "shs": sh, "scales": scales, "rotations": rotations,
@@ -173,6 +211,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             if (not buf.is_cuda) or buf.dtype != torch.float32 or not buf.is_contiguous() or buf.numel() != src.numel():
                 raise _rt.GsrError("accumulate_grads[%r] must be a contiguous CUDA float32 tensor of %d elements"
                                    % (k, src.numel()))
+            if src.requires_grad and not src.is_leaf:
+                # autograd receives None for an accumulated input: a non-leaf (e.g. scales = exp(_scaling)) would
+                # silently lose the gradient of whatever produced it
+                raise _rt.GsrError("accumulate_grads[%r]: the input is not a leaf tensor; accumulate only into the "
+                                   "gradients of leaves (pass the activated tensor without accumulate_grads instead)" % k)
         if ("se3_S" in acc) != ("se3_theta" in acc):
             raise _rt.GsrError("accumulate_grads: give both se3_S and se3_theta or neither")
         ctx.acc = acc
@@ -193,12 +236,28 @@ class _RasterizeGaussians(torch.autograd.Function):
             deform.S if deform.S is not None else none, deform.theta if deform.theta is not None else none,
             deform.body_id if deform.body_id is not None else none)
         ctx.mark_non_differentiable(radii)
-        _RasterizeGaussians.last_deformed_means = means_def
-        _RasterizeGaussians.last_num_rendered = num_rendered
+        if aux is not None:          # per-call results for the caller (no class-level state: rasterizers may interleave)
+            aux["deformed_means"] = means_def
+            aux["num_rendered"] = num_rendered
         return color, radii
 
     @staticmethod
     def backward(ctx, grad_out_color, _):
+        if ctx.raster_settings.debug:
+            # reference :132-139
+            cpu_args = cpu_deep_copy_tuple((grad_out_color,) + tuple(ctx.saved_tensors))
+            try:
+                out = _RasterizeGaussians._backward(ctx, grad_out_color)
+                torch.cuda.synchronize(grad_out_color.device)
+                return out
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        return _RasterizeGaussians._backward(ctx, grad_out_color)
+
+    @staticmethod
+    def _backward(ctx, grad_out_color):
         lib = _rt.load()
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img,
          means_def, tw_S, tw_theta, body_id) = ctx.saved_tensors
@@ -264,6 +323,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             ret("se3_theta", grad_theta),
             None,
             None,
+            None,
         )
         return grads
 
@@ -287,7 +347,8 @@ class GaussianRasterizer(nn.Module):
     def __init__(self, raster_settings):
         super().__init__()
         self.raster_settings = raster_settings
-        self.deformed_means = None
+        self.deformed_means = None       # of this rasterizer's last forward with se3_S/se3_theta
+        self.num_rendered = 0            # of this rasterizer's last forward
 
     def markVisible(self, positions):
         # Mark visible points (based on frustum culling for camera) with a boolean
@@ -322,6 +383,7 @@ class GaussianRasterizer(nn.Module):
         if body_id is not None and se3_S is None:
             raise Exception('body_id needs se3_S/se3_theta (one twist per rigid body)!')
 
+        aux = {}
         out = rasterize_gaussians(
             means3D,
             means2D,
@@ -336,6 +398,8 @@ class GaussianRasterizer(nn.Module):
             se3_theta,
             body_id,
             accumulate_grads,
+            aux,
         )
-        self.deformed_means = _RasterizeGaussians.last_deformed_means
+        self.deformed_means = aux.get("deformed_means")
+        self.num_rendered = aux.get("num_rendered", 0)
         return out

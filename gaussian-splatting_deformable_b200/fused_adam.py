@@ -60,23 +60,34 @@ class FusedAdam:
                 raise _rt.GsrError("FusedAdam: parameters must be CUDA float32 tensors (no CPU fallback)")
         self._params = flat_params
         dev = flat_params[0].device
-        total = sum(p.numel() for p in flat_params)
-        pad = (-total) % 4
-        self.flat_params = torch.empty(total + pad, dtype=torch.float32, device=dev)
-        off = 0
+        # same 32-byte-aligned layout as the gradient buffer (view_parallel.flat_layout): the Adam kernel walks all four
+        # flat buffers with one index, and the rasterizer's vector accesses need aligned tensor starts whatever P is
+        offs, total = view_parallel.flat_layout(flat_params)
+        self.flat_params = torch.zeros(total, dtype=torch.float32, device=dev)
         self._begin = []
+        it = iter(offs)
         for g in self.param_groups:
-            self._begin.append(off)
+            first = True
             for p in g["params"]:
+                off = next(it)
+                if first:
+                    self._begin.append(off)
+                    first = False
                 n = p.numel()
                 self.flat_params[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_params[off:off + n].view_as(p)
-                off += n
-        self._begin.append(off)
+        self._begin.append(total)
         self.grads = view_parallel.FlatGradBuffer(flat_params)       # p.grad = views of grads.flat
         self.exp_avg = torch.zeros_like(self.grads.flat)
         self.exp_avg_sq = torch.zeros_like(self.grads.flat)
-        self.state_step = 0
+        # torch.optim.Adam keeps one step count per parameter and skips parameters whose .grad is None (a dormant group,
+        # e.g. the deformation network before its warm-up ends, keeps its moments and bias correction).  Gradients here
+        # always exist (views of the flat buffer), so dormancy is stated explicitly: step(skip=[group names]).
+        self._steps = [0] * len(self.param_groups)
+
+    @property
+    def state_step(self):
+        return max(self._steps) if self._steps else 0
 
     # -- torch.optim surface the reference uses --
     def zero_grad(self, set_to_none=True):
@@ -84,14 +95,20 @@ class FusedAdam:
         # they are zeroed in place and stay attached (accumulate_grads / the all-reduce use the same memory)
         self.grads.zero_()
 
-    def step(self):
+    def step(self, skip=()):
+        """One Adam step on every group except those named (or indexed) in `skip`: a skipped group is what
+        torch.optim.Adam does for parameters whose .grad is None - values, moments and step count untouched."""
         lib = _rt.load()
-        self.state_step += 1
-        t = self.state_step
         n = len(self.param_groups)
         begin = (ctypes.c_ulonglong * (n + 1))(*self._begin)
         ss, bc, b1s, b2s, es = [], [], [], [], []
-        for g in self.param_groups:
+        for i, g in enumerate(self.param_groups):
+            if i in skip or g.get("name") in skip:
+                # lr 0 and betas 1: m = lerp(m, g, 0), v = 1 v + 0 g g, p -= 0 -> the kernel leaves the group as it is
+                ss.append(0.0); bc.append(1.0); b1s.append(1.0); b2s.append(1.0); es.append(g["eps"])
+                continue
+            self._steps[i] += 1
+            t = self._steps[i]
             b1, b2 = g["betas"]
             bias_correction1 = 1 - b1 ** t
             bias_correction2 = 1 - b2 ** t
@@ -109,27 +126,32 @@ class FusedAdam:
     # -- optimizer-state surgery of densification (scene/gaussian_model.py:1027-1100) on the flat buffers --
     def _group_views(self, buf):
         """Per group: list of views of `buf` shaped like the group's parameters."""
-        out, off = [], 0
+        out = []
+        it = iter(view_parallel.flat_layout(self._params)[0])
         for g in self.param_groups:
             vs = []
             for p in g["params"]:
-                n = p.numel()
-                vs.append(buf[off:off + n].view_as(p))
-                off += n
+                off = next(it)
+                vs.append(buf[off:off + p.numel()].view_as(p))
             out.append(vs)
         return out
 
     def _rebuild(self, new_p, new_m, new_v):
         """Re-home every parameter (same Python objects, possibly new shapes) into fresh flat buffers."""
         dev = self.flat_params.device
-        total = sum(t.numel() for grp in new_p for t in grp)
-        flat_p = torch.empty(total + ((-total) % 4), dtype=torch.float32, device=dev)
+        offs, total = view_parallel.flat_layout([t for grp in new_p for t in grp])
+        flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
-        off, begin, params = 0, [], []
+        begin, params = [], []
+        it = iter(offs)
         for g, ps, ms, vs in zip(self.param_groups, new_p, new_m, new_v):
-            begin.append(off)
+            first = True
             for p, val, m, v in zip(g["params"], ps, ms, vs):
+                off = next(it)
+                if first:
+                    begin.append(off)
+                    first = False
                 n = val.numel()
                 flat_p[off:off + n].copy_(val.reshape(-1))
                 flat_m[off:off + n].copy_(m.reshape(-1))
@@ -137,8 +159,7 @@ class FusedAdam:
                 p.grad = None
                 p.data = flat_p[off:off + n].view(val.shape)
                 params.append(p)
-                off += n
-        begin.append(off)
+        begin.append(total)
         self.flat_params, self.exp_avg, self.exp_avg_sq, self._begin, self._params = flat_p, flat_m, flat_v, begin, params
         self.grads = view_parallel.FlatGradBuffer(params)
         return {g.get("name", str(i)): g["params"][0] for i, g in enumerate(self.param_groups) if len(g["params"]) == 1}
@@ -182,13 +203,59 @@ class FusedAdam:
                 P[i], M[i], V[i] = [t], [torch.zeros_like(t)], [torch.zeros_like(t)]
         return self._rebuild(P, M, V)
 
+    # -- checkpoint surface: torch.optim.Adam's own state_dict layout (the reference saves `optimizer.state_dict()` in
+    # capture() and restores it in restore(), scene/gaussian_model.py:686-728), so chkpnt*.pth files go both ways --
     def state_dict(self):
-        return {"step": self.state_step, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+        state, packed, idx = {}, [], 0
+        M, V = self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        for gi, g in enumerate(self.param_groups):
+            ids = []
+            for m, v in zip(M[gi], V[gi]):
+                if self._steps[gi] > 0:         # torch creates a parameter's state at its first step
+                    state[idx] = {"step": torch.tensor(float(self._steps[gi])), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+                ids.append(idx)
+                idx += 1
+            d = {k: v for k, v in g.items() if k != "params"}
+            for k, v in (("weight_decay", 0), ("amsgrad", False), ("maximize", False), ("foreach", None), ("capturable", False),
+                         ("differentiable", False), ("fused", None), ("decoupled_weight_decay", False)):
+                d.setdefault(k, v)
+            d["params"] = ids
+            packed.append(d)
+        return {"state": state, "param_groups": packed}
 
     def load_state_dict(self, sd):
-        self.state_step = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+        if "state" not in sd:                   # round-1 private layout: one global step + the flat moment buffers
+            if sd["exp_avg"].numel() != self.exp_avg.numel() or sd["exp_avg_sq"].numel() != self.exp_avg_sq.numel():
+                raise ValueError("load_state_dict: flat moment buffers have %d elements, this optimizer %d"
+                                 % (sd["exp_avg"].numel(), self.exp_avg.numel()))
+            self._steps = [int(sd["step"])] * len(self.param_groups)
+            self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            for g, s_ in zip(self.param_groups, sd["param_groups"]):
+                g.update({k: v for k, v in s_.items() if k != "params"})
+            return
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        M, V = self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        for gi, (g, s_) in enumerate(zip(self.param_groups, groups)):
+            if len(s_["params"]) != len(g["params"]):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            steps = set()
+            for pid, p, m, v in zip(s_["params"], g["params"], M[gi], V[gi]):
+                st = sd["state"].get(pid)
+                if st is None:
+                    m.zero_(); v.zero_(); steps.add(0)
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape) or tuple(st["exp_avg_sq"].shape) != tuple(p.shape):
+                    raise ValueError("load_state_dict: moments of parameter %d have shape %s, the parameter %s"
+                                     % (pid, tuple(st["exp_avg"].shape), tuple(p.shape)))
+                m.copy_(st["exp_avg"]); v.copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+            if len(steps) > 1:
+                raise ValueError("load_state_dict: parameters of group %r carry different step counts %s; FusedAdam keeps "
+                                 "one step count per group" % (g.get("name", gi), sorted(steps)))
+            self._steps[gi] = steps.pop() if steps else 0
+            g.update({k: v for k, v in s_.items() if k not in ("params", "foreach", "capturable", "differentiable", "fused",
+                                                               "weight_decay", "amsgrad", "maximize", "decoupled_weight_decay")})
+            if s_.get("weight_decay", 0) or s_.get("amsgrad", False) or s_.get("maximize", False):
+                raise ValueError("FusedAdam implements plain Adam only (no weight decay / amsgrad / maximize)")

@@ -22,6 +22,21 @@ def partition_views(num_views, world_size, rank):
     return list(range(rank, num_views, world_size))
 
 
+ALIGN = 8        # every tensor of a flat buffer starts on a 32-byte boundary (8 floats): the kernels move quaternion
+                 # records as 128-bit and SH records as 256-bit accesses, and a packed layout would only be aligned
+                 # when the point count happens to be a multiple of 4 (it is not after a prune / densify)
+
+
+def flat_layout(params, align=ALIGN):
+    """Start offsets (in floats) of `params` laid out back to back with `align`-float alignment, and the total
+    length (itself a multiple of `align`).  Padding elements are never written: their gradients stay zero."""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offs, off
+
+
 class FlatGradBuffer:
     """Gradients of a set of leaf tensors laid out in ONE contiguous fp32 buffer.
 
@@ -31,14 +46,17 @@ class FlatGradBuffer:
 
     def __init__(self, params):
         self.params = list(params)
-        total = sum(p.numel() for p in self.params)
+        self.offsets, total = flat_layout(self.params)
         first = self.params[0]
         self.flat = torch.zeros(total, dtype=torch.float32, device=first.device)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        self._attach()
+
+    def _attach(self, only_if_replaced=False):
+        for p, off in zip(self.params, self.offsets):
+            g = self.flat[off:off + p.numel()].view_as(p)
+            if only_if_replaced and p.grad is not None and p.grad.data_ptr() == g.data_ptr():
+                continue
+            p.grad = g
 
     def rebind(self, params):
         """Attach the same flat buffer to a new set of parameter tensors of identical shapes (e.g. a step's freshly
@@ -47,22 +65,12 @@ class FlatGradBuffer:
         if [tuple(p.shape) for p in params] != [tuple(p.shape) for p in self.params]:
             raise ValueError("rebind: parameter shapes differ")
         self.params = params
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        self._attach()
         return self
 
     def zero_(self):
         self.flat.zero_()
-        off = 0
-        for p in self.params:          # re-attach: callers may have replaced .grad
-            n = p.numel()
-            g = self.flat[off:off + n].view_as(p)
-            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
-                p.grad = g
-            off += n
+        self._attach(only_if_replaced=True)      # re-attach: callers may have replaced .grad
 
     def all_reduce(self, group=None, average=False):
         """Sum (or average) the flat buffer over all ranks.  Returns bytes reduced."""

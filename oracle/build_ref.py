@@ -24,6 +24,12 @@ gcc 13 needs: `--pre-include cstdint` for
 rasterizer_impl.h:40-41 and `--pre-include cfloat` for simple_knn.cu:90,154.
 The module name is changed with -DTORCH_EXTENSION_NAME only (no source edit).
 
+It also STAGES (plain file copies, into the git-ignored oracle/_ref/py/ only - never into the tracked tree)
+the reference's Python modules that the contract tests drive unmodified on the GPU box, where /root/reference
+does not exist: gaussian_renderer/__init__.py (render()), scene/gaussian_model.py (GaussianModel and the
+deformation networks), scene/rigid_body.py, utils/*.py and the reference's own Python wrapper
+diff_gaussian_rasterization/__init__.py (bound to ref_dgr_C.so by oracle/ref_py.py).
+
 /root/reference exists only in the build container.  On the GPU box the
 prebuilt .so files (git-ignored, but shipped by gpurun) are used as they are.
 """
@@ -83,12 +89,37 @@ def _build(name, srcs, extra, objdir):
     return so
 
 
+STAGED_PY = [
+    ("gaussian_renderer/__init__.py", "gaussian_renderer/__init__.py"),
+    ("scene/gaussian_model.py", "scene/gaussian_model.py"),            # no scene/__init__.py: namespace package, so the
+    ("scene/rigid_body.py", "scene/rigid_body.py"),                    # dataset readers are never imported
+    ("utils/general_utils.py", "utils/general_utils.py"),
+    ("utils/graphics_utils.py", "utils/graphics_utils.py"),
+    ("utils/sh_utils.py", "utils/sh_utils.py"),
+    ("utils/system_utils.py", "utils/system_utils.py"),
+    ("utils/loss_utils.py", "utils/loss_utils.py"),
+    ("submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py",
+     "ref_dgr/diff_gaussian_rasterization/__init__.py"),
+]
+
+
+def stage_python():
+    """Copy the reference's Python modules needed by the contract tests into oracle/_ref/py (git-ignored)."""
+    import shutil
+    for src, dst in STAGED_PY:
+        d = os.path.join(OUT, "py", dst)
+        os.makedirs(os.path.dirname(d), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, src), d)
+    print("[oracle/_ref] staged %d reference Python modules under %s" % (len(STAGED_PY), os.path.join(OUT, "py")))
+
+
 def build(force=False):
     """Build both reference extensions if the reference tree is present."""
     if not os.path.isdir(DGR):
         print("[oracle/_ref] reference tree not present (%s); using prebuilt files" % REF)
         return False
     os.makedirs(OUT, exist_ok=True)
+    stage_python()
     dgr_so = os.path.join(OUT, "ref_dgr_C.so")
     knn_so = os.path.join(OUT, "ref_knn_C.so")
     if force or not os.path.exists(dgr_so):

@@ -25,6 +25,48 @@ def rel_to_max(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+# Gradient bar (BASELINE.json north_star: "gradients must agree within 1e-4 relative, since atomics are
+# nondeterministic").  Every element must satisfy  |a - b| <= GRAD_RTOL |b| + GRAD_ATOL max|b|  - a relative bound
+# with a floor of 1e-5 of the tensor's largest entry (both implementations sum thousands of fp32 terms of mixed sign
+# in unordered atomics, so an entry that cancels to ~0 carries the rounding of the terms, not of the result; the
+# reference differs from ITSELF by ~2e-6 of max from run to run, see profiles/r02_grad_error.json) - and the 99.9th
+# percentile of the per-row relative error (row = one Gaussian; floor 1e-3 of the largest row) must be <= 1e-4 too.
+GRAD_RTOL = 1e-4
+GRAD_ATOL = 1e-5
+GRAD_ROW_P999 = 1e-4
+_REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "grad_report.jsonl")
+
+
+def grad_stats(a, b):
+    """Error statistics of gradient `a` against reference `b`: elementwise and per row (row = first dimension)."""
+    a, b = a.detach().double(), b.detach().double().reshape(a.shape)
+    d = (a - b).abs()
+    bmax = float(b.abs().max()) + 1e-300
+    excess = d - (GRAD_RTOL * b.abs() + GRAD_ATOL * bmax)
+    rows = d.reshape(d.shape[0], -1).amax(1) if d.dim() > 0 and d.shape[0] > 0 else d.reshape(1)
+    brow = b.abs().reshape(b.shape[0], -1).amax(1) if b.dim() > 0 and b.shape[0] > 0 else b.abs().reshape(1)
+    rel_row = rows / (brow + 1e-3 * float(brow.max()) + 1e-300)
+    live = rel_row[brow > 0]
+    q = lambda t, p: float(torch.quantile(t[:: max(1, t.numel() // 4000000)], p)) if t.numel() else 0.0
+    return {"rel_to_max": float(d.max()) / bmax, "violations": int((excess > 0).sum()), "elements": d.numel(),
+            "worst_excess_of_max": float(excess.max()) / bmax if d.numel() else 0.0,
+            "row_rel_p50": q(live, 0.5), "row_rel_p99": q(live, 0.99), "row_rel_p999": q(live, 0.999),
+            "row_rel_max": float(live.max()) if live.numel() else 0.0}
+
+
+def assert_grad_close(a, b, what=""):
+    """The gradient bar above; the measured statistics are appended to gpurun_out/grad_report.jsonl when that
+    directory exists (they are summarised in profiles/)."""
+    st = grad_stats(a, b)
+    if os.path.isdir(os.path.dirname(_REPORT)):
+        import json
+        with open(_REPORT, "a") as f:
+            f.write(json.dumps(dict(what=what, **st)) + "\n")
+    assert st["violations"] == 0, (what, st)
+    assert st["row_rel_p999"] <= GRAD_ROW_P999, (what, st)
+    return st
+
+
 def make_view_settings(P, W, H, k=0, K=1, bg=(0.1, 0.2, 0.3), seed=0, scale_mult=1.0, sh_degree=3, scale_modifier=1.0):
     dev = "cuda"
     sc = synthetic.make_scene(P, seed=seed, device=dev, scale_mult=scale_mult)

@@ -191,7 +191,8 @@ def test_flat_grad_buffer_rebind_and_sequential_render_views():
     import view_parallel
     a = [torch.zeros(5, 3, requires_grad=True), torch.zeros(7, requires_grad=True)]
     buf = view_parallel.FlatGradBuffer(a)
-    assert buf.flat.numel() == 22 and a[1].grad.data_ptr() == buf.flat[15:].data_ptr()
+    # every tensor starts on a 32-byte boundary (8 floats): 15 -> 16, 7 -> 8
+    assert buf.offsets == [0, 16] and buf.flat.numel() == 24 and a[1].grad.data_ptr() == buf.flat[16:].data_ptr()
     a[0].grad += 2.0
     b = [torch.zeros(5, 3, requires_grad=True), torch.zeros(7, requires_grad=True)]
     buf.rebind(b)                                               # same memory, new owners, nothing cleared

@@ -1,0 +1,424 @@
+"""Contract-level parity (round 2): the reference's REAL render() and GaussianModel driven over both rasterizers,
+the largest BASELINE config, every compiled-in kernel variant, arbitrary point counts through the flat buffers,
+and the frozen error / debug conventions of the operator API."""
+import json
+import os
+import subprocess
+import sys
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-5
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ref():
+    from oracle import ref_driver
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return ref_driver
+
+
+def _ref_py():
+    from oracle import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref/py not staged (needs /root/reference at build time)")
+    return ref_py
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[3]: 6 M Gaussians at 3840x2160 (tile/sort-heavy stress), full size, against the reference
+# ---------------------------------------------------------------------------
+def test_c4_6m_gaussians_at_4k_vs_reference():
+    import synthetic
+    from _gpu_util import assert_grad_close, bits_equal, intermediates, make_view_settings, run_ours
+    rd = _ref()
+    P, W, H = 6000000, 3840, 2160
+    sc, cam, rs = make_view_settings(P, W, H, bg=(0, 0, 0))
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    f = rd.forward(rs, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+    R = f["num_rendered"]
+    assert 40000000 < R < (1 << 30)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    assert tiles == 32400
+    m = intermediates(rs, sc)
+    assert m["R"] == R
+    assert torch.equal(m["radii"], f["radii"])
+    g = rd.slice_geom(f["geom"], P)
+    vis = f["radii"] > 0
+    for k in ("depths", "means2D", "conic_opacity", "rgb"):
+        assert bits_equal(m[k][vis], g[k][vis]), k
+    b = rd.slice_binning(f["binning"], R)
+    assert torch.equal(m["keys_sorted"], b["point_list_keys"])           # tile keys + sort order, 47-bit keys
+    assert torch.equal(m["point_list"], b["point_list"])
+    im = rd.slice_img(f["img"], W, H)
+    assert torch.equal(m["ranges"], im["ranges"][:tiles])
+    assert torch.equal(m["n_contrib"], im["n_contrib"])
+    assert float((m["color"] - f["color"]).abs().max()) <= IMG_TOL
+    del m, g, b, im
+    bw = rd.backward(rs, f, grad, sc["means3D"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+    del f
+    torch.cuda.synchronize()
+    o = run_ours(rs, sc, grad)
+    for k in ("means3D", "opacities", "shs", "scales", "rotations"):
+        assert_grad_close(o["grads"][k], bw[k], "C4 6M@4K " + k)
+    assert_grad_close(o["means2D_grad"], bw["means2D"], "C4 6M@4K means2D")
+
+
+# ---------------------------------------------------------------------------
+# The render() contract (gaussian_renderer/__init__.py:20-195): the reference's own render() and GaussianModel,
+# unmodified, once over the reference rasterizer and once over the drop-in modules.
+# ---------------------------------------------------------------------------
+def _real_gaussian_model(gm, P, seed):
+    """A real scene.gaussian_model.GaussianModel filled the way create_from_pcd fills it (:807-832), with the
+    synthetic cloud's pre-activation values and a deformation network whose output heads are large enough to matter."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    pc = gm.GaussianModel(3)
+    xyz = (torch.rand((P, 3), generator=g) * 2.0 - 1.0) * 1.3
+    s0 = 0.25 * (2.6 ** 3 / P) ** (1.0 / 3.0) * 2.0
+    par = lambda t: torch.nn.Parameter(t.cuda().contiguous().requires_grad_(True))
+    pc._xyz = par(xyz)
+    pc._features_dc = par(torch.randn((P, 1, 3), generator=g))
+    pc._features_rest = par(0.2 * torch.randn((P, 15, 3), generator=g))
+    pc._scaling = par(math.log(s0) + 0.5 * torch.randn((P, 3), generator=g))
+    pc._rotation = par(torch.randn((P, 4), generator=g))
+    pc._opacity = par(2.0 * torch.randn((P, 1), generator=g))
+    pc.max_radii2D = torch.zeros(P, device="cuda")
+    pc.active_sh_degree = 3
+    torch.manual_seed(seed + 1)
+    pc.offset_model = gm.DirectTemporalNeRF().cuda()      # nn.Linear default init: offsets of order 0.1 on every head
+    return pc
+
+
+def _leaves(pc):
+    return [("xyz", pc._xyz), ("f_dc", pc._features_dc), ("f_rest", pc._features_rest), ("scaling", pc._scaling),
+            ("rotation", pc._rotation), ("opacity", pc._opacity)] + \
+        [("mlp." + n, p) for n, p in pc.offset_model.named_parameters()]
+
+
+@pytest.mark.parametrize("iteration,override", [(5000, False), (100, False), (5000, True)])
+def test_reference_render_contract_over_both_rasterizers(iteration, override):
+    import diff_gaussian_rasterization as ours
+    import synthetic
+    from _gpu_util import assert_grad_close
+    rp = _ref_py()
+    gm = rp.gaussian_model()
+    render_ref = rp.render_fn(rp.reference_rasterizer_module())
+    render_ours = rp.render_fn(ours)
+    assert render_ours.__globals__["GaussianRasterizer"] is ours.GaussianRasterizer
+    P, W, H = 60000, 640, 400
+    pc = _real_gaussian_model(gm, P, seed=3)
+    cam = synthetic.make_camera(3, 8, W, H, device="cuda")
+    cam.time = 0.37
+    pipe = SimpleNamespace(debug=False, convert_SHs_python=False, compute_cov3D_python=False)
+    bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    gimg = synthetic.make_image_grad(W, H, device="cuda")
+    oc = torch.rand(P, 3, device="cuda") if override else None
+    outs = []
+    for fn in (render_ref, render_ours):
+        for _, p in _leaves(pc):
+            p.grad = None
+        out = fn(cam, pc, pipe, bg, iteration=iteration, scaling_modifier=0.9, override_color=oc)
+        (out["render"] * gimg).sum().backward()
+        torch.cuda.synchronize()
+        grads = {n: (p.grad.clone() if p.grad is not None else None) for n, p in _leaves(pc)}
+        outs.append((out, grads, out["viewspace_points"].grad.clone()))
+    (a, ga, va), (b, gb, vb) = outs
+    # dict keys of gaussian_renderer/__init__.py:185-195
+    keys = ["render", "viewspace_points", "visibility_filter", "radii", "means3D", "means3D_ori", "rotations",
+            "means3D_offset", "opacities", "rot_offset"]
+    assert list(a.keys()) == keys and list(b.keys()) == keys
+    assert torch.equal(a["radii"], b["radii"]) and b["radii"].dtype == torch.int32
+    assert torch.equal(a["visibility_filter"], b["visibility_filter"]) and int(b["visibility_filter"].sum()) > P // 4
+    assert float((a["render"] - b["render"]).abs().max()) <= IMG_TOL
+    for k in ("means3D", "means3D_ori", "rotations", "means3D_offset", "opacities", "rot_offset"):
+        assert torch.equal(a[k], b[k]), k                     # produced by the same torch ops above the rasterizer
+    assert_grad_close(vb, va, "render() it=%d viewspace_points" % iteration)          # densification statistic (train.py:613)
+    for n in ga:
+        if ga[n] is None:
+            assert gb[n] is None, n
+            continue
+        assert_grad_close(gb[n], ga[n], "render() it=%d %s" % (iteration, n))
+
+
+def test_reference_render_python_cov_and_sh_paths():
+    """pipe.compute_cov3D_python / convert_SHs_python (gaussian_renderer/__init__.py:111-137): cov3D_precomp and
+    colors_precomp enter the rasterizer instead of scales/rotations/shs."""
+    import diff_gaussian_rasterization as ours
+    import synthetic
+    from _gpu_util import assert_grad_close
+    rp = _ref_py()
+    gm = rp.gaussian_model()
+    render_ref = rp.render_fn(rp.reference_rasterizer_module())
+    render_ours = rp.render_fn(ours)
+    P, W, H = 30000, 400, 300
+    pc = _real_gaussian_model(gm, P, seed=5)
+    cam = synthetic.make_camera(1, 8, W, H, device="cuda")
+    pipe = SimpleNamespace(debug=False, convert_SHs_python=True, compute_cov3D_python=True)
+    bg = torch.zeros(3, device="cuda")
+    gimg = synthetic.make_image_grad(W, H, device="cuda")
+    res = []
+    for fn in (render_ref, render_ours):
+        for _, p in _leaves(pc):
+            p.grad = None
+        out = fn(cam, pc, pipe, bg, iteration=100)
+        (out["render"] * gimg).sum().backward()
+        res.append((out["render"].detach(), out["radii"], {n: p.grad.clone() for n, p in _leaves(pc) if p.grad is not None}))
+    assert torch.equal(res[0][1], res[1][1])
+    assert float((res[0][0] - res[1][0]).abs().max()) <= IMG_TOL
+    for n in ("xyz", "f_dc", "f_rest", "scaling", "rotation", "opacity"):
+        assert_grad_close(res[1][2][n], res[0][2][n], "render() python paths " + n)
+
+
+# ---------------------------------------------------------------------------
+# Every compiled-in kernel variant (selected by environment variables read once per process) in its own process
+# ---------------------------------------------------------------------------
+VARIANTS = [
+    {"GSR_BINNING_RADIX": "1"},                                            # radix path for the tile lists
+    {"GSR_BLEND_FWD_V": "1", "GSR_BLEND_BWD_V": "1"},                      # first-generation blend kernels
+    {"GSR_BLEND_FWD_V": "1", "GSR_BLEND_BWD_V": "1", "GSR_BLEND_TMA": "1"},  # ... with TMA (cp.async.bulk) staging
+    {"GSR_BLEND_FWD_V": "1", "GSR_BLEND_BWD_V": "1", "GSR_FWD_PPT": "1", "GSR_BWD_PPT": "2"},
+    {"GSR_SWEEP_COUNT_V": "1", "GSR_SWEEP_SCATTER_V": "1"},               # striped sweep kernels (also the >51200-tile path)
+    {"GSR_FWD_NP": "2", "GSR_BWD_NP": "2"},
+    {"GSR_FWD_STRAIGHT": "0", "GSR_BWD_STRAIGHT": "0", "GSR_BWD_SMEM_RED": "0"},
+]
+
+
+@pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+def test_kernel_variant_in_subprocess(env):
+    _ref()
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_variant_check.py")], env=e, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "VARIANT_OK" in r.stdout
+
+
+def test_image_wider_than_the_sweep_limit_takes_the_radix_path():
+    """Images wider than 16384 px cannot use the counting sort's per-warp stripe counters
+    (GSR_SWEEP_MAX_STRIPE_TILES): api.cu falls back to the radix path automatically."""
+    from _gpu_util import intermediates
+    import synthetic
+    rd = _ref()
+    P, W, H = 30000, 16512, 96
+    sc = synthetic.make_scene(P, seed=4, device="cuda", scale_mult=6.0)
+    cam = synthetic.make_camera(0, 1, W, H, device="cuda", fovx=2.6)
+    rs = synthetic.raster_settings(cam, torch.zeros(3, device="cuda"))
+    f = rd.forward(rs, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+    R = f["num_rendered"]
+    assert R > 10000
+    m = intermediates(rs, sc)
+    b = rd.slice_binning(f["binning"], R)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    assert m["R"] == R
+    assert torch.equal(m["keys_sorted"], b["point_list_keys"])
+    assert torch.equal(m["point_list"], b["point_list"])
+    assert torch.equal(m["ranges"], rd.slice_img(f["img"], W, H)["ranges"][:tiles])
+    assert float((m["color"] - f["color"]).abs().max()) <= IMG_TOL
+
+
+# ---------------------------------------------------------------------------
+# Point counts that are not multiples of 4, through the flat parameter / gradient buffers, before and after
+# densification surgery (packed offsets misaligned the quaternion float4 accesses)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("P", [1003, 50001, 50002, 50003])
+def test_flat_buffers_with_any_point_count(P):
+    import fused_adam
+    import synthetic
+    from _gpu_util import assert_grad_close
+    from diff_gaussian_rasterization import GaussianRasterizer
+    rd = _ref()
+    W, H = 320, 200
+    sc = synthetic.make_scene(P, seed=7, device="cuda", scale_mult=2.0)
+    cam = synthetic.make_camera(0, 1, W, H, device="cuda")
+    rs = synthetic.raster_settings(cam, torch.zeros(3, device="cuda"))
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    # a leaf order that packs the quaternions behind odd-sized tensors
+    order = ("opacities", "means3D", "scales", "rotations", "shs")
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in order}
+    opt = fused_adam.FusedAdam([{"params": [leaves[k]], "lr": 0.0, "name": k} for k in order], lr=0.0, eps=1e-15)
+
+    def render_and_check(tag):
+        opt.zero_grad()
+        n = leaves["means3D"].shape[0]
+        for k in order:
+            assert leaves[k].data_ptr() % 32 == 0 and leaves[k].grad.data_ptr() % 32 == 0, (tag, k)
+        sinks = {k: leaves[k].grad for k in order}
+        m2d = torch.zeros(n, 3, device="cuda", requires_grad=True)
+        color, radii = GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                              shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                                              accumulate_grads=sinks)
+        (color * grad).sum().backward()
+        cur = {k: leaves[k].detach() for k in order}
+        f = rd.forward(rs, cur["means3D"], cur["opacities"], shs=cur["shs"], scales=cur["scales"], rotations=cur["rotations"])
+        b = rd.backward(rs, f, grad, cur["means3D"], shs=cur["shs"], scales=cur["scales"], rotations=cur["rotations"])
+        assert torch.equal(radii, f["radii"]) and float((color - f["color"]).abs().max()) <= IMG_TOL
+        for k in order:
+            assert_grad_close(leaves[k].grad, b[k], "P=%d %s %s" % (n, tag, k))
+        opt.step()
+
+    render_and_check("packed")
+    g = torch.Generator().manual_seed(P)
+    keep = (torch.rand(P, generator=g) > 0.25).cuda()
+    if int(keep.sum()) % 4 == 0:
+        keep[keep.nonzero()[0]] = False
+    opt.prune(keep)
+    render_and_check("pruned")
+    n_new = 37
+    ext = synthetic.make_scene(n_new, seed=8, device="cuda", scale_mult=2.0)
+    opt.append({k: ext[k] for k in order})
+    assert leaves["means3D"].shape[0] == int(keep.sum()) + n_new
+    render_and_check("appended")
+
+
+def test_raw_abi_accepts_unaligned_quaternions():
+    """The C ABI itself must not fault on a 4-byte-aligned rotations / dL_drots pointer (scalar path)."""
+    import synthetic
+    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    sc, cam, rs = make_view_settings(20001, 256, 160, scale_mult=2.0)
+    grad = synthetic.make_image_grad(256, 160, device="cuda")
+    a = run_ours(rs, sc, grad)
+    off = dict(sc)
+    buf = torch.zeros(sc["rotations"].numel() + 1, device="cuda")
+    buf[1:] = sc["rotations"].reshape(-1)
+    off["rotations"] = buf[1:].view_as(sc["rotations"])
+    assert off["rotations"].data_ptr() % 16 != 0
+    b = run_ours(rs, off, grad)
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["radii"], b["radii"])
+    assert rel_to_max(b["grads"]["rotations"], a["grads"]["rotations"]) <= 1e-5
+
+
+# ---------------------------------------------------------------------------
+# Frozen error / debug conventions
+# ---------------------------------------------------------------------------
+def test_prefiltered_violation_is_reported_not_fatal():
+    """auxiliary.h:154-160: with prefiltered=True a point behind the near plane is an error.  The reference
+    printf()s and __trap()s; here the same message comes back as an exception and the context survives."""
+    import gsr_runtime as rt
+    import synthetic
+    from _gpu_util import make_view_settings, run_ours
+    sc, cam, rs = make_view_settings(5000, 128, 96)
+    with pytest.raises(rt.GsrError, match="Point is filtered although prefiltered is set"):
+        bad = dict(sc)
+        bad["means3D"] = sc["means3D"].clone()
+        bad["means3D"][17] = torch.tensor([0.0, 0.0, -30.0], device="cuda")
+        run_ours(rs._replace(prefiltered=True), bad, None)
+    torch.cuda.synchronize()                                        # context alive
+    vis = dict(sc)
+    vis["means3D"] = sc["means3D"] * 0.5                            # everything in front of the camera
+    a = run_ours(rs._replace(prefiltered=True), vis, None)
+    b = run_ours(rs, vis, None)
+    assert torch.equal(a["color"], b["color"])
+
+
+def test_debug_mode_syncs_and_dumps_a_snapshot_on_failure(tmp_path, monkeypatch):
+    """diff_gaussian_rasterization/__init__.py:83-90,132-139: debug=True runs synchronously and, when the native
+    call raises, writes snapshot_fw.dump with the CPU copies of the arguments and re-raises."""
+    import gsr_runtime as rt
+    import synthetic
+    from _gpu_util import make_view_settings, run_ours
+    monkeypatch.chdir(tmp_path)
+    sc, cam, rs = make_view_settings(3000, 96, 64, scale_mult=2.0)
+    grad = synthetic.make_image_grad(96, 64, device="cuda")
+    a = run_ours(rs, sc, grad)
+    d = run_ours(rs._replace(debug=True), sc, grad)                  # same results, no dump on success
+    assert torch.equal(a["color"], d["color"]) and not os.path.exists("snapshot_fw.dump")
+    bad = dict(sc)
+    bad["means3D"] = sc["means3D"].clone()
+    bad["means3D"][5] = torch.tensor([0.0, 0.0, -30.0], device="cuda")
+    with pytest.raises(rt.GsrError):
+        run_ours(rs._replace(debug=True, prefiltered=True), bad, None)
+    snap = torch.load("snapshot_fw.dump", weights_only=False)
+    assert isinstance(snap, tuple) and torch.equal(snap[1], bad["means3D"].cpu()) and snap[17] is True and snap[18] is True
+
+
+def test_two_rasterizers_interleaved_keep_their_own_results():
+    import synthetic
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from _gpu_util import make_view_settings
+    sc, cam, rs = make_view_settings(4000, 128, 96, scale_mult=2.0)
+    S, th = synthetic.make_twists(4000, device="cuda")
+    r1, r2 = GaussianRasterizer(rs), GaussianRasterizer(rs)
+    kw = dict(means2D=torch.zeros(4000, 3, device="cuda"), opacities=sc["opacities"], shs=sc["shs"], scales=sc["scales"],
+              rotations=sc["rotations"])
+    r1(means3D=sc["means3D"], se3_S=S, se3_theta=th, **kw)
+    d1 = r1.deformed_means.clone()
+    n1 = r1.num_rendered
+    r2(means3D=sc["means3D"] * 0.5, se3_S=S, se3_theta=2 * th, **kw)
+    assert torch.equal(r1.deformed_means, d1) and r1.num_rendered == n1
+    assert not torch.equal(r2.deformed_means, d1)
+
+
+def test_accumulate_grads_rejects_non_leaf_inputs():
+    import gsr_runtime as rt
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from _gpu_util import make_view_settings
+    sc, cam, rs = make_view_settings(2000, 96, 64)
+    raw = sc["scales"].log().requires_grad_(True)
+    scales = raw.exp()                                              # non-leaf
+    sink = torch.zeros_like(scales)
+    with pytest.raises(rt.GsrError, match="not a leaf"):
+        GaussianRasterizer(rs)(means3D=sc["means3D"], means2D=torch.zeros(2000, 3, device="cuda"), opacities=sc["opacities"],
+                               shs=sc["shs"], scales=scales, rotations=sc["rotations"], accumulate_grads={"scales": sink})
+
+
+# ---------------------------------------------------------------------------
+# FusedAdam <-> torch.optim.Adam checkpoints (scene/gaussian_model.py:698,725)
+# ---------------------------------------------------------------------------
+def test_fused_adam_state_dict_round_trips_with_torch_adam():
+    import fused_adam
+    g = torch.Generator().manual_seed(13)
+    shapes = {"xyz": (1003, 3), "f_dc": (1003, 1, 3), "opacity": (1003, 1), "net": (7, 5)}
+    lrs = {"xyz": 1.6e-4, "f_dc": 2.5e-3, "opacity": 0.05, "net": 1e-3}
+    base = {k: torch.randn(s, generator=g).cuda() for k, s in shapes.items()}
+    mk = lambda: {k: v.clone().requires_grad_(True) for k, v in base.items()}
+
+    def groups(ps):
+        return [{"params": [ps[k]], "lr": lrs[k], "name": k} for k in shapes]
+    pa, pb = mk(), mk()
+    oa = fused_adam.FusedAdam(groups(pa), lr=0.0, eps=1e-15)
+    ob = torch.optim.Adam(groups(pb), lr=0.0, eps=1e-15)
+
+    def step(oa_, pa_, ob_, pb_, skip=()):
+        oa_.zero_grad()
+        for k in shapes:
+            gr = torch.randn(shapes[k], generator=g).cuda() * 0.1
+            pa_[k].grad.copy_(gr)
+            pb_[k].grad = None if k in skip else gr.clone()
+        oa_.step(skip=skip)
+        ob_.step()
+    step(oa, pa, ob, pb)
+    step(oa, pa, ob, pb, skip=("net",))             # a dormant group: torch skips grad None, so its step count lags
+    step(oa, pa, ob, pb)
+    for k in shapes:
+        assert torch.allclose(pa[k].detach(), pb[k].detach(), rtol=1e-6, atol=1e-7), k
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert set(sa.keys()) == set(sb.keys()) == {"state", "param_groups"}
+    assert sorted(sa["state"].keys()) == sorted(sb["state"].keys())
+    for i in sb["state"]:
+        assert float(sa["state"][i]["step"]) == float(sb["state"][i]["step"])
+        assert sa["state"][i]["exp_avg"].shape == sb["state"][i]["exp_avg"].shape
+        assert torch.allclose(sa["state"][i]["exp_avg"], sb["state"][i]["exp_avg"], rtol=1e-6, atol=1e-9)
+        assert torch.allclose(sa["state"][i]["exp_avg_sq"], sb["state"][i]["exp_avg_sq"], rtol=1e-6, atol=1e-12)
+    assert [g_["params"] for g_ in sa["param_groups"]] == [g_["params"] for g_ in sb["param_groups"]]
+    assert [g_["name"] for g_ in sa["param_groups"]] == list(shapes)
+    # torch -> fused and fused -> torch: resume in the OTHER optimizer and keep stepping in lockstep
+    pc_, pd_ = {k: pb[k].detach().clone().requires_grad_(True) for k in shapes}, {k: pa[k].detach().clone().requires_grad_(True) for k in shapes}
+    oc = fused_adam.FusedAdam(groups(pc_), lr=0.0, eps=1e-15)
+    oc.load_state_dict(sb)
+    od = torch.optim.Adam(groups(pd_), lr=0.0, eps=1e-15)
+    od.load_state_dict(sa)
+    step(oc, pc_, od, pd_)
+    step(oc, pc_, od, pd_)
+    for k in shapes:
+        assert torch.allclose(pc_[k].detach(), pd_[k].detach(), rtol=1e-6, atol=1e-7), k
+    bad = ob.state_dict()
+    bad["state"][0]["exp_avg"] = bad["state"][0]["exp_avg"][:-1]
+    with pytest.raises(ValueError):
+        oc.load_state_dict(bad)

@@ -73,7 +73,7 @@ def test_forward_stages_bit_exact_vs_reference(P, W, H, smult):
                                               (30000, 250, 130, 5.0, (1, 1, 1)), (1000000, 1920, 1080, 1.0, (0, 0, 0))])
 def test_forward_backward_vs_reference(P, W, H, smult, bg):
     import synthetic
-    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    from _gpu_util import assert_grad_close, make_view_settings, rel_to_max, run_ours
     rd = _ref()
     sc, cam, rs = make_view_settings(P, W, H, scale_mult=smult, bg=bg)
     grad = synthetic.make_image_grad(W, H, device="cuda")
@@ -82,8 +82,12 @@ def test_forward_backward_vs_reference(P, W, H, smult, bg):
     assert torch.equal(o["radii"], f["radii"])
     assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
     for k in ("means3D", "opacities", "shs", "scales", "rotations"):
-        assert rel_to_max(o["grads"][k], b[k]) <= GRAD_TOL, k
-    assert rel_to_max(o["means2D_grad"], b["means2D"]) <= GRAD_TOL
+        assert_grad_close(o["grads"][k], b[k], "fwd_bwd_vs_reference P=%d %dx%d %s" % (P, W, H, k))
+    assert_grad_close(o["means2D_grad"], b["means2D"], "fwd_bwd_vs_reference P=%d %dx%d means2D" % (P, W, H))
+    # noise floor of the bar: the reference against a second run of itself (unordered atomics)
+    _, b2 = _ref_fb(rd, rs, sc, grad)
+    for k in ("means3D", "shs"):
+        assert_grad_close(b2[k], b[k], "REFERENCE_vs_itself P=%d %dx%d %s" % (P, W, H, k))
 
 
 @pytest.mark.parametrize("case", ["sh3", "sh1", "precomp"])
@@ -138,7 +142,7 @@ def test_vs_cpu_oracle():
 @pytest.mark.parametrize("deg", [0, 1, 2])
 def test_lower_sh_degrees_vs_reference(deg):
     import synthetic
-    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    from _gpu_util import assert_grad_close, make_view_settings, rel_to_max, run_ours
     rd = _ref()
     P, W, H = 30000, 400, 240
     sc, cam, rs = make_view_settings(P, W, H, sh_degree=deg, scale_mult=1.5, scale_modifier=0.7)
@@ -148,14 +152,14 @@ def test_lower_sh_degrees_vs_reference(deg):
     assert torch.equal(o["radii"], f["radii"])
     assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
     for k in ("means3D", "shs", "scales", "rotations", "opacities"):
-        assert rel_to_max(o["grads"][k], b[k]) <= GRAD_TOL, k
+        assert_grad_close(o["grads"][k], b[k], "sh_degree_%d %s" % (deg, k))
     nz = (deg + 1) ** 2
     assert float(o["grads"]["shs"][:, nz:].abs().max()) == 0.0      # inactive coefficients get zero gradient
 
 
 def test_precomputed_color_and_covariance_vs_reference():
     import synthetic
-    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    from _gpu_util import assert_grad_close, make_view_settings, rel_to_max, run_ours
     rd = _ref()
     P, W, H = 30000, 320, 320
     sc, cam, rs = make_view_settings(P, W, H, scale_mult=2.0, sh_degree=0)
@@ -168,9 +172,9 @@ def test_precomputed_color_and_covariance_vs_reference():
     o = run_ours(rs, sc, grad, colors_precomp=colors, cov3D_precomp=cov)
     assert torch.equal(o["radii"], f["radii"])
     assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
-    assert rel_to_max(o["extra_grads"]["colors"], b["colors"]) <= GRAD_TOL
-    assert rel_to_max(o["extra_grads"]["cov3D"], b["cov3D"]) <= GRAD_TOL
-    assert rel_to_max(o["grads"]["means3D"], b["means3D"]) <= GRAD_TOL
+    assert_grad_close(o["extra_grads"]["colors"], b["colors"], "precomp colors")
+    assert_grad_close(o["extra_grads"]["cov3D"], b["cov3D"], "precomp cov3D")
+    assert_grad_close(o["grads"]["means3D"], b["means3D"], "precomp means3D")
     assert o["grads"]["shs"] is None and o["grads"]["scales"] is None
 
 
@@ -178,7 +182,7 @@ def test_fused_se3_per_gaussian():
     """Protocol of SURVEY.md 7: (i) SE3 stage vs the torch op graph within 1e-6;
     (ii) OUR deformed means fed to the reference -> downstream bit-exact; gradients 1e-4."""
     import synthetic
-    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    from _gpu_util import assert_grad_close, make_view_settings, rel_to_max, run_ours
     from oracle import rigid_body_port
     rd = _ref()
     P, W, H = 100000, 640, 360
@@ -195,17 +199,17 @@ def test_fused_se3_per_gaussian():
     assert torch.equal(o["radii"], f["radii"])
     assert float((o["color"] - f["color"]).abs().max()) <= IMG_TOL
     (y * b["means3D"]).sum().backward()
-    assert rel_to_max(o["grads"]["means3D"], x.grad) <= GRAD_TOL
-    assert rel_to_max(o["extra_grads"]["S"], S_.grad) <= GRAD_TOL
-    assert rel_to_max(o["extra_grads"]["theta"], th_.grad) <= GRAD_TOL
+    assert_grad_close(o["grads"]["means3D"], x.grad, "fused_se3 means3D")
+    assert_grad_close(o["extra_grads"]["S"], S_.grad, "fused_se3 S")
+    assert_grad_close(o["extra_grads"]["theta"], th_.grad, "fused_se3 theta")
     for k in ("shs", "scales", "rotations", "opacities"):
-        assert rel_to_max(o["grads"][k], b[k]) <= GRAD_TOL, k
+        assert_grad_close(o["grads"][k], b[k], "fused_se3 " + k)
 
 
 def test_fused_se3_rigid_bodies():
     """64 rigid bodies (config C3): body table + body_id must equal the per-Gaussian expansion."""
     import synthetic
-    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    from _gpu_util import assert_grad_close, make_view_settings, rel_to_max, run_ours
     P, W, H = 60000, 400, 400
     sc, cam, rs = make_view_settings(P, W, H, scale_mult=1.5)
     grad = synthetic.make_image_grad(W, H, device="cuda")
@@ -387,7 +391,7 @@ def test_accumulate_grads_matches_autograd_sum():
             (color * grad).sum().backward()
         if accumulate:      # .grad tensors are still the views into the flat buffer
             assert all(v.grad.data_ptr() >= buf.flat.data_ptr() for v in leaves.values())
-            assert buf.flat.numel() == P * 66
+            assert buf.flat.numel() == P * 66               # P is a multiple of 8: no padding
         return {k: v.grad.clone() for k, v in leaves.items()}
     a, b = run(True), run(False)
     for k in a:

@@ -93,6 +93,15 @@ def test_two_rank_allreduce_equals_single_process_sum(tmp_path):
         seen += torch.from_numpy(radii > 0).float()
     flat_ref = torch.cat([ref[k].reshape(-1) for k in KEYS])
     assert flat_ref.numel() == P * 59                    # 59 floats (236 B) per Gaussian
-    torch.testing.assert_close(r0["flat"], flat_ref, rtol=1e-5, atol=1e-5 * float(flat_ref.abs().max()))
+    # the flat buffer starts every tensor on a 32-byte boundary (view_parallel.flat_layout); padding stays zero
+    import view_parallel as vp
+    offs, total = vp.flat_layout([ref[k] for k in KEYS])
+    assert r0["flat"].numel() == total
+    got = torch.cat([r0["flat"][o:o + ref[k].numel()] for o, k in zip(offs, KEYS)])
+    pad = r0["flat"].clone()
+    for o, k in zip(offs, KEYS):
+        pad[o:o + ref[k].numel()] = 0
+    assert float(pad.abs().max()) == 0.0
+    torch.testing.assert_close(got, flat_ref, rtol=1e-5, atol=1e-5 * float(flat_ref.abs().max()))
     assert abs(float(r0["loss"]) - loss) <= 1e-4 * abs(loss)
     assert torch.equal(r0["stats"]["denom"].reshape(-1), seen)
