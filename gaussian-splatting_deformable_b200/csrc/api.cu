@@ -507,6 +507,40 @@ int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t*
     return gsr_launch_mark_visible(P, means3D, v, present, (cudaStream_t)stream_);
 }
 
+int gsr_mlp_gemm(const gsr_gemm* g, void* stream_) {
+    if (!g) return gsr_set_error_msg(-1, "mlp_gemm: NULL argument block");
+    GsrGemmArgs a{};
+    a.M = g->M; a.N = g->N;
+    a.A0_hi = g->A0_hi; a.A0_lo = g->A0_lo; a.K0 = g->K0; a.ldA0 = g->ldA0;
+    a.A1_hi = g->A1_hi; a.A1_lo = g->A1_lo; a.K1 = g->K1; a.ldA1 = g->ldA1;
+    a.B_hi = g->B_hi; a.B_lo = g->B_lo; a.ldB = g->ldB;
+    a.mode = g->mode; a.k_splits = g->k_splits; a.bias = g->bias; a.mask_src = g->mask_src; a.ld_mask = g->ld_mask;
+    a.out_hi = g->out_hi; a.out_lo = g->out_lo; a.ld_out = g->ld_out;
+    a.outT_hi = g->outT_hi; a.outT_lo = g->outT_lo; a.ld_outT = g->ld_outT;
+    a.colsum = g->colsum; a.error_flag = g->error_flag;
+    a.prof_name = g->mode == GSR_GEMM_ATOMIC ? "mlp_gemm_dw" : (g->mask_src ? "mlp_gemm_dx" : "mlp_gemm_fwd");
+    if (a.mode < 0 || a.mode > 3) return gsr_set_error_msg(-2, "mlp_gemm: unknown epilogue mode");
+    if ((a.A1_hi == nullptr) != (a.A1_lo == nullptr)) return gsr_set_error_msg(-1, "mlp_gemm: second A segment needs both planes");
+    return gsr_launch_mlp_gemm(a, (cudaStream_t)stream_);
+}
+int gsr_mlp_split(const float* x, int64_t n, float* hi, float* lo, void* stream_) {
+    if (n > 0 && (!x || !hi || !lo)) return gsr_set_error_msg(-1, "mlp_split: NULL pointer");
+    return gsr_launch_mlp_split(x, n, hi, lo, (cudaStream_t)stream_);
+}
+int gsr_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float* hi, float* lo, int ldT, void* stream_) {
+    if (rows > 0 && cols > 0 && (!x || !hi || !lo)) return gsr_set_error_msg(-1, "mlp_split_transpose: NULL pointer");
+    return gsr_launch_mlp_split_transpose(x, rows, cols, ld_in, hi, lo, ldT, (cudaStream_t)stream_);
+}
+int gsr_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, int64_t ldT, void* stream_) {
+    if (P > 0 && (!xyz || !e_hi || !e_lo)) return gsr_set_error_msg(-1, "mlp_embed: NULL pointer");
+    if ((eT_hi == nullptr) != (eT_lo == nullptr)) return gsr_set_error_msg(-1, "mlp_embed: give both transposed planes or neither");
+    return gsr_launch_mlp_embed(xyz, P, e_hi, e_lo, eT_hi, eT_lo, ldT, (cudaStream_t)stream_);
+}
+int gsr_mlp_embed_backward(const float* xyz, int P, const float* d_embed, float* dxyz, int accumulate, void* stream_) {
+    if (P > 0 && (!xyz || !d_embed || !dxyz)) return gsr_set_error_msg(-1, "mlp_embed_backward: NULL pointer");
+    return gsr_launch_mlp_embed_bwd(xyz, P, d_embed, dxyz, accumulate, (cudaStream_t)stream_);
+}
+
 size_t gsr_knn_bytes(int P) { return gsr_knn_temp_bytes(P); }
 int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream_) {
     if (P > 0 && (!points || !mean_dist2 || !temp)) return gsr_set_error_msg(-1, "knn: NULL pointer");

@@ -180,3 +180,32 @@ int gsr_launch_se3_matrices_bwd(int N, const float* S, const float* theta, const
 size_t gsr_knn_temp_bytes(int P);
 int gsr_launch_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes,
                          cudaStream_t stream);
+
+// ---- deformation-network GEMMs on tcgen05 (mlp_gemm.cu) -----------------------------------
+// C[M x N] = epilogue(A[M x K] . B[N x K]^T), every operand as (hi, lo) fp32 planes (x = hi + lo, hi a TF32 value):
+// three kind::tf32 MMAs per product give an fp32-grade result.  A may be the concatenation of two K segments
+// (the skip connection: [embedding | hidden]).  K-major operands only: A row stride ldA, B row stride ldB.
+#define GSR_GEMM_RELU_SPLIT 0   // v = relu(acc + bias)        -> (hi, lo) planes row-major (+ transposed planes)
+#define GSR_GEMM_SPLIT 1        // v = (acc + bias) [* mask]   -> (hi, lo) planes row-major (+ transposed planes)
+#define GSR_GEMM_PLAIN 2        // v = (acc + bias) [* mask]   -> fp32 [M x ld_out] in out_hi
+#define GSR_GEMM_ATOMIC 3       // out_hi[M x ld_out] += acc   (split-K partial sums, weight gradients)
+struct GsrGemmArgs {
+    int M, N;
+    const float* A0_hi; const float* A0_lo; int K0; long long ldA0;
+    const float* A1_hi; const float* A1_lo; int K1; long long ldA1;       // optional second K segment (null: none)
+    const float* B_hi; const float* B_lo; long long ldB;                  // [N x (K0pad + K1pad)], K padded to 32 per segment
+    int mode;
+    int k_splits;                 // > 1: tiles are (row tile, K range) pairs (use with GSR_GEMM_ATOMIC)
+    const float* bias;            // [N] or null
+    const float* mask_src; int ld_mask;    // v = mask_src[m][n] > 0 ? v : 0  (ReLU backward) or null
+    float* out_hi; float* out_lo; int ld_out;
+    float* outT_hi; float* outT_lo; long long ld_outT;   // transposed planes [N x ld_outT] or null
+    float* colsum;                // [N] += column sums of the stored values (bias gradients) or null
+    uint32_t* error_flag;         // device word, set if a pipeline wait timed out
+    const char* prof_name;
+};
+int gsr_launch_mlp_gemm(const GsrGemmArgs& g, cudaStream_t stream);
+int gsr_launch_mlp_split(const float* x, long long n, float* hi, float* lo, cudaStream_t stream);
+int gsr_launch_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float* hi, float* lo, int ldT, cudaStream_t stream);
+int gsr_launch_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, long long ldT, cudaStream_t stream);
+int gsr_launch_mlp_embed_bwd(const float* xyz, int P, const float* de, float* dxyz, int accumulate, cudaStream_t stream);

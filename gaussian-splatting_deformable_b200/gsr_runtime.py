@@ -48,6 +48,24 @@ class gsr_deform(ctypes.Structure):
     ]
 
 
+class gsr_gemm(ctypes.Structure):
+    """Mirror of `struct gsr_gemm` (include/gsr_b200.h)."""
+    _fields_ = [
+        ("M", ctypes.c_int32), ("N", ctypes.c_int32),
+        ("A0_hi", ctypes.c_void_p), ("A0_lo", ctypes.c_void_p), ("K0", ctypes.c_int32), ("ldA0", ctypes.c_int64),
+        ("A1_hi", ctypes.c_void_p), ("A1_lo", ctypes.c_void_p), ("K1", ctypes.c_int32), ("ldA1", ctypes.c_int64),
+        ("B_hi", ctypes.c_void_p), ("B_lo", ctypes.c_void_p), ("ldB", ctypes.c_int64),
+        ("mode", ctypes.c_int32), ("k_splits", ctypes.c_int32),
+        ("bias", ctypes.c_void_p),
+        ("mask_src", ctypes.c_void_p), ("ld_mask", ctypes.c_int32),
+        ("out_hi", ctypes.c_void_p), ("out_lo", ctypes.c_void_p), ("ld_out", ctypes.c_int32),
+        ("outT_hi", ctypes.c_void_p), ("outT_lo", ctypes.c_void_p), ("ld_outT", ctypes.c_int64),
+        ("colsum", ctypes.c_void_p),
+        ("error_flag", ctypes.c_void_p),
+    ]
+
+
+GEMM_RELU_SPLIT, GEMM_SPLIT, GEMM_PLAIN, GEMM_ATOMIC = 0, 1, 2, 3
 DEFORM_NONE, DEFORM_PER_GAUSSIAN, DEFORM_RIGID_BODIES = 0, 1, 2
 
 _P = ctypes.c_void_p
@@ -79,6 +97,11 @@ _SIGNATURES = {
     "gsr_ssim_l1_loss_backward": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_float, _P, _P,
                                                  _P, _P]),
     "gsr_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gsr_mlp_gemm": (ctypes.c_int, [ctypes.POINTER(gsr_gemm), _P]),
+    "gsr_mlp_split": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P]),
+    "gsr_mlp_split_transpose": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, ctypes.c_int, _P]),
+    "gsr_mlp_embed": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "gsr_mlp_embed_backward": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, ctypes.c_int, _P]),
     "gsr_mark_visible": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, _P, _P, _P]),
     "gsr_knn_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_knn_dist2": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_size_t, _P]),

@@ -34,6 +34,11 @@
  *       <- utils/loss_utils.py:17-64 (l1_loss, ssim) combined as in train.py:323,529
  *   gsr_adam_step
  *       <- torch.optim.Adam as configured at scene/gaussian_model.py:834-846
+ *   gsr_mlp_embed / gsr_mlp_embed_backward
+ *       <- Embedder.embed, scene/gaussian_model.py:33-81 (multires 10 positional embedding of the positions)
+ *   gsr_mlp_gemm (+ gsr_mlp_split / gsr_mlp_split_transpose operand preparation)
+ *       <- the nn.Linear layers of DirectTemporalNeRF.query_time, scene/gaussian_model.py:285-293 (forward) and
+ *          their autograd (input and weight gradients): cuBLAS SGEMM in the reference, tcgen05 tensor cores here
  */
 #ifndef GSR_B200_H
 #define GSR_B200_H
@@ -186,6 +191,37 @@ int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 
 /* ---- the rest of the reference's operator surface -------------------------- */
 int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t* present, void* stream);
+
+/* Deformation-network linear layers on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
+ * TMEM, operands staged by TMA), with an fp32-grade result: every operand is given as two fp32 planes, x = hi + lo
+ * with hi a TF32 value (gsr_mlp_split), and each product is evaluated as hi.hi + lo.hi + hi.lo.
+ *   C[M x N] = epilogue(A[M x K] . B[N x K]^T),  N <= 256,  all operands K-major (row stride ldA / ldB floats,
+ *   multiples of 4, 16-byte aligned planes).  A may be two K segments ([A0 | A1], the network's skip connection);
+ *   each segment's K is padded to a multiple of 32 in B's column numbering (segment 1 starts at 32 ceil(K0 / 32)).
+ * mode 0: relu(acc + bias) -> (hi, lo) planes;  1: (acc + bias), optionally zeroed where mask_src <= 0 -> planes;
+ *      2: same value -> fp32 in out_hi;  3: out_hi += acc with atomics (k_splits > 1: split over K, weight gradients).
+ * outT_*: the same values transposed ([N x ld_outT]); colsum[n] += column sums (bias gradients). */
+typedef struct gsr_gemm {
+    int32_t M, N;
+    const float* A0_hi; const float* A0_lo; int32_t K0; int64_t ldA0;
+    const float* A1_hi; const float* A1_lo; int32_t K1; int64_t ldA1;
+    const float* B_hi; const float* B_lo; int64_t ldB;
+    int32_t mode;
+    int32_t k_splits;
+    const float* bias;
+    const float* mask_src; int32_t ld_mask;
+    float* out_hi; float* out_lo; int32_t ld_out;
+    float* outT_hi; float* outT_lo; int64_t ld_outT;
+    float* colsum;
+    uint32_t* error_flag;
+} gsr_gemm;
+int gsr_mlp_gemm(const gsr_gemm* g, void* stream);
+int gsr_mlp_split(const float* x, int64_t n, float* hi, float* lo, void* stream);
+/* x [rows x cols] (row stride ld_in) -> planes of x^T [cols x ldT] */
+int gsr_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float* hi, float* lo, int ldT, void* stream);
+/* positions [P,3] -> embedding planes [P x 64] (63 values, column 63 zero) and, optionally, transposed [64 x ldT] */
+int gsr_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, int64_t ldT, void* stream);
+int gsr_mlp_embed_backward(const float* xyz, int P, const float* d_embed /*[P x 64]*/, float* dxyz, int accumulate, void* stream);
 
 size_t gsr_knn_bytes(int P);
 int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream);
