@@ -531,6 +531,13 @@ int gsr_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float
     if (rows > 0 && cols > 0 && (!x || !hi || !lo)) return gsr_set_error_msg(-1, "mlp_split_transpose: NULL pointer");
     return gsr_launch_mlp_split_transpose(x, rows, cols, ld_in, hi, lo, ldT, (cudaStream_t)stream_);
 }
+int gsr_mlp_prepare(const float* x, int rows, int cols, int64_t ld_in, float* hi, float* lo, int64_t ld_out, float* hiT,
+                    float* loT, int64_t ldT, float* colsum, void* stream_) {
+    if (rows > 0 && cols > 0 && !x) return gsr_set_error_msg(-1, "mlp_prepare: NULL input");
+    if ((hi == nullptr) != (lo == nullptr) || (hiT == nullptr) != (loT == nullptr))
+        return gsr_set_error_msg(-1, "mlp_prepare: planes come in (hi, lo) pairs");
+    return gsr_launch_mlp_prepare(x, rows, cols, ld_in, hi, lo, ld_out, hiT, loT, ldT, colsum, (cudaStream_t)stream_);
+}
 int gsr_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, int64_t ldT, void* stream_) {
     if (P > 0 && (!xyz || !e_hi || !e_lo)) return gsr_set_error_msg(-1, "mlp_embed: NULL pointer");
     if ((eT_hi == nullptr) != (eT_lo == nullptr)) return gsr_set_error_msg(-1, "mlp_embed: give both transposed planes or neither");

@@ -207,5 +207,7 @@ struct GsrGemmArgs {
 int gsr_launch_mlp_gemm(const GsrGemmArgs& g, cudaStream_t stream);
 int gsr_launch_mlp_split(const float* x, long long n, float* hi, float* lo, cudaStream_t stream);
 int gsr_launch_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float* hi, float* lo, int ldT, cudaStream_t stream);
+int gsr_launch_mlp_prepare(const float* x, int rows, int cols, long long ld_in, float* hi, float* lo, long long ld_out,
+                           float* hiT, float* loT, long long ldT, float* colsum, cudaStream_t stream);
 int gsr_launch_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, long long ldT, cudaStream_t stream);
 int gsr_launch_mlp_embed_bwd(const float* xyz, int P, const float* de, float* dxyz, int accumulate, cudaStream_t stream);

@@ -4,7 +4,7 @@
 // The reference evaluates DirectTemporalNeRF (scene/gaussian_model.py:242-316: 84 -> 8 x 256 ReLU, skip after layer
 // 4, heads 3/3/4/48) with torch fp32 linears, i.e. cuBLAS SGEMM on the FP32 pipe.  Tensor cores take TF32 (10-bit
 // mantissa) at best, which alone misses the fp32 result by ~1e-3; so every operand travels as two planes
-//      x = hi + lo,   hi = x with the 13 low mantissa bits cleared (exactly a TF32 value),   lo = x - hi (exact)
+//      x = hi + lo,   hi = x rounded to nearest TF32 value (13 low mantissa bits zero),   lo = x - hi (exact)
 // and every product is   A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (three kind::tf32 MMAs into one fp32 TMEM
 // accumulator; the dropped lo.lo term and the TF32 rounding of lo are ~2^-22 relative).  Measured against an fp64
 // evaluation the result is as close as cuBLAS SGEMM's own (tests/test_gpu_mlp.py).
@@ -110,7 +110,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// hi = x rounded TO NEAREST to TF32 precision (11 significant bits; ties away from zero): then |lo| = |x - hi| <= 2^-12 |x|
+// carries at most 12 significant bits, of which the tensor core keeps 11, i.e. the split loses <= 2^-23 |x| - fp32's own
+// half-ulp (truncating instead would leave |lo| <= 2^-11 |x| with 13 bits and lose 2^-21 |x|: measured 4x the error).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 template <int BN>
 struct SmemLayout {
@@ -386,9 +389,13 @@ int launch(const GsrGemmArgs& g, cudaStream_t stream) {
         if (int rc = make_map(&a1h, g.A1_hi, g.M, g.K1, g.ldA1, BM)) return rc;
         if (int rc = make_map(&a1l, g.A1_lo, g.M, g.K1, g.ldA1, BM)) return rc;
     } else { a1h = a0h; a1l = a0l; }
-    // B [N rows x (kb0 + kb1) * 32 cols]: rows beyond N read as zero, so the MMA always runs at the full BN
-    if (int rc = make_map(&bh, g.B_hi, g.N, g.ldB < (long long)(kb0 + kb1) * BK ? g.ldB : (long long)(kb0 + kb1) * BK, g.ldB, BN)) return rc;
-    if (int rc = make_map(&bl, g.B_lo, g.N, g.ldB < (long long)(kb0 + kb1) * BK ? g.ldB : (long long)(kb0 + kb1) * BK, g.ldB, BN)) return rc;
+    // B [N rows x K cols]: K = K0, or 32 ceil(K0 / 32) + K1 with two segments.  The map's extent is the TRUE K (reads
+    // beyond it are zero-filled by TMA, never fetched: the caller's padding may hold anything) and rows beyond N read
+    // as zero, so the MMA always runs at the full BN.
+    const long long bcols = g.A1_hi ? (long long)kb0 * BK + g.K1 : (long long)g.K0;
+    if (g.ldB < bcols) return gsr_set_error_msg(-2, "mlp_gemm: ldB is smaller than K");
+    if (int rc = make_map(&bh, g.B_hi, g.N, bcols, g.ldB, BN)) return rc;
+    if (int rc = make_map(&bl, g.B_lo, g.N, bcols, g.ldB, BN)) return rc;
     GemmParams p{};
     p.M = g.M; p.N = g.N; p.kblocks[0] = kb0; p.kblocks[1] = kb1;
     p.m_tiles = gsr_div_up(g.M, BM);
@@ -447,6 +454,42 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
     const int r = i / cols, c = i % cols;
     const float v = x[(size_t)r * ld_in + c], h = tf32_hi(v);
     hi[(size_t)c * ldT + r] = h; lo[(size_t)c * ldT + r] = v - h;
+}
+
+// x [rows x cols] (row stride ld_in) -> row-major planes [rows x ld_out] and/or transposed planes [cols x ldT], plus column
+// sums: the operand preparation of a gradient that arrives from autograd (dL/d heads).  32 x 32 tiles through shared memory,
+// so that both the reads and the transposed writes are 128-byte lines.
+__global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ x, int rows, int cols, long long ld_in,
+                                                     float* __restrict__ hi, float* __restrict__ lo, long long ld_out,
+                                                     float* __restrict__ hiT, float* __restrict__ loT, long long ldT,
+                                                     float* __restrict__ colsum) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const long long r = r0 + ty + 8 * k;
+        const int c = c0 + tx;
+        const float v = (r < rows && c < cols) ? x[r * ld_in + c] : 0.0f;
+        tile[ty + 8 * k][tx] = v;
+        if (hi && r < rows && c < cols) { const float h = tf32_hi(v); hi[r * ld_out + c] = h; lo[r * ld_out + c] = v - h; }
+    }
+    __syncthreads();
+    if (hiT) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = c0 + ty + 8 * k;
+            const long long r = r0 + tx;
+            if (c < cols && r < rows) { const float v = tile[tx][ty + 8 * k], h = tf32_hi(v); hiT[c * ldT + r] = h; loT[c * ldT + r] = v - h; }
+        }
+    }
+    if (colsum && ty == 0) {
+        float sacc = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 32; r++) sacc += tile[r][tx];
+        if (c0 + tx < cols && sacc != 0.0f) atomicAdd(colsum + c0 + tx, sacc);
+    }
 }
 
 // Positional embedding of gaussian_model.py:33-81 with multires 10: [x, sin(2^0 x), cos(2^0 x), ..., sin(2^9 x), cos(2^9 x)]
@@ -526,6 +569,15 @@ int gsr_launch_mlp_split_transpose(const float* x, int rows, int cols, int ld_in
     if (rows <= 0 || cols <= 0) return 0;
     { GsrProfScope prof_("mlp_split_transpose", stream);
     split_transpose_kernel<<<gsr_div_up((long long)rows * cols, 256), 256, 0, stream>>>(x, rows, cols, ld_in, hi, lo, ldT); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+int gsr_launch_mlp_prepare(const float* x, int rows, int cols, long long ld_in, float* hi, float* lo, long long ld_out,
+                           float* hiT, float* loT, long long ldT, float* colsum, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const dim3 grid(gsr_div_up(rows, 32), gsr_div_up(cols, 32), 1);
+    { GsrProfScope prof_("mlp_prepare", stream);
+    prepare_kernel<<<grid, 256, 0, stream>>>(x, rows, cols, ld_in, hi, lo, ld_out, hiT, loT, ldT, colsum); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

@@ -1,0 +1,362 @@
+"""Drop-in for the reference's deformation networks, evaluated on the tensor cores.
+
+`DirectTemporalNeRF` (scene/gaussian_model.py:242-316) is the network `GaussianModel.get_xyz_all` queries every iteration
+(:761-769): positional embedding of the positions (63) and of the view's time (21) -> 8 x 256 ReLU layers, the embedded
+position re-concatenated in front of the activations after layer 4 -> four linear heads (dx 3, dx_scale 3, dx_rot 4,
+mlp_shs 48).  `DirectTemporalNeRF_se3` (:99-173) has the same trunk with heads (w 3, v 3) that become the screw axis and
+angle of the SE3 exponential map.
+
+Same class names, constructor defaults, parameter names (`_time.N.weight`, `_time_out.weight`, ...: the reference's
+`offset_model.pth` state-dicts load unchanged), call signature and return values.  The linears run as tcgen05
+(`kind::tf32`) GEMMs with hi/lo operand splitting (csrc/mlp_gemm.cu): three tensor-core products per term give the
+reference's fp32 result to ~1e-6 (plain TF32 or BF16 would miss it by ~1e-3), forward and backward.
+
+Data flow (P points, everything stays on the device, no torch compute on P-sized tensors):
+  gsr_mlp_embed       xyz -> embedding planes [P x 64] (+ transposed, when gradients are wanted)
+  gsr_mlp_gemm x 8    hidden layers: relu(A W^T + b) -> (hi, lo) planes = next layer's A operand (+ transposed planes)
+                      layer 0 folds the time embedding (one value per view) into its bias; layer 5 reads [embedding | hidden]
+  gsr_mlp_gemm        the four heads as one [58 x 256] GEMM -> fp32 [P x 64]
+backward, per layer:  dA = dZ W masked by the ReLU of the layer below (+ column sums = bias gradient), and
+                      dW += dZ^T A as a split-K GEMM over the points with an atomic epilogue;
+  gsr_mlp_embed_backward  d embedding -> d xyz.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+import gsr_runtime as _rt
+
+EMBED = 64          # 63 embedded position channels + 1 zero column (TMA rows are 16-byte multiples)
+HEADS = 58          # 3 + 3 + 4 + 48
+_SPLIT_K = 1024         # points per tile of a weight-gradient GEMM: the tensor core accumulates with truncation, so a long
+                        # accumulation drifts (measured 1e-5 of max at K = 1350, 6e-5 at 6800); 1024 keeps it at fp32 level
+
+
+def _planes(x):
+    """(hi, lo) planes of a small fp32 tensor (weights)."""
+    lib = _rt.load()
+    x = x.detach().contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _rt.check(lib.gsr_mlp_split(x.data_ptr(), x.numel(), hi.data_ptr(), lo.data_ptr(), _rt.stream_ptr(x.device)))
+    return hi, lo
+
+
+def time_embedding(t, num_freqs=10):
+    """Embedder.embed (gaussian_model.py:62-63) of one time value: [t, sin(t 2^0), cos(t 2^0), ...] (21 values)."""
+    t = torch.as_tensor(t, dtype=torch.float32).reshape(1)
+    out = [t]
+    for k in range(num_freqs):
+        f = torch.tensor(2.0 ** k, dtype=torch.float32, device=t.device)
+        out += [torch.sin(t * f), torch.cos(t * f)]
+    return torch.cat(out)
+
+
+class _Gemm:
+    """One gsr_mlp_gemm call; keeps the argument struct readable."""
+
+    @staticmethod
+    def run(dev, M, N, A0, K0, B, mode, *, A1=None, K1=0, bias=None, mask=None, out=None, outT=None, ld_out=None,
+            ld_outT=0, colsum=None, k_splits=1, err=None, ldA0=None, ldA1=None, ldB=None, out_ptr_offset=0):
+        lib = _rt.load()
+        g = _rt.gsr_gemm()
+        g.M, g.N = int(M), int(N)
+        g.A0_hi, g.A0_lo, g.K0 = A0[0].data_ptr(), A0[1].data_ptr(), int(K0)
+        g.ldA0 = int(ldA0 if ldA0 is not None else A0[0].stride(0))
+        if A1 is not None:
+            g.A1_hi, g.A1_lo, g.K1 = A1[0].data_ptr(), A1[1].data_ptr(), int(K1)
+            g.ldA1 = int(ldA1 if ldA1 is not None else A1[0].stride(0))
+        g.B_hi, g.B_lo = B[0].data_ptr(), B[1].data_ptr()
+        g.ldB = int(ldB if ldB is not None else B[0].stride(0))
+        g.mode, g.k_splits = int(mode), int(k_splits)
+        if bias is not None:
+            g.bias = bias.data_ptr()
+        if mask is not None:
+            g.mask_src, g.ld_mask = mask.data_ptr(), int(mask.stride(0))
+        if isinstance(out, tuple):
+            g.out_hi, g.out_lo = out[0].data_ptr(), out[1].data_ptr()
+            g.ld_out = int(ld_out if ld_out is not None else out[0].stride(0))
+        else:
+            g.out_hi = out.data_ptr() + 4 * int(out_ptr_offset)
+            g.ld_out = int(ld_out if ld_out is not None else out.stride(0))
+        if outT is not None:
+            g.outT_hi, g.outT_lo, g.ld_outT = outT[0].data_ptr(), outT[1].data_ptr(), int(ld_outT)
+        if colsum is not None:
+            g.colsum = colsum.data_ptr()
+        if err is not None:
+            g.error_flag = err.data_ptr()
+        _rt.check(lib.gsr_mlp_gemm(ctypes.byref(g), _rt.stream_ptr(dev)))
+
+
+def _pack_weights(weights, biases, te, in_pts, n_layers):
+    """The network's parameters in the layout the GEMMs read.  Returns (per-layer dicts, packed head weight, head bias).
+    Layer 0: [256 x 84] -> position part [256 x 64] (column 63 zero) with the time part folded into the bias;
+    the skip layer [256 x (63 + 256)] -> [256 x (64 + 256)] with a zero column at 63."""
+    packed = []
+    for i in range(n_layers):
+        W, b = weights[i].detach(), biases[i].detach()
+        if i == 0:
+            Wp = torch.zeros((W.shape[0], EMBED), dtype=torch.float32, device=W.device)
+            Wp[:, :in_pts] = W[:, :in_pts]
+            beff = b + W[:, in_pts:] @ te
+            packed.append(dict(W=Wp, b=beff.contiguous(), skip=False))
+        elif W.shape[1] > W.shape[0]:
+            Wp = torch.zeros((W.shape[0], EMBED + W.shape[0]), dtype=torch.float32, device=W.device)
+            Wp[:, :in_pts] = W[:, :in_pts]
+            Wp[:, EMBED:] = W[:, in_pts:]
+            packed.append(dict(W=Wp, b=b.contiguous(), skip=True))
+        else:
+            packed.append(dict(W=W.contiguous(), b=b.contiguous(), skip=False))
+    Wh = torch.cat([w.detach() for w in weights[n_layers:]], 0).contiguous()      # [58 x 256]
+    bh = torch.cat([b.detach() for b in biases[n_layers:]], 0).contiguous()
+    return packed, Wh, bh
+
+
+class _DeformMLPFn(torch.autograd.Function):
+    """forward(x [P,3], te [21], head_sizes, *weights (L layers + heads), *biases) -> fp32 [P x 64] (heads in the first
+    sum(head_sizes) columns)."""
+
+    @staticmethod
+    def forward(ctx, x, te, head_sizes, n_layers, *wb):
+        lib = _rt.load()
+        if not x.is_cuda:
+            raise _rt.GsrError("deform_mlp runs on CUDA tensors only (no CPU fallback)")
+        n_w = n_layers + len(head_sizes)
+        weights, biases = wb[:n_w], wb[n_w:]
+        dev = x.device
+        P = int(x.shape[0])
+        Wd = int(weights[0].shape[0])                       # 256
+        in_pts = int(weights[0].shape[1]) - int(te.numel())
+        need_grad = any(ctx.needs_input_grad)
+        f32 = dict(dtype=torch.float32, device=dev)
+        Pp = (P + 3) // 4 * 4
+        x_c = x.detach().float().contiguous()
+        packed, Wh, bh = _pack_weights(weights, biases, te.detach().to(dev), in_pts, n_layers)
+        n_heads = int(Wh.shape[0])
+        st = _rt.stream_ptr(dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            E = (torch.empty((P, EMBED), **f32), torch.empty((P, EMBED), **f32))
+            ET = (torch.empty((EMBED, Pp), **f32), torch.empty((EMBED, Pp), **f32)) if need_grad else None
+            _rt.check(lib.gsr_mlp_embed(x_c.data_ptr(), P, E[0].data_ptr(), E[1].data_ptr(),
+                                        ET[0].data_ptr() if ET else None, ET[1].data_ptr() if ET else None, Pp, st))
+            acts, actsT = [], []
+            prev = None
+            pool = [] if need_grad else [(torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32)) for _ in range(2)]
+            for i, L in enumerate(packed):
+                Wp = _planes(L["W"])
+                H = (torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32)) if need_grad else pool[i & 1]
+                HT = (torch.empty((Wd, Pp), **f32), torch.empty((Wd, Pp), **f32)) if need_grad else None
+                if i == 0:
+                    _Gemm.run(dev, P, Wd, E, EMBED, Wp, _rt.GEMM_RELU_SPLIT, bias=L["b"], out=H, outT=HT, ld_outT=Pp, err=err)
+                elif L["skip"]:
+                    _Gemm.run(dev, P, Wd, E, EMBED, Wp, _rt.GEMM_RELU_SPLIT, A1=prev, K1=Wd, bias=L["b"], out=H, outT=HT,
+                              ld_outT=Pp, err=err)
+                else:
+                    _Gemm.run(dev, P, Wd, prev, Wd, Wp, _rt.GEMM_RELU_SPLIT, bias=L["b"], out=H, outT=HT, ld_outT=Pp, err=err)
+                prev = H
+                if need_grad:
+                    acts.append(H); actsT.append(HT)
+            out = torch.empty((P, EMBED), **f32)
+            if n_heads < EMBED:
+                out[:, n_heads:].zero_()
+            _Gemm.run(dev, P, n_heads, prev, Wd, _planes(Wh), _rt.GEMM_PLAIN, bias=bh, out=out, err=err)
+        ctx.err = err
+        if need_grad:
+            ctx.state = dict(x=x_c, te=te.detach().to(dev), E=E, ET=ET, acts=acts, actsT=actsT, packed=packed, Wh=Wh, P=P, Pp=Pp,
+                             Wd=Wd, in_pts=in_pts, n_layers=n_layers, n_heads=n_heads, head_sizes=tuple(head_sizes),
+                             shapes=[tuple(w.shape) for w in weights])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _rt.load()
+        s = ctx.state
+        dev = g_out.device
+        P, Pp, Wd, n_heads, n_layers = s["P"], s["Pp"], s["Wd"], s["n_heads"], s["n_layers"]
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = _rt.stream_ptr(dev)
+        err = ctx.err
+        g = g_out.float()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        splits = max(74, (P + _SPLIT_K - 1) // _SPLIT_K)
+        with torch.cuda.device(dev):
+            # dL/d heads -> operand planes (+ transposed) and the head biases' gradient
+            dO = (torch.empty((P, EMBED), **f32), torch.empty((P, EMBED), **f32))
+            dOT = (torch.empty((EMBED, Pp), **f32), torch.empty((EMBED, Pp), **f32))
+            db_heads = torch.zeros(EMBED, **f32)
+            _rt.check(lib.gsr_mlp_prepare(g.data_ptr(), P, EMBED, g.stride(0), dO[0].data_ptr(), dO[1].data_ptr(), EMBED,
+                                          dOT[0].data_ptr(), dOT[1].data_ptr(), Pp, db_heads.data_ptr(), st))
+            acts, actsT, E, ET = s["acts"], s["actsT"], s["E"], s["ET"]
+            # heads: dWh = dO^T H_last ; dZ_last = (dO Wh) masked by relu(H_last)
+            dWh = torch.zeros((n_heads, Wd), **f32)
+            _Gemm.run(dev, n_heads, Wd, dOT, P, actsT[-1], _rt.GEMM_ATOMIC, out=dWh, k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+            WhT = torch.zeros((Wd, EMBED), **f32)
+            WhT[:, :n_heads] = s["Wh"].t()
+            dZ = (torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32))
+            dZT = (torch.empty((Wd, Pp), **f32), torch.empty((Wd, Pp), **f32))
+            dZ2 = (torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32))
+            dZT2 = (torch.empty((Wd, Pp), **f32), torch.empty((Wd, Pp), **f32))
+            db = [torch.zeros(Wd, **f32) for _ in range(n_layers)]
+            dWp = [torch.zeros_like(L["W"]) for L in s["packed"]]
+            dE = torch.zeros((P, EMBED), **f32)
+            _Gemm.run(dev, P, Wd, dO, EMBED, _planes(WhT), _rt.GEMM_SPLIT, mask=acts[-1][0], out=dZ, outT=dZT, ld_outT=Pp,
+                      colsum=db[n_layers - 1], err=err)
+            for i in range(n_layers - 1, -1, -1):
+                L = s["packed"][i]
+                # weight gradient of layer i: dZ_i^T [256 x P] . input_i^T
+                if i == 0:
+                    _Gemm.run(dev, Wd, EMBED, dZT, P, ET, _rt.GEMM_ATOMIC, out=dWp[i], k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+                elif L["skip"]:
+                    _Gemm.run(dev, Wd, EMBED, dZT, P, ET, _rt.GEMM_ATOMIC, out=dWp[i], ld_out=EMBED + Wd, k_splits=splits,
+                              ldA0=Pp, ldB=Pp, err=err)
+                    _Gemm.run(dev, Wd, Wd, dZT, P, actsT[i - 1], _rt.GEMM_ATOMIC, out=dWp[i], ld_out=EMBED + Wd,
+                              out_ptr_offset=EMBED, k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+                else:
+                    _Gemm.run(dev, Wd, Wd, dZT, P, actsT[i - 1], _rt.GEMM_ATOMIC, out=dWp[i], k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+                # input gradient of layer i
+                WT = L["W"].t().contiguous()                      # [K_in x 256]
+                if i == 0:
+                    _Gemm.run(dev, P, EMBED, dZ, Wd, _planes(WT), _rt.GEMM_ATOMIC, out=dE, err=err)
+                else:
+                    if L["skip"]:
+                        _Gemm.run(dev, P, EMBED, dZ, Wd, _planes(WT[:EMBED].contiguous()), _rt.GEMM_ATOMIC, out=dE, err=err)
+                        WT = WT[EMBED:].contiguous()
+                    _Gemm.run(dev, P, Wd, dZ, Wd, _planes(WT), _rt.GEMM_SPLIT, mask=acts[i - 1][0], out=dZ2, outT=dZT2,
+                              ld_outT=Pp, colsum=db[i - 1], err=err)
+                    dZ, dZ2, dZT, dZT2 = dZ2, dZ, dZT2, dZT
+            dx = torch.empty((P, 3), **f32)
+            _rt.check(lib.gsr_mlp_embed_backward(s["x"].data_ptr(), P, dE.data_ptr(), dx.data_ptr(), 0, st))
+        # unpack the padded layouts into the parameters' own shapes (0.5 M values in total)
+        in_pts, te = s["in_pts"], s["te"]
+        gw, gb = [], []
+        for i, L in enumerate(s["packed"]):
+            if i == 0:
+                gw.append(torch.cat([dWp[i][:, :in_pts], torch.outer(db[i], te)], 1))
+            elif L["skip"]:
+                gw.append(torch.cat([dWp[i][:, :in_pts], dWp[i][:, EMBED:]], 1))
+            else:
+                gw.append(dWp[i])
+            gb.append(db[i])
+        o = 0
+        for hs in s["head_sizes"]:
+            gw.append(dWh[o:o + hs]); gb.append(db_heads[o:o + hs]); o += hs
+        ctx.state = None
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, *gw, *gb)
+
+
+def _check_pipeline(err):
+    if int(err.item()) != 0:
+        raise _rt.GsrError("deform_mlp: a tensor-core pipeline wait timed out (workspace corrupted?)")
+
+
+class _Trunk(nn.Module):
+    """Shared construction: `_time` = 8 linears (the skip layer takes the embedded position in front), same order of
+    nn.Linear construction as the reference so that the same seed gives the same initial weights."""
+
+    def _build(self, D, W, in_pts, in_time, skips):
+        layers = [nn.Linear(in_pts + in_time, W)]
+        for i in range(D - 1):
+            layers += [nn.Linear(W + (in_pts if i in skips else 0), W)]
+        return nn.ModuleList(layers)
+
+    def _run(self, x, te, heads, check=False):
+        weights = [l.weight for l in self._time] + [h.weight for h in heads]
+        biases = [l.bias for l in self._time] + [h.bias for h in heads]
+        sizes = tuple(int(h.weight.shape[0]) for h in heads)
+        out = _DeformMLPFn.apply(x, te, sizes, len(self._time), *weights, *biases)
+        return out
+
+
+class DirectTemporalNeRF(_Trunk):
+    """scene/gaussian_model.py:242-316 (constructor arguments kept; only D = 8, W = 256, skips = [4] are built natively)."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, input_ch_time=1, output_ch=4, skips=[4],
+                 use_viewdirs=False, memory=[], embed_fn=None, zero_canonical=True):
+        super().__init__()
+        if memory:
+            raise NotImplementedError
+        if W % 32 or (len(skips) > 1):
+            raise _rt.GsrError("deform_mlp: width must be a multiple of 32 with at most one skip layer")
+        self.D, self.W, self.skips = D, W, list(skips)
+        self.input_ch = input_ch * 21                  # get_embedder(10, input_ch, 0)
+        self.input_ch_time = 21                        # get_embedder(10, 1, 0)
+        if self.input_ch != 63:
+            raise _rt.GsrError("deform_mlp: the native embedding handles 3-D positions")
+        self.input_ch_views, self.use_viewdirs, self.memory, self.zero_canonical = input_ch_views, use_viewdirs, memory, zero_canonical
+        self._time = self._build(D, W, self.input_ch, self.input_ch_time, self.skips)
+        self._time_out = nn.Linear(W, 3)
+        self._time_out_scale = nn.Linear(W, 3)
+        self._time_out_rot = nn.Linear(W, 4)
+        self._time_out_shs = nn.Linear(W, 48)
+
+    def forward(self, x, ts, iteration):
+        # gaussian_model.py:303: "Only accepts all points from same time"
+        if torch.is_tensor(ts):
+            t0 = ts.reshape(-1)[:1]
+            assert bool((ts[:, :1] == t0).all()), "Only accepts all points from same time"
+            te = time_embedding(t0.detach().float().to(x.device))         # same torch sin / cos kernels as the reference's embedder
+        else:
+            te = time_embedding(float(ts)).to(x.device)
+        n = x.shape[0]
+        if iteration < 3000:                            # gaussian_model.py:305-310: the network's output is discarded
+            z = lambda c: torch.zeros((n, c), dtype=torch.float32, device=x.device)
+            return z(3), z(3), z(4), z(48)
+        out = self._run(x, te, [self._time_out, self._time_out_scale, self._time_out_rot, self._time_out_shs])
+        return out[:, 0:3], out[:, 3:6], out[:, 6:10], out[:, 10:58]
+
+
+def screw_from_raw(w_raw, v_raw, eps=0.0):
+    """gaussian_model.py:161-164: theta = |w|, S = (w, v) / theta.  The reference has no guard (theta = 0 gives NaN);
+    with eps > 0 points whose |w| <= eps get the identity (S = 0, theta = 0) instead."""
+    theta = torch.norm(w_raw, dim=-1)
+    if eps > 0.0:
+        ok = theta > eps
+        safe = torch.where(ok, theta, torch.ones_like(theta))
+        S = torch.cat([w_raw, v_raw], -1) / safe[..., None] * ok[..., None]
+        return S, theta * ok
+    return torch.cat([w_raw / theta[..., None], v_raw / theta[..., None]], dim=-1), theta
+
+
+class DirectTemporalNeRF_se3(_Trunk):
+    """scene/gaussian_model.py:99-173.  `forward` returns the [N,4,4] transforms like the reference (through the drop-in
+    rigid_body.exp_se3); `screw(x, ts)` returns (S [N,6], theta [N]) for the rasterizer's fused SE3 inputs
+    (GaussianRasterizer(..., se3_S=S, se3_theta=theta)), which never materialises the transforms.
+    The native trunk takes 3-D positions and one time per call and embeds them itself (input_ch 63 / input_ch_time 21 is
+    what the reference's own embedders produce for it)."""
+
+    def __init__(self, D=8, W=256, input_ch=63, input_ch_views=3, input_ch_time=21, output_ch=4, skips=[4],
+                 use_viewdirs=False, memory=[], embed_fn=None, zero_canonical=True, theta_eps=0.0):
+        super().__init__()
+        if memory:
+            raise NotImplementedError
+        if input_ch != 63 or input_ch_time != 21:
+            raise _rt.GsrError("deform_mlp: the native se3 trunk is built for the embedded inputs (63 + 21 channels)")
+        self.D, self.W, self.skips, self.input_ch, self.input_ch_time = D, W, list(skips), input_ch, input_ch_time
+        self.theta_eps = theta_eps
+        self._time = self._build(D, W, input_ch, input_ch_time, self.skips)
+        self._w = nn.Linear(W, 3)
+        self._v = nn.Linear(W, 3)
+
+    def raw_heads(self, x, ts):
+        """(w_raw [N,3], v_raw [N,3]) = query_time (gaussian_model.py:141-150).  `x` is either the positions [N,3] or, as
+        the reference's forward takes it, their embedding [N,63] (whose first three channels ARE the positions:
+        include_input=True, gaussian_model.py:43-45); likewise `ts` is a time, [N,1] times or their [N,21] embedding."""
+        if x.shape[1] == self.input_ch and self.input_ch != 3:
+            x = x[:, :3]
+        t0 = ts.reshape(-1)[:1].detach().float().to(x.device) if torch.is_tensor(ts) else float(ts)
+        te = time_embedding(t0).to(x.device)
+        out = self._run(x, te, [self._w, self._v])
+        return out[:, 0:3], out[:, 3:6]
+
+    def screw(self, x, ts):
+        w, v = self.raw_heads(x, ts)
+        return screw_from_raw(w, v, self.theta_eps)
+
+    def forward(self, x, ts, iteration):
+        import rigid_body
+        S, theta = self.screw(x, ts)
+        if iteration < 3000:                             # gaussian_model.py:169-171 (returns [N,3] zeros: the reference's shape bug, kept)
+            return torch.zeros((x.shape[0], 3), dtype=torch.float32, device=x.device)
+        return rigid_body.exp_se3(S, theta)

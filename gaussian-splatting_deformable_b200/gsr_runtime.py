@@ -100,6 +100,7 @@ _SIGNATURES = {
     "gsr_mlp_gemm": (ctypes.c_int, [ctypes.POINTER(gsr_gemm), _P]),
     "gsr_mlp_split": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P, _P]),
     "gsr_mlp_split_transpose": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, ctypes.c_int, _P]),
+    "gsr_mlp_prepare": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P]),
     "gsr_mlp_embed": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, _P, ctypes.c_int64, _P]),
     "gsr_mlp_embed_backward": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, ctypes.c_int, _P]),
     "gsr_mark_visible": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, _P, _P, _P]),

@@ -219,6 +219,10 @@ int gsr_mlp_gemm(const gsr_gemm* g, void* stream);
 int gsr_mlp_split(const float* x, int64_t n, float* hi, float* lo, void* stream);
 /* x [rows x cols] (row stride ld_in) -> planes of x^T [cols x ldT] */
 int gsr_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float* hi, float* lo, int ldT, void* stream);
+/* x [rows x cols] (row stride ld_in) -> any of: row-major planes [rows x ld_out], transposed planes [cols x ldT],
+ * colsum[c] += column sums.  Prepares a gradient that arrives from autograd as a GEMM operand. */
+int gsr_mlp_prepare(const float* x, int rows, int cols, int64_t ld_in, float* hi, float* lo, int64_t ld_out, float* hiT,
+                    float* loT, int64_t ldT, float* colsum, void* stream);
 /* positions [P,3] -> embedding planes [P x 64] (63 values, column 63 zero) and, optionally, transposed [64 x ldT] */
 int gsr_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, int64_t ldT, void* stream);
 int gsr_mlp_embed_backward(const float* xyz, int P, const float* d_embed /*[P x 64]*/, float* dxyz, int accumulate, void* stream);
