@@ -517,10 +517,9 @@ int gsr_mlp_gemm(const gsr_gemm* g, void* stream_) {
     a.mode = g->mode; a.k_splits = g->k_splits; a.bias = g->bias; a.mask_src = g->mask_src; a.ld_mask = g->ld_mask;
     a.out_hi = g->out_hi; a.out_lo = g->out_lo; a.ld_out = g->ld_out;
     a.outT_hi = g->outT_hi; a.outT_lo = g->outT_lo; a.ld_outT = g->ld_outT;
-    a.colsum = g->colsum; a.error_flag = g->error_flag;
+    a.colsum = g->colsum; a.error_flag = g->error_flag; a.mn_major = g->mn_major;
     a.prof_name = g->mode == GSR_GEMM_ATOMIC ? "mlp_gemm_dw" : (g->mask_src ? "mlp_gemm_dx" : "mlp_gemm_fwd");
     if (a.mode < 0 || a.mode > 3) return gsr_set_error_msg(-2, "mlp_gemm: unknown epilogue mode");
-    if ((a.A1_hi == nullptr) != (a.A1_lo == nullptr)) return gsr_set_error_msg(-1, "mlp_gemm: second A segment needs both planes");
     return gsr_launch_mlp_gemm(a, (cudaStream_t)stream_);
 }
 int gsr_mlp_split(const float* x, int64_t n, float* hi, float* lo, void* stream_) {
@@ -534,13 +533,12 @@ int gsr_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float
 int gsr_mlp_prepare(const float* x, int rows, int cols, int64_t ld_in, float* hi, float* lo, int64_t ld_out, float* hiT,
                     float* loT, int64_t ldT, float* colsum, void* stream_) {
     if (rows > 0 && cols > 0 && !x) return gsr_set_error_msg(-1, "mlp_prepare: NULL input");
-    if ((hi == nullptr) != (lo == nullptr) || (hiT == nullptr) != (loT == nullptr))
-        return gsr_set_error_msg(-1, "mlp_prepare: planes come in (hi, lo) pairs");
+    if ((lo && !hi) || (loT && !hiT)) return gsr_set_error_msg(-1, "mlp_prepare: a lo plane needs its hi plane");
     return gsr_launch_mlp_prepare(x, rows, cols, ld_in, hi, lo, ld_out, hiT, loT, ldT, colsum, (cudaStream_t)stream_);
 }
 int gsr_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, int64_t ldT, void* stream_) {
-    if (P > 0 && (!xyz || !e_hi || !e_lo)) return gsr_set_error_msg(-1, "mlp_embed: NULL pointer");
-    if ((eT_hi == nullptr) != (eT_lo == nullptr)) return gsr_set_error_msg(-1, "mlp_embed: give both transposed planes or neither");
+    if (P > 0 && (!xyz || !e_hi)) return gsr_set_error_msg(-1, "mlp_embed: NULL pointer");
+    if (eT_lo && !eT_hi) return gsr_set_error_msg(-1, "mlp_embed: a lo plane needs its hi plane");
     return gsr_launch_mlp_embed(xyz, P, e_hi, e_lo, eT_hi, eT_lo, ldT, (cudaStream_t)stream_);
 }
 int gsr_mlp_embed_backward(const float* xyz, int P, const float* d_embed, float* dxyz, int accumulate, void* stream_) {

@@ -182,12 +182,14 @@ int gsr_launch_knn_dist2(int P, const float* points, float* mean_dist2, void* te
                          cudaStream_t stream);
 
 // ---- deformation-network GEMMs on tcgen05 (mlp_gemm.cu) -----------------------------------
-// C[M x N] = epilogue(A[M x K] . B[N x K]^T), every operand as (hi, lo) fp32 planes (x = hi + lo, hi a TF32 value):
-// three kind::tf32 MMAs per product give an fp32-grade result.  A may be the concatenation of two K segments
-// (the skip connection: [embedding | hidden]).  K-major operands only: A row stride ldA, B row stride ldB.
-#define GSR_GEMM_RELU_SPLIT 0   // v = relu(acc + bias)        -> (hi, lo) planes row-major (+ transposed planes)
-#define GSR_GEMM_SPLIT 1        // v = (acc + bias) [* mask]   -> (hi, lo) planes row-major (+ transposed planes)
-#define GSR_GEMM_PLAIN 2        // v = (acc + bias) [* mask]   -> fp32 [M x ld_out] in out_hi
+// C[M x N] = epilogue(A[M x K] . B[N x K]^T); every operand enters the tensor core as x = hi + lo (hi a TF32 value) and
+// three kind::tf32 MMAs per product give an fp32-grade result.  An operand is given either as ONE fp32 plane (*_lo ==
+// null: split in shared memory by the kernel) or as pre-split (hi, lo) planes.  A may be the concatenation of two K
+// segments (the skip connection: [embedding | hidden]).  K-major operands only: A row stride ldA, B row stride ldB.
+// Outputs: out_lo == null -> one fp32 plane in out_hi; else (hi, lo) planes.  Same for the transposed copy outT_*.
+#define GSR_GEMM_RELU_SPLIT 0   // v = relu(acc + bias)
+#define GSR_GEMM_SPLIT 1        // v = (acc + bias) [masked]
+#define GSR_GEMM_PLAIN 2        // v = (acc + bias) [masked]   (same as 1; kept for callers that name the fp32 output)
 #define GSR_GEMM_ATOMIC 3       // out_hi[M x ld_out] += acc   (split-K partial sums, weight gradients)
 struct GsrGemmArgs {
     int M, N;
@@ -202,6 +204,7 @@ struct GsrGemmArgs {
     float* outT_hi; float* outT_lo; long long ld_outT;   // transposed planes [N x ld_outT] or null
     float* colsum;                // [N] += column sums of the stored values (bias gradients) or null
     uint32_t* error_flag;         // device word, set if a pipeline wait timed out
+    int mn_major;                 // 1: A0_hi is [K0 x M] and B_hi is [K0 x N] row-major single planes (C += A^T B, atomic mode)
     const char* prof_name;
 };
 int gsr_launch_mlp_gemm(const GsrGemmArgs& g, cudaStream_t stream);

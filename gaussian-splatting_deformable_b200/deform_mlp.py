@@ -12,12 +12,13 @@ Same class names, constructor defaults, parameter names (`_time.N.weight`, `_tim
 reference's fp32 result to ~1e-6 (plain TF32 or BF16 would miss it by ~1e-3), forward and backward.
 
 Data flow (P points, everything stays on the device, no torch compute on P-sized tensors):
-  gsr_mlp_embed       xyz -> embedding planes [P x 64] (+ transposed, when gradients are wanted)
-  gsr_mlp_gemm x 8    hidden layers: relu(A W^T + b) -> (hi, lo) planes = next layer's A operand (+ transposed planes)
+  gsr_mlp_embed       xyz -> embedding [P x 64]
+  gsr_mlp_gemm x 8    hidden layers: relu(A W^T + b) -> fp32 [P x 256] = next layer's A operand
                       layer 0 folds the time embedding (one value per view) into its bias; layer 5 reads [embedding | hidden]
   gsr_mlp_gemm        the four heads as one [58 x 256] GEMM -> fp32 [P x 64]
 backward, per layer:  dA = dZ W masked by the ReLU of the layer below (+ column sums = bias gradient), and
-                      dW += dZ^T A as a split-K GEMM over the points with an atomic epilogue;
+                      dW += dZ^T A as a split-K GEMM over the points (both operands read row-major as MN-major tensor-core
+                      operands: no transposed copies) with an atomic epilogue;
   gsr_mlp_embed_backward  d embedding -> d xyz.
 """
 import ctypes
@@ -57,17 +58,21 @@ class _Gemm:
 
     @staticmethod
     def run(dev, M, N, A0, K0, B, mode, *, A1=None, K1=0, bias=None, mask=None, out=None, outT=None, ld_out=None,
-            ld_outT=0, colsum=None, k_splits=1, err=None, ldA0=None, ldA1=None, ldB=None, out_ptr_offset=0):
+            ld_outT=0, colsum=None, k_splits=1, err=None, ldA0=None, ldA1=None, ldB=None, out_ptr_offset=0, mn_major=False):
         lib = _rt.load()
         g = _rt.gsr_gemm()
         g.M, g.N = int(M), int(N)
-        g.A0_hi, g.A0_lo, g.K0 = A0[0].data_ptr(), A0[1].data_ptr(), int(K0)
-        g.ldA0 = int(ldA0 if ldA0 is not None else A0[0].stride(0))
+        pl = lambda t: (t[0], t[1]) if isinstance(t, tuple) else (t, None)       # (hi, lo) planes, or ONE fp32 plane
+        a0, a0l = pl(A0)
+        g.A0_hi, g.A0_lo, g.K0 = a0.data_ptr(), (a0l.data_ptr() if a0l is not None else None), int(K0)
+        g.ldA0 = int(ldA0 if ldA0 is not None else a0.stride(0))
         if A1 is not None:
-            g.A1_hi, g.A1_lo, g.K1 = A1[0].data_ptr(), A1[1].data_ptr(), int(K1)
-            g.ldA1 = int(ldA1 if ldA1 is not None else A1[0].stride(0))
-        g.B_hi, g.B_lo = B[0].data_ptr(), B[1].data_ptr()
-        g.ldB = int(ldB if ldB is not None else B[0].stride(0))
+            a1, a1l = pl(A1)
+            g.A1_hi, g.A1_lo, g.K1 = a1.data_ptr(), (a1l.data_ptr() if a1l is not None else None), int(K1)
+            g.ldA1 = int(ldA1 if ldA1 is not None else a1.stride(0))
+        b, bl = pl(B)
+        g.B_hi, g.B_lo = b.data_ptr(), (bl.data_ptr() if bl is not None else None)
+        g.ldB = int(ldB if ldB is not None else b.stride(0))
         g.mode, g.k_splits = int(mode), int(k_splits)
         if bias is not None:
             g.bias = bias.data_ptr()
@@ -80,11 +85,13 @@ class _Gemm:
             g.out_hi = out.data_ptr() + 4 * int(out_ptr_offset)
             g.ld_out = int(ld_out if ld_out is not None else out.stride(0))
         if outT is not None:
-            g.outT_hi, g.outT_lo, g.ld_outT = outT[0].data_ptr(), outT[1].data_ptr(), int(ld_outT)
+            t, tl = pl(outT)
+            g.outT_hi, g.outT_lo, g.ld_outT = t.data_ptr(), (tl.data_ptr() if tl is not None else None), int(ld_outT)
         if colsum is not None:
             g.colsum = colsum.data_ptr()
         if err is not None:
             g.error_flag = err.data_ptr()
+        g.mn_major = 1 if mn_major else 0
         _rt.check(lib.gsr_mlp_gemm(ctypes.byref(g), _rt.stream_ptr(dev)))
 
 
@@ -113,11 +120,11 @@ def _pack_weights(weights, biases, te, in_pts, n_layers):
 
 
 class _DeformMLPFn(torch.autograd.Function):
-    """forward(x [P,3], te [21], head_sizes, *weights (L layers + heads), *biases) -> fp32 [P x 64] (heads in the first
+    """forward(x [P,3], te [21], head_sizes, n_layers, grad_mode, *weights (L layers + heads), *biases) -> fp32 [P x 64] (heads in the first
     sum(head_sizes) columns)."""
 
     @staticmethod
-    def forward(ctx, x, te, head_sizes, n_layers, *wb):
+    def forward(ctx, x, te, head_sizes, n_layers, grad_mode, *wb):
         lib = _rt.load()
         if not x.is_cuda:
             raise _rt.GsrError("deform_mlp runs on CUDA tensors only (no CPU fallback)")
@@ -127,7 +134,7 @@ class _DeformMLPFn(torch.autograd.Function):
         P = int(x.shape[0])
         Wd = int(weights[0].shape[0])                       # 256
         in_pts = int(weights[0].shape[1]) - int(te.numel())
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)      # (grad mode is always off INSIDE forward)
         f32 = dict(dtype=torch.float32, device=dev)
         Pp = (P + 3) // 4 * 4
         x_c = x.detach().float().contiguous()
@@ -136,34 +143,31 @@ class _DeformMLPFn(torch.autograd.Function):
         st = _rt.stream_ptr(dev)
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            E = (torch.empty((P, EMBED), **f32), torch.empty((P, EMBED), **f32))
-            ET = (torch.empty((EMBED, Pp), **f32), torch.empty((EMBED, Pp), **f32)) if need_grad else None
-            _rt.check(lib.gsr_mlp_embed(x_c.data_ptr(), P, E[0].data_ptr(), E[1].data_ptr(),
-                                        ET[0].data_ptr() if ET else None, ET[1].data_ptr() if ET else None, Pp, st))
-            acts, actsT = [], []
+            # activations travel as ONE fp32 plane each (the consumer GEMM splits its tiles in shared memory)
+            E = torch.empty((P, EMBED), **f32)
+            _rt.check(lib.gsr_mlp_embed(x_c.data_ptr(), P, E.data_ptr(), None, None, None, 0, st))
+            acts = []
             prev = None
-            pool = [] if need_grad else [(torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32)) for _ in range(2)]
+            pool = [] if need_grad else [torch.empty((P, Wd), **f32) for _ in range(2)]
             for i, L in enumerate(packed):
                 Wp = _planes(L["W"])
-                H = (torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32)) if need_grad else pool[i & 1]
-                HT = (torch.empty((Wd, Pp), **f32), torch.empty((Wd, Pp), **f32)) if need_grad else None
+                H = torch.empty((P, Wd), **f32) if need_grad else pool[i & 1]
                 if i == 0:
-                    _Gemm.run(dev, P, Wd, E, EMBED, Wp, _rt.GEMM_RELU_SPLIT, bias=L["b"], out=H, outT=HT, ld_outT=Pp, err=err)
+                    _Gemm.run(dev, P, Wd, E, EMBED, Wp, _rt.GEMM_RELU_SPLIT, bias=L["b"], out=H, err=err)
                 elif L["skip"]:
-                    _Gemm.run(dev, P, Wd, E, EMBED, Wp, _rt.GEMM_RELU_SPLIT, A1=prev, K1=Wd, bias=L["b"], out=H, outT=HT,
-                              ld_outT=Pp, err=err)
+                    _Gemm.run(dev, P, Wd, E, EMBED, Wp, _rt.GEMM_RELU_SPLIT, A1=prev, K1=Wd, bias=L["b"], out=H, err=err)
                 else:
-                    _Gemm.run(dev, P, Wd, prev, Wd, Wp, _rt.GEMM_RELU_SPLIT, bias=L["b"], out=H, outT=HT, ld_outT=Pp, err=err)
+                    _Gemm.run(dev, P, Wd, prev, Wd, Wp, _rt.GEMM_RELU_SPLIT, bias=L["b"], out=H, err=err)
                 prev = H
                 if need_grad:
-                    acts.append(H); actsT.append(HT)
+                    acts.append(H)
             out = torch.empty((P, EMBED), **f32)
             if n_heads < EMBED:
                 out[:, n_heads:].zero_()
             _Gemm.run(dev, P, n_heads, prev, Wd, _planes(Wh), _rt.GEMM_PLAIN, bias=bh, out=out, err=err)
         ctx.err = err
         if need_grad:
-            ctx.state = dict(x=x_c, te=te.detach().to(dev), E=E, ET=ET, acts=acts, actsT=actsT, packed=packed, Wh=Wh, P=P, Pp=Pp,
+            ctx.state = dict(x=x_c, te=te.detach().to(dev), E=E, acts=acts, packed=packed, Wh=Wh, P=P, Pp=Pp,
                              Wd=Wd, in_pts=in_pts, n_layers=n_layers, n_heads=n_heads, head_sizes=tuple(head_sizes),
                              shapes=[tuple(w.shape) for w in weights])
         return out
@@ -182,39 +186,36 @@ class _DeformMLPFn(torch.autograd.Function):
             g = g.contiguous()
         splits = max(74, (P + _SPLIT_K - 1) // _SPLIT_K)
         with torch.cuda.device(dev):
-            # dL/d heads -> operand planes (+ transposed) and the head biases' gradient
-            dO = (torch.empty((P, EMBED), **f32), torch.empty((P, EMBED), **f32))
-            dOT = (torch.empty((EMBED, Pp), **f32), torch.empty((EMBED, Pp), **f32))
+            # dL/d heads is already a K-major fp32 plane [P x 64]; its column sums are the head biases' gradient
+            if g.stride(0) % 4 or g.data_ptr() % 16:
+                g = g.contiguous()
+            dO = g
             db_heads = torch.zeros(EMBED, **f32)
-            _rt.check(lib.gsr_mlp_prepare(g.data_ptr(), P, EMBED, g.stride(0), dO[0].data_ptr(), dO[1].data_ptr(), EMBED,
-                                          dOT[0].data_ptr(), dOT[1].data_ptr(), Pp, db_heads.data_ptr(), st))
-            acts, actsT, E, ET = s["acts"], s["actsT"], s["E"], s["ET"]
+            _rt.check(lib.gsr_mlp_prepare(g.data_ptr(), P, EMBED, g.stride(0), None, None, 0, None, None, 0, db_heads.data_ptr(), st))
+            acts, E = s["acts"], s["E"]
+            # Weight gradients dW = dZ^T X read dZ [P x 256] and X [P x K_in] as they lie (row-major, the reduction runs over
+            # rows: MN-major tensor-core operands), split over the points with an atomic epilogue.
+            def weight_grad(dZ_, M_, X, N_, out, **kw):
+                _Gemm.run(dev, M_, N_, dZ_, P, X, _rt.GEMM_ATOMIC, out=out, k_splits=splits, mn_major=True, err=err, **kw)
             # heads: dWh = dO^T H_last ; dZ_last = (dO Wh) masked by relu(H_last)
             dWh = torch.zeros((n_heads, Wd), **f32)
-            _Gemm.run(dev, n_heads, Wd, dOT, P, actsT[-1], _rt.GEMM_ATOMIC, out=dWh, k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+            weight_grad(dO, n_heads, acts[-1], Wd, dWh)
             WhT = torch.zeros((Wd, EMBED), **f32)
             WhT[:, :n_heads] = s["Wh"].t()
-            dZ = (torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32))
-            dZT = (torch.empty((Wd, Pp), **f32), torch.empty((Wd, Pp), **f32))
-            dZ2 = (torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32))
-            dZT2 = (torch.empty((Wd, Pp), **f32), torch.empty((Wd, Pp), **f32))
+            dZ, dZ2 = torch.empty((P, Wd), **f32), torch.empty((P, Wd), **f32)
             db = [torch.zeros(Wd, **f32) for _ in range(n_layers)]
             dWp = [torch.zeros_like(L["W"]) for L in s["packed"]]
             dE = torch.zeros((P, EMBED), **f32)
-            _Gemm.run(dev, P, Wd, dO, EMBED, _planes(WhT), _rt.GEMM_SPLIT, mask=acts[-1][0], out=dZ, outT=dZT, ld_outT=Pp,
-                      colsum=db[n_layers - 1], err=err)
+            _Gemm.run(dev, P, Wd, dO, EMBED, _planes(WhT), _rt.GEMM_SPLIT, mask=acts[-1], out=dZ, colsum=db[n_layers - 1], err=err)
             for i in range(n_layers - 1, -1, -1):
                 L = s["packed"][i]
-                # weight gradient of layer i: dZ_i^T [256 x P] . input_i^T
                 if i == 0:
-                    _Gemm.run(dev, Wd, EMBED, dZT, P, ET, _rt.GEMM_ATOMIC, out=dWp[i], k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+                    weight_grad(dZ, Wd, E, EMBED, dWp[i])
                 elif L["skip"]:
-                    _Gemm.run(dev, Wd, EMBED, dZT, P, ET, _rt.GEMM_ATOMIC, out=dWp[i], ld_out=EMBED + Wd, k_splits=splits,
-                              ldA0=Pp, ldB=Pp, err=err)
-                    _Gemm.run(dev, Wd, Wd, dZT, P, actsT[i - 1], _rt.GEMM_ATOMIC, out=dWp[i], ld_out=EMBED + Wd,
-                              out_ptr_offset=EMBED, k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+                    weight_grad(dZ, Wd, E, EMBED, dWp[i], ld_out=EMBED + Wd)
+                    weight_grad(dZ, Wd, acts[i - 1], Wd, dWp[i], ld_out=EMBED + Wd, out_ptr_offset=EMBED)
                 else:
-                    _Gemm.run(dev, Wd, Wd, dZT, P, actsT[i - 1], _rt.GEMM_ATOMIC, out=dWp[i], k_splits=splits, ldA0=Pp, ldB=Pp, err=err)
+                    weight_grad(dZ, Wd, acts[i - 1], Wd, dWp[i])
                 # input gradient of layer i
                 WT = L["W"].t().contiguous()                      # [K_in x 256]
                 if i == 0:
@@ -223,9 +224,8 @@ class _DeformMLPFn(torch.autograd.Function):
                     if L["skip"]:
                         _Gemm.run(dev, P, EMBED, dZ, Wd, _planes(WT[:EMBED].contiguous()), _rt.GEMM_ATOMIC, out=dE, err=err)
                         WT = WT[EMBED:].contiguous()
-                    _Gemm.run(dev, P, Wd, dZ, Wd, _planes(WT), _rt.GEMM_SPLIT, mask=acts[i - 1][0], out=dZ2, outT=dZT2,
-                              ld_outT=Pp, colsum=db[i - 1], err=err)
-                    dZ, dZ2, dZT, dZT2 = dZ2, dZ, dZT2, dZT
+                    _Gemm.run(dev, P, Wd, dZ, Wd, _planes(WT), _rt.GEMM_SPLIT, mask=acts[i - 1], out=dZ2, colsum=db[i - 1], err=err)
+                    dZ, dZ2 = dZ2, dZ
             dx = torch.empty((P, 3), **f32)
             _rt.check(lib.gsr_mlp_embed_backward(s["x"].data_ptr(), P, dE.data_ptr(), dx.data_ptr(), 0, st))
         # unpack the padded layouts into the parameters' own shapes (0.5 M values in total)
@@ -243,7 +243,7 @@ class _DeformMLPFn(torch.autograd.Function):
         for hs in s["head_sizes"]:
             gw.append(dWh[o:o + hs]); gb.append(db_heads[o:o + hs]); o += hs
         ctx.state = None
-        return (dx if ctx.needs_input_grad[0] else None, None, None, None, *gw, *gb)
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, None, *gw, *gb)
 
 
 def _check_pipeline(err):
@@ -265,7 +265,7 @@ class _Trunk(nn.Module):
         weights = [l.weight for l in self._time] + [h.weight for h in heads]
         biases = [l.bias for l in self._time] + [h.bias for h in heads]
         sizes = tuple(int(h.weight.shape[0]) for h in heads)
-        out = _DeformMLPFn.apply(x, te, sizes, len(self._time), *weights, *biases)
+        out = _DeformMLPFn.apply(x, te, sizes, len(self._time), torch.is_grad_enabled(), *weights, *biases)
         return out
 
 

@@ -62,6 +62,7 @@ class gsr_gemm(ctypes.Structure):
         ("outT_hi", ctypes.c_void_p), ("outT_lo", ctypes.c_void_p), ("ld_outT", ctypes.c_int64),
         ("colsum", ctypes.c_void_p),
         ("error_flag", ctypes.c_void_p),
+        ("mn_major", ctypes.c_int32),
     ]
 
 

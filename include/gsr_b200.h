@@ -193,13 +193,15 @@ int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 int gsr_mark_visible(const gsr_view* view, int P, const float* means3D, uint8_t* present, void* stream);
 
 /* Deformation-network linear layers on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
- * TMEM, operands staged by TMA), with an fp32-grade result: every operand is given as two fp32 planes, x = hi + lo
- * with hi a TF32 value (gsr_mlp_split), and each product is evaluated as hi.hi + lo.hi + hi.lo.
+ * TMEM, operands staged by TMA), with an fp32-grade result: every operand enters the tensor core as x = hi + lo with hi
+ * a TF32 value, and each product is evaluated as hi.hi + lo.hi + hi.lo.  An operand is given as ONE fp32 plane (its *_lo
+ * pointer NULL: the kernel splits the tile in shared memory - for the P-sized activations, which then cross HBM once) or
+ * as planes pre-split by gsr_mlp_split (the weights).  Outputs likewise: out_lo / outT_lo NULL = one fp32 plane.
  *   C[M x N] = epilogue(A[M x K] . B[N x K]^T),  N <= 256,  all operands K-major (row stride ldA / ldB floats,
  *   multiples of 4, 16-byte aligned planes).  A may be two K segments ([A0 | A1], the network's skip connection);
- *   each segment's K is padded to a multiple of 32 in B's column numbering (segment 1 starts at 32 ceil(K0 / 32)).
- * mode 0: relu(acc + bias) -> (hi, lo) planes;  1: (acc + bias), optionally zeroed where mask_src <= 0 -> planes;
- *      2: same value -> fp32 in out_hi;  3: out_hi += acc with atomics (k_splits > 1: split over K, weight gradients).
+ *   each segment's K is padded to a multiple of 16 in B's column numbering (segment 1 starts at 16 ceil(K0 / 16)).
+ * mode 0: relu(acc + bias);  1 (= 2): (acc + bias), optionally zeroed where mask_src <= 0;
+ *      3: out_hi += acc with atomics (k_splits > 1: split over K, weight gradients).
  * outT_*: the same values transposed ([N x ld_outT]); colsum[n] += column sums (bias gradients). */
 typedef struct gsr_gemm {
     int32_t M, N;
@@ -214,6 +216,8 @@ typedef struct gsr_gemm {
     float* outT_hi; float* outT_lo; int64_t ld_outT;
     float* colsum;
     uint32_t* error_flag;
+    int32_t mn_major;      /* 1: C[M x N] += A^T B with A0_hi [K0 x M] and B_hi [K0 x N] ROW-major single planes (the reduction
+                              runs over rows = points: weight gradients straight from the row-major activations); mode 3 only */
 } gsr_gemm;
 int gsr_mlp_gemm(const gsr_gemm* g, void* stream);
 int gsr_mlp_split(const float* x, int64_t n, float* hi, float* lo, void* stream);
@@ -223,7 +227,7 @@ int gsr_mlp_split_transpose(const float* x, int rows, int cols, int ld_in, float
  * colsum[c] += column sums.  Prepares a gradient that arrives from autograd as a GEMM operand. */
 int gsr_mlp_prepare(const float* x, int rows, int cols, int64_t ld_in, float* hi, float* lo, int64_t ld_out, float* hiT,
                     float* loT, int64_t ldT, float* colsum, void* stream);
-/* positions [P,3] -> embedding planes [P x 64] (63 values, column 63 zero) and, optionally, transposed [64 x ldT] */
+/* positions [P,3] -> embedding [P x 64] (63 values, column 63 zero; one plane if e_lo is NULL) and, optionally, transposed [64 x ldT] */
 int gsr_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, int64_t ldT, void* stream);
 int gsr_mlp_embed_backward(const float* xyz, int P, const float* d_embed /*[P x 64]*/, float* dxyz, int accumulate, void* stream);
 
