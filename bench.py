@@ -368,6 +368,62 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
     return total
 
 
+def deform_network_timing(impl, P, dev, steps=3):
+    """SURVEY 8f row f1 beside the headline: the deformation network DirectTemporalNeRF (scene/gaussian_model.py:242-316)
+    that the reference's render() queries for every view, forward and forward+backward over all P Gaussians.
+    ours: deform_mlp.DirectTemporalNeRF (tcgen05 hi/lo-split TF32 GEMMs); reference: the same network as torch fp32
+    linears (oracle/deform_mlp_port.DeformMLP, bit-identical to the reference class - tests/test_oracle_cpu.py)."""
+    torch.manual_seed(0)
+    if impl == "ours":
+        import deform_mlp
+        net = deform_mlp.DirectTemporalNeRF().to(dev)
+    else:
+        from oracle import deform_mlp_port
+        net = deform_mlp_port.DeformMLP().to(dev)
+    g = torch.Generator().manual_seed(1)
+    x0 = ((torch.rand((P, 3), generator=g) * 2 - 1) * 1.3).to(dev)
+    ts = torch.full((P, 1), 0.4, device=dev)
+    proj = [torch.randn((P, c), generator=g).to(dev) for c in (3, 3, 4, 48)]
+
+    def fwd():
+        with torch.no_grad():
+            net(x0, ts, 5000)
+
+    def fwd_bwd():
+        x = x0.clone().requires_grad_(True)
+        for p in net.parameters():
+            p.grad = None
+        torch.autograd.backward(net(x, ts, 5000), proj)
+
+    def timed(fn):
+        fn(); fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+    t_f, t_fb = timed(fwd), timed(fwd_bwd)
+    flops = 2.0 * P * (64 * 256 + 6 * 256 * 256 + 320 * 256 + 256 * 58)
+    out = {"P": P, "fwd_ms": round(t_f, 3), "fwd_bwd_ms": round(t_fb, 3),
+           "fwd_fp32_equivalent_TFLOPs": round(flops / t_f / 1e9, 1),
+           "what": "DirectTemporalNeRF (84 -> 8 x 256 ReLU, skip at 4 -> heads 3/3/4/48) over all P Gaussians, one time value"}
+    if impl == "ours":
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        out["roofline"] = {"bound": "tensor", "achieved": round(3 * flops / t_f / 1e9, 1), "peak": tf32_peak, "unit": "TFLOP/s",
+                           "frac": round(3 * flops / t_f / 1e9 / tf32_peak, 4),
+                           "note": "forward; achieved counts the 3 TF32 tensor-core products issued per fp32-grade product; peak = half of "
+                                   "the measured sustained bf16 cuBLAS rate (TF32 runs at half the bf16 rate on tcgen05)"}
+    return out
+
+
 def cpu_baseline(n=100000, iters=30):
     """Reference torch-CPU deformation stage (config C1): exp_se3 + apply, fwd+bwd."""
     import synthetic
@@ -411,6 +467,7 @@ def main():
                     help="also time the whole C5-style training step: per-view loss 0.8 L1 + 0.2 (1 - SSIM) against a fixed "
                          "target, gradient all-reduce, Adam step (ours: fused kernels; reference: its torch ops)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mlp", action="store_true", help="skip the deformation-network timing (SURVEY 8f f1) reported beside the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = CONFIGS[args.config]
@@ -719,6 +776,13 @@ def main():
         out["roofline"] = roofline
         out["roofline_hbm"] = roofline_hbm
         out["kernels"] = kernels
+    if not args.no_mlp and world == 1:
+        try:
+            del leaves
+            torch.cuda.empty_cache()
+            out["deform_network"] = deform_network_timing(args.impl, min(args.P, 1000000), dev)
+        except Exception as ex:  # pragma: no cover
+            out["deform_network"] = {"error": repr(ex)}
     if not args.no_cpu_baseline and world == 1:
         try:
             out["cpu_baseline"] = cpu_baseline()

@@ -546,6 +546,28 @@ int gsr_mlp_embed_backward(const float* xyz, int P, const float* d_embed, float*
     return gsr_launch_mlp_embed_bwd(xyz, P, d_embed, dxyz, accumulate, (cudaStream_t)stream_);
 }
 
+int gsr_densify_stats(int P, const float* viewspace_grad, const int32_t* radii, float* xyz_gradient_accum, float* xyz_gradient_accum_3vec,
+                      float* denom, float* max_radii2D, void* stream_) {
+    if (P > 0 && (!viewspace_grad || !radii || !xyz_gradient_accum || !denom || !max_radii2D)) return gsr_set_error_msg(-1, "densify_stats: NULL pointer");
+    return gsr_launch_densify_stats(P, viewspace_grad, radii, xyz_gradient_accum, xyz_gradient_accum_3vec, denom, max_radii2D, (cudaStream_t)stream_);
+}
+int gsr_densify_decide(int P, const float* xyz_gradient_accum, const float* denom, const float* scaling_raw, float grad_threshold,
+                       float size_threshold, uint8_t* flags, void* stream_) {
+    if (P > 0 && (!xyz_gradient_accum || !denom || !scaling_raw || !flags)) return gsr_set_error_msg(-1, "densify_decide: NULL pointer");
+    return gsr_launch_densify_decide(P, xyz_gradient_accum, denom, scaling_raw, grad_threshold, size_threshold, flags, (cudaStream_t)stream_);
+}
+int gsr_densify_split(int n, int N, const float* xyz, const float* scaling_raw, const float* rotation_raw, const float* normals, float* new_xyz,
+                      float* new_scaling, void* stream_) {
+    if (n > 0 && (!xyz || !scaling_raw || !rotation_raw || !normals || !new_xyz || !new_scaling)) return gsr_set_error_msg(-1, "densify_split: NULL pointer");
+    return gsr_launch_densify_split(n, N, xyz, scaling_raw, rotation_raw, normals, new_xyz, new_scaling, (cudaStream_t)stream_);
+}
+int gsr_densify_prune(int P, const float* opacity_raw, const float* scaling_raw, const float* max_radii2D, float min_opacity,
+                      float max_screen_size, float world_size_limit, int use_size, uint8_t* prune, void* stream_) {
+    if (P > 0 && (!opacity_raw || !scaling_raw || !prune || (use_size && !max_radii2D))) return gsr_set_error_msg(-1, "densify_prune: NULL pointer");
+    return gsr_launch_densify_prune(P, opacity_raw, scaling_raw, max_radii2D, min_opacity, max_screen_size, world_size_limit, use_size, prune,
+                                    (cudaStream_t)stream_);
+}
+
 size_t gsr_knn_bytes(int P) { return gsr_knn_temp_bytes(P); }
 int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream_) {
     if (P > 0 && (!points || !mean_dist2 || !temp)) return gsr_set_error_msg(-1, "knn: NULL pointer");

@@ -214,3 +214,13 @@ int gsr_launch_mlp_prepare(const float* x, int rows, int cols, long long ld_in, 
                            float* hiT, float* loT, long long ldT, float* colsum, cudaStream_t stream);
 int gsr_launch_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, long long ldT, cudaStream_t stream);
 int gsr_launch_mlp_embed_bwd(const float* xyz, int P, const float* de, float* dxyz, int accumulate, cudaStream_t stream);
+
+// ---- densification (densify.cu) -------------------------------------------------------------
+int gsr_launch_densify_stats(int P, const float* grad2d, const int* radii, float* accum, float* accum3, float* denom, float* max_radii,
+                             cudaStream_t stream);
+int gsr_launch_densify_decide(int P, const float* accum, const float* denom, const float* scaling_raw, float grad_threshold,
+                              float size_threshold, uint8_t* flags, cudaStream_t stream);
+int gsr_launch_densify_split(int n, int N, const float* xyz, const float* scaling_raw, const float* rot_raw, const float* z, float* new_xyz,
+                             float* new_scaling, cudaStream_t stream);
+int gsr_launch_densify_prune(int P, const float* opacity_raw, const float* scaling_raw, const float* max_radii, float min_opacity,
+                             float max_screen_size, float world_size_limit, int use_size, uint8_t* prune, cudaStream_t stream);

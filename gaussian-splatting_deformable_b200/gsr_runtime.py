@@ -104,6 +104,10 @@ _SIGNATURES = {
     "gsr_mlp_prepare": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _P, _P]),
     "gsr_mlp_embed": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, _P, ctypes.c_int64, _P]),
     "gsr_mlp_embed_backward": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, ctypes.c_int, _P]),
+    "gsr_densify_stats": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gsr_densify_decide": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_float, ctypes.c_float, _P, _P]),
+    "gsr_densify_split": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gsr_densify_prune": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, _P, _P]),
     "gsr_mark_visible": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, _P, _P, _P]),
     "gsr_knn_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_knn_dist2": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_size_t, _P]),

@@ -34,6 +34,9 @@
  *       <- utils/loss_utils.py:17-64 (l1_loss, ssim) combined as in train.py:323,529
  *   gsr_adam_step
  *       <- torch.optim.Adam as configured at scene/gaussian_model.py:834-846
+ *   gsr_densify_stats / gsr_densify_decide / gsr_densify_split / gsr_densify_prune
+ *       <- GaussianModel.add_densification_stats, densify_and_clone, densify_and_split, densify_and_prune
+ *          scene/gaussian_model.py:1129-1257 (torch indexing ops in the reference)
  *   gsr_mlp_embed / gsr_mlp_embed_backward
  *       <- Embedder.embed, scene/gaussian_model.py:33-81 (multires 10 positional embedding of the positions)
  *   gsr_mlp_gemm (+ gsr_mlp_split / gsr_mlp_split_transpose operand preparation)
@@ -230,6 +233,23 @@ int gsr_mlp_prepare(const float* x, int rows, int cols, int64_t ld_in, float* hi
 /* positions [P,3] -> embedding [P x 64] (63 values, column 63 zero; one plane if e_lo is NULL) and, optionally, transposed [64 x ldT] */
 int gsr_mlp_embed(const float* xyz, int P, float* e_hi, float* e_lo, float* eT_hi, float* eT_lo, int64_t ldT, void* stream);
 int gsr_mlp_embed_backward(const float* xyz, int P, const float* d_embed /*[P x 64]*/, float* dxyz, int accumulate, void* stream);
+
+/* Densification (scene/gaussian_model.py:1129-1257, train.py:610-648): per-point statistics and decisions.  All arrays are
+ * the reference's own tensors (pre-activation log-scales / opacity logits / un-normalised quaternions).
+ *   gsr_densify_stats   add_densification_stats + the max_radii2D update for the points a view saw (radii > 0)
+ *   gsr_densify_decide  flags[i] bit 0 = clone, bit 1 = split  (grads = accum / denom, NaN -> 0; size_threshold = percent_dense * extent)
+ *   gsr_densify_split   the n selected points x N samples: new positions R(q)(z exp(scaling)) + xyz and new log-scales
+ *                       log(exp(scaling) / (0.8 N)); `normals` = [n N, 3] standard normals, row r belongs to point r % n
+ *   gsr_densify_prune   prune[i] = sigmoid(opacity) < min_opacity, or (use_size) max_radii2D > max_screen_size or
+ *                       max(exp(scaling)) > world_size_limit */
+int gsr_densify_stats(int P, const float* viewspace_grad, const int32_t* radii, float* xyz_gradient_accum, float* xyz_gradient_accum_3vec,
+                      float* denom, float* max_radii2D, void* stream);
+int gsr_densify_decide(int P, const float* xyz_gradient_accum, const float* denom, const float* scaling_raw, float grad_threshold,
+                       float size_threshold, uint8_t* flags, void* stream);
+int gsr_densify_split(int n, int N, const float* xyz, const float* scaling_raw, const float* rotation_raw, const float* normals, float* new_xyz,
+                      float* new_scaling, void* stream);
+int gsr_densify_prune(int P, const float* opacity_raw, const float* scaling_raw, const float* max_radii2D, float min_opacity,
+                      float max_screen_size, float world_size_limit, int use_size, uint8_t* prune, void* stream);
 
 size_t gsr_knn_bytes(int P);
 int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream);
