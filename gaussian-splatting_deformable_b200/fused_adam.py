@@ -5,7 +5,11 @@ The reference builds `torch.optim.Adam(l, lr=0.0, eps=1e-15)` from a list of per
 writing `param_group['lr']` (gaussian_model.py:869-886).  `FusedAdam` takes the same list, re-homes every
 parameter as a view of ONE flat fp32 buffer (gradients: `view_parallel.FlatGradBuffer`, which is also the
 all-reduce buffer; moments: two more flat buffers) and runs the whole step as one kernel.
-Arithmetic is torch.optim.Adam's (torch 2.11; no amsgrad, weight decay or maximize).
+Arithmetic is torch.optim.Adam's (torch 2.11; no amsgrad, weight decay or maximize).  `state_dict()` /
+`load_state_dict()` use torch.optim.Adam's own layout, so the reference's checkpoints (scene/gaussian_model.py:698,725)
+go both ways.  Differences: the step count is kept per GROUP (torch: per parameter; the reference always steps the
+parameters of a group together), and a group whose gradients were not produced must be named in `step(skip=...)`
+(torch skips parameters whose `.grad` is None; here gradients always exist as views of the flat buffer).
 """
 import ctypes
 import math

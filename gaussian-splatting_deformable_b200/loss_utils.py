@@ -72,10 +72,14 @@ class _SsimL1(torch.autograd.Function):
             win = _window11()
             _rt.check(lib.gsr_ssim_l1_loss_forward(_rt.ptr(x), _rt.ptr(y), C, H, W, win.data_ptr(), float(lam),
                                                    _rt.ptr(dmaps), _rt.ptr(out), _rt.stream_ptr(dev)))
+        if gt.requires_grad:
+            raise _rt.GsrError("l1_ssim_loss / ssim: the target image must not require grad (only `image` is differentiated)")
         ctx.save_for_backward(x, y, dmaps)
         ctx.lam = float(lam)
         ctx.in_dtype = image.dtype
-        return out[3], out[4], out[5]
+        loss, l1, ss = out[3], out[4], out[5]
+        ctx.mark_non_differentiable(l1, ss)          # logging values: differentiating them raises instead of returning zeros
+        return loss, l1, ss
 
     @staticmethod
     def backward(ctx, g_loss, g_l1, g_ssim):

@@ -5,8 +5,10 @@ PLY element `vertex` whose properties are all `float` (f4), in this order:
     x y z  nx ny nz  f_dc_0..2  f_rest_0..(3*((D+1)^2-1)-1)  opacity  scale_0..2  rot_0..3
 with the SH features stored channel-major (the reference flattens `features.transpose(1, 2)`), the normals zero,
 and every tensor PRE-activation (log-scales, opacity logits, un-normalised quaternions).  `plyfile` emits the header
-below byte for byte (format line, element line, one `property float <name>` per attribute, `end_header`), so files
-written here load in the reference's `render.py` / the SIBR viewer and vice versa.
+below byte for byte (format line, element line, one `property float <name>` per attribute, `end_header`).  This module
+covers the PLY element only: the reference's `load_ply` also torch.load()s five network state-dicts from beside the
+file (scene/gaussian_model.py:1014+) - `checkpoint_io.save_point_cloud` writes the pair the reference (and the SIBR
+viewer, which reads the PLY alone) expects.  `double` properties, which other writers emit, are accepted on load.
 
 Host-side IO only (numpy); nothing here is on the hot path.
 """
@@ -58,7 +60,7 @@ def save_ply(path, xyz, features_dc, features_rest, opacity, scaling, rotation):
 def _read_header(f):
     if f.readline().strip() != b"ply":
         raise ValueError("not a PLY file")
-    fmt, count, props, in_vertex = None, None, [], False
+    fmt, count, props, types, in_vertex = None, None, [], [], False
     while True:
         line = f.readline()
         if not line:
@@ -75,26 +77,39 @@ def _read_header(f):
             elif count is not None:
                 raise ValueError("only a single vertex element is supported")
         elif tok[0] == "property" and in_vertex:
-            if tok[1] not in ("float", "float32"):
-                raise ValueError("vertex property %s is not float" % tok[-1])
+            if tok[1] not in _PLY_TYPES:
+                raise ValueError("vertex property %s has unsupported type %s" % (tok[-1], tok[1]))
             props.append(tok[2])
+            types.append(_PLY_TYPES[tok[1]])
         elif tok[0] == "end_header":
             break
     if fmt not in ("binary_little_endian", "binary_big_endian", "ascii") or count is None:
         raise ValueError("unsupported PLY header")
-    return fmt, count, props
+    return fmt, count, props, types
+
+
+# scalar property types plyfile accepts for these attributes (the reference writes 'f4'; other writers use double)
+_PLY_TYPES = {"float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
 
 
 def load_ply(path, max_sh_degree=3, device="cpu"):
     """Returns the reference's parameter tensors (gaussian_model.load_ply, :965-1005): xyz [P,3], features_dc [P,1,3],
     features_rest [P,K,3], opacity [P,1], scaling [P,3], rotation [P,4], float32 on `device`."""
     with open(path, "rb") as f:
-        fmt, n, props = _read_header(f)
+        fmt, n, props, types = _read_header(f)
         if fmt == "ascii":
-            data = np.loadtxt(f, dtype=np.float32, ndmin=2)[:n]
+            data = np.loadtxt(f, dtype=np.float64, ndmin=2)[:n].astype(np.float32)
+            if data.shape != (n, len(props)):
+                raise ValueError("load_ply: ASCII body has shape %s, header promises %d x %d" % (data.shape, n, len(props)))
         else:
-            data = np.frombuffer(f.read(4 * n * len(props)), dtype="<f4" if fmt == "binary_little_endian" else ">f4")
-            data = data.reshape(n, len(props)).astype(np.float32)
+            order = "<" if fmt == "binary_little_endian" else ">"
+            rec = np.dtype([(p, order + t) for p, t in zip(props, types)])
+            buf = f.read(rec.itemsize * n)
+            if len(buf) != rec.itemsize * n:
+                raise ValueError("load_ply: file is truncated (%d of %d body bytes for %d vertices x %d properties)"
+                                 % (len(buf), rec.itemsize * n, n, len(props)))
+            table = np.frombuffer(buf, dtype=rec)
+            data = np.stack([table[p].astype(np.float32) for p in props], axis=1) if props else np.zeros((n, 0), np.float32)
     col = {name: i for i, name in enumerate(props)}
 
     def cols(prefix):

@@ -122,3 +122,61 @@ def test_densify_and_prune_vs_reference_gaussian_model(P, size_threshold):
     _same_state(pc, mine, opt, stats, "after reset")
     # the densified set renders through flat buffers of an arbitrary row count (32-byte aligned tensor starts)
     assert all(mine[k].data_ptr() % 32 == 0 for k in mine)
+
+
+def test_checkpoint_tuple_and_sidecars_round_trip_with_the_reference(tmp_path):
+    """f4: chkpnt_<it>.pth = (GaussianModel.capture(), iteration) + the five network state-dicts (train.py:685-697),
+    both directions: the reference's capture restores into FusedAdam, ours restores into the reference's GaussianModel."""
+    import checkpoint_io
+    import densify
+    import fused_adam
+    gm = _gm()
+    P = 5003
+    pc = _reference_model(gm, P, seed=31)
+    mine, net, opt, stats = _ours_from(pc)
+    g = torch.Generator().manual_seed(1)
+    for it in range(3):
+        _step_both(pc, mine, opt, g)
+    # ---- reference -> ours ----
+    ref_nets = {"offset_model": pc.offset_model, "offset_model_rot": pc.offset_model_rot, "offset_model_scaling": pc.offset_model_scaling,
+                "opacity_mask": pc.opacity_mask, "shs_model": pc.shs_model}
+    d = tmp_path / "ckpt_save"
+    d.mkdir()
+    torch.save((pc.capture(), 3), str(d / "chkpnt_3.pth"))
+    for k, m in ref_nets.items():
+        torch.save(m.state_dict(), str(d / ("%s_3.pth" % k)))
+    model_args, first_iter, nets = checkpoint_io.load_checkpoint(str(d / "chkpnt_3.pth"))
+    assert first_iter == 3
+    for k in checkpoint_io.NETWORKS:                          # every parameter name and shape of the reference's networks
+        a, b = nets[k].state_dict(), ref_nets[k].state_dict()
+        assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[n].cpu(), b[n].cpu()) for n in a), k
+
+    def make_opt(params):
+        groups = []
+        for grp in pc.optimizer.param_groups:
+            ps = list(nets["offset_model"].parameters()) if grp["name"] == "offset_model" else [params[grp["name"]]]
+            groups.append({"params": ps, "lr": grp["lr"], "name": grp["name"]})
+        return fused_adam.FusedAdam(groups, lr=0.0, eps=1e-15)
+    sh, params, st2, opt2, lr_scale = checkpoint_io.restore(model_args, make_opt)
+    assert sh == pc.active_sh_degree and lr_scale == pc.spatial_lr_scale
+    _same_state(pc, params, opt2, st2, "restored from the reference's checkpoint")
+    _step_both(pc, params, opt2, g)
+    _same_state(pc, params, opt2, st2, "stepped after restore")
+    # ---- ours -> reference ----
+    path = checkpoint_io.save_checkpoint(str(tmp_path / "out"), 4, checkpoint_io.capture(sh, params, st2, opt2, lr_scale), nets)
+    (model_params, it4) = torch.load(path, map_location="cuda:0", weights_only=False)
+    pc2 = gm.GaussianModel(3)
+    pc2.restore(model_params, OPT)                              # the reference's own restore (training_setup + load_state_dict)
+    for k in checkpoint_io.NETWORKS:
+        getattr(pc2, k).load_state_dict(torch.load(os.path.join(os.path.dirname(path), "%s_4.pth" % k)))
+    assert it4 == 4
+    _same_state(pc2, params, opt2, st2, "the reference restored our checkpoint")
+    _step_both(pc2, params, opt2, g)
+    _same_state(pc2, params, opt2, st2, "stepped after the reference's restore")
+    # ---- save_ply's sidecars ----
+    checkpoint_io.save_point_cloud(str(tmp_path / "pc" / "point_cloud.ply"), params["xyz"], params["f_dc"], params["f_rest"],
+                                   params["opacity"], params["scaling"], params["rotation"], nets)
+    t, nets2 = checkpoint_io.load_point_cloud(str(tmp_path / "pc" / "point_cloud.ply"))
+    assert torch.equal(t["xyz"], params["xyz"].detach()) and torch.equal(t["features_rest"], params["f_rest"].detach())
+    for k in checkpoint_io.NETWORKS:                          # and the reference's own classes accept every file strictly
+        getattr(pc2, k).load_state_dict(torch.load(str(tmp_path / "pc" / (k + ".pth"))), strict=True)

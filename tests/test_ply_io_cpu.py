@@ -5,6 +5,7 @@ import os
 import struct
 
 import numpy as np
+import pytest
 import torch
 
 import ply_io
@@ -63,3 +64,43 @@ def test_reader_accepts_what_plyfile_variants_write_and_rejects_the_rest(tmp_pat
         assert False
     except ValueError:
         pass
+
+
+def test_load_accepts_double_properties_and_reports_truncation(tmp_path):
+    import numpy as np
+    import ply_io
+    P = 7
+    g = torch.Generator().manual_seed(3)
+    t = dict(xyz=torch.randn(P, 3, generator=g), features_dc=torch.randn(P, 1, 3, generator=g), features_rest=torch.randn(P, 15, 3, generator=g),
+             opacity=torch.randn(P, 1, generator=g), scaling=torch.randn(P, 3, generator=g), rotation=torch.randn(P, 4, generator=g))
+    path = str(tmp_path / "a" / "point_cloud.ply")
+    ply_io.save_ply(path, t["xyz"], t["features_dc"], t["features_rest"], t["opacity"], t["scaling"], t["rotation"])
+    raw = open(path, "rb").read()
+    head, body = raw[:raw.index(b"end_header\n") + 11], raw[raw.index(b"end_header\n") + 11:]
+    # the same table written by a tool that uses doubles (plyfile reads those; so does load_ply)
+    dbl = str(tmp_path / "double.ply")
+    with open(dbl, "wb") as f:
+        f.write(head.replace(b"property float ", b"property double "))
+        f.write(np.frombuffer(body, dtype="<f4").astype("<f8").tobytes())
+    back = ply_io.load_ply(dbl)
+    for k in t:
+        assert torch.equal(back[k], t[k]), k
+    cut = str(tmp_path / "cut.ply")
+    open(cut, "wb").write(raw[:-10])
+    with pytest.raises(ValueError, match="truncated"):
+        ply_io.load_ply(cut)
+
+
+def test_sidecar_networks_have_the_reference_parameter_names():
+    """checkpoint_io.make_networks against the REAL classes of scene/gaussian_model.py (staged by oracle/build_ref.py)."""
+    from oracle import ref_py
+    if not os.path.exists(os.path.join(ref_py.PY, "scene", "gaussian_model.py")):
+        pytest.skip("oracle/_ref/py not staged")
+    import checkpoint_io
+    gm = ref_py.gaussian_model()
+    ref = gm.GaussianModel(3)
+    mine = checkpoint_io.make_networks()
+    for name in checkpoint_io.NETWORKS:
+        a = {k: tuple(v.shape) for k, v in mine[name].state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in getattr(ref, name).state_dict().items()}
+        assert a == b and list(a) == list(b), name
