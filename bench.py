@@ -466,6 +466,9 @@ def main():
     ap.add_argument("--train", action="store_true",
                     help="also time the whole C5-style training step: per-view loss 0.8 L1 + 0.2 (1 - SSIM) against a fixed "
                          "target, gradient all-reduce, Adam step (ours: fused kernels; reference: its torch ops)")
+    ap.add_argument("--sync-free", type=int, default=1,
+                    help="ours: 1 = diff_gaussian_rasterization.set_sync_free(True): the duplicate list is sized from the previous "
+                         "steps' num_rendered x 1.25 and the forward has no host round trip; 0 = read num_rendered back in every forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mlp", action="store_true", help="skip the deformation-network timing (SURVEY 8f f1) reported beside the headline")
     args = ap.parse_args()
@@ -501,6 +504,8 @@ def main():
         import gsr_runtime as rt
         rt.load()
         step_fn = step_ours
+        import diff_gaussian_rasterization as dgr
+        dgr.set_sync_free(bool(args.sync_free))
 
     host, cams, bg, grad = build_workload(args, rank, world, dev)
     leaves = to_device(host, dev)
@@ -540,6 +545,7 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
     if args.impl == "ours":
+        dgr.check_sync_free()          # raises if any timed view overflowed its capacity-sized workspace (its work would be missing)
         launches = rt.launch_count(reset=True)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -644,6 +650,8 @@ def main():
         _ = float(loss.item())                        # device -> host read of the step's result
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if args.impl == "ours":
+        dgr.check_sync_free()
     if world > 1:
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
     e2e_val = args.P * views_total / (float(e2e_s.item()) / args.steps)
@@ -784,6 +792,7 @@ def main():
         "config": {"workload": "%s; %d views/GPU/step on a camera circle (C5's 64 cameras at 8 GPUs)" % (cfg["what"], args.views),
                    "name": args.config,
                    "P": args.P, "width": args.W, "height": args.H, "views_per_gpu_per_step": args.views, "streams": args.streams,
+                   "sync_free_forward": bool(args.sync_free) if args.impl == "ours" else False,
                    "parallelism": "view-parallel x%d, per-Gaussian grad all-reduce (NCCL)" % world if world > 1 else "single GPU",
                    "l2": "inputs (264 MB params+twists, 85 MB geometry state, 190 MB keys) exceed the 126 MB L2 every view"},
         "clocks": clocks,

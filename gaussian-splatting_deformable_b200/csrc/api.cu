@@ -213,18 +213,18 @@ void gsr_binning_layout(uint32_t R, int W, int H, size_t out[4]) {
     out[3] = in_b ? L.tkeys_a : L.tkeys_b;
 }
 
-int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* means3D, const float* scales,
-                           const float* rotations, const float* opacities, const float* shs,
-                           const float* cov3D_precomp, const float* colors_precomp, const gsr_deform* deform,
-                           float* means_out, int32_t* radii, void* geom_ws, size_t geom_bytes,
-                           uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream_) {
+static int forward_preprocess_impl(const gsr_view* view, int P, int M, const float* means3D, const float* scales,
+                                   const float* rotations, const float* opacities, const float* shs,
+                                   const float* cov3D_precomp, const float* colors_precomp, const gsr_deform* deform,
+                                   float* means_out, int32_t* radii, void* geom_ws, size_t geom_bytes,
+                                   uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream_, bool sync) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (host_num_rendered) *host_num_rendered = 0;
+    if (host_num_rendered && sync) *host_num_rendered = 0;
     if (P < 0) return gsr_set_error_msg(-1, "P must be >= 0");
     if (P == 0) return 0;
     GsrView v;
     if (int rc = fill_view(view, M, v)) return rc;
-    if (!means3D || !opacities || !radii || !geom_ws || !host_num_rendered)
+    if (!means3D || !opacities || !radii || !geom_ws || (sync && !host_num_rendered))
         return gsr_set_error_msg(-1, "forward_preprocess: required pointer is NULL");
     if ((shs == nullptr) == (colors_precomp == nullptr))
         return gsr_set_error_msg(-1, "provide exactly one of SHs or precomputed colors");
@@ -267,6 +267,7 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* mean
     a.flags = a.depth_hist + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 60;
     GSR_CHECK(cudaMemsetAsync(ws + L.dsort_temp, 0, L.dsort_temp_bytes, stream));
     if (int rc = gsr_launch_preprocess_fwd(a, v, stream)) return rc;
+    if (!sync) return 0;            // capacity mode: counters and flags are read back by gsr_forward_render_capacity
     if (a.prefiltered) {
         // rare path: one more 4-byte read-back before the sync
         static thread_local uint32_t h_flags;
@@ -283,8 +284,25 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* mean
     return 0;
 }
 
-int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* radii, void* geom_ws, void* binning_ws,
-                       size_t binning_bytes, void* image_ws, float* out_color, int materialize_keys, void* stream_) {
+int gsr_forward_preprocess(const gsr_view* view, int P, int M, const float* means3D, const float* scales,
+                           const float* rotations, const float* opacities, const float* shs,
+                           const float* cov3D_precomp, const float* colors_precomp, const gsr_deform* deform,
+                           float* means_out, int32_t* radii, void* geom_ws, size_t geom_bytes,
+                           uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream_) {
+    return forward_preprocess_impl(view, P, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, deform,
+                                   means_out, radii, geom_ws, geom_bytes, host_num_rendered, debug_dump_cov3D, stream_, true);
+}
+int gsr_forward_preprocess_async(const gsr_view* view, int P, int M, const float* means3D, const float* scales,
+                                 const float* rotations, const float* opacities, const float* shs,
+                                 const float* cov3D_precomp, const float* colors_precomp, const gsr_deform* deform,
+                                 float* means_out, int32_t* radii, void* geom_ws, size_t geom_bytes, void* stream_) {
+    return forward_preprocess_impl(view, P, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, deform,
+                                   means_out, radii, geom_ws, geom_bytes, nullptr, 0, stream_, false);
+}
+
+static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const int32_t* radii, void* geom_ws, void* binning_ws,
+                               size_t binning_bytes, void* image_ws, float* out_color, int materialize_keys, void* stream_,
+                               bool capacity_mode, uint32_t* host_status4) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GsrView v;
     if (int rc = fill_view(view, 0, v)) return rc;
@@ -316,6 +334,8 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
             return rc;
         const uint32_t* order = d_in_b ? dvals_b : dvals_a;
         const uint32_t* sorted_tiles = nullptr;
+        if (capacity_mode && !BL.sweep)
+            return gsr_set_error_msg(-2, "forward_render_capacity: this image size takes the radix binning path, which needs the exact num_rendered");
         if (BL.sweep) {
             // 2+3. stable counting sort of the (never materialised) duplicates by tile id
             const GsrTileBinPlan pl = gsr_make_tile_bin_plan(v.grid_x, v.grid_y);
@@ -327,7 +347,9 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
                                                  reinterpret_cast<uint32_t*>(bw + BL.matrix),
                                                  reinterpret_cast<uint32_t*>(bw + BL.totals),
                                                  reinterpret_cast<uint32_t*>(bw + BL.tile_base), ranges, plist,
-                                                 reinterpret_cast<uint32_t*>(gw + L.dsort_temp) + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 61, stream))
+                                                 reinterpret_cast<uint32_t*>(gw + L.dsort_temp) + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 61, stream,
+                                                 capacity_mode ? R : 0u,
+                                                 reinterpret_cast<uint32_t*>(gw + L.dsort_temp) + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 59))
                 return rc;
             point_list = plist;
             if (materialize_keys) {
@@ -374,7 +396,27 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* r
     b.out_color = out_color;
     b.final_T = reinterpret_cast<float*>(iw + IL.final_T);
     b.n_contrib = reinterpret_cast<uint32_t*>(iw + IL.n_contrib);
-    return gsr_launch_blend_fwd(b, stream);
+    if (int rc = gsr_launch_blend_fwd(b, stream)) return rc;
+    if (capacity_mode && host_status4 && P > 0 && geom_ws) {
+        // words 59..62 of the sort state: overflow flag, prefiltered violation, (scan ticket), num_rendered
+        const GeomLayout L = geom_layout(P);
+        const uint32_t* st = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(geom_ws) + L.dsort_temp) +
+                             GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 59;
+        GSR_CHECK(cudaMemcpyAsync(host_status4, st, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    }
+    return 0;
+}
+
+int gsr_forward_render(const gsr_view* view, int P, uint32_t R, const int32_t* radii, void* geom_ws, void* binning_ws,
+                       size_t binning_bytes, void* image_ws, float* out_color, int materialize_keys, void* stream_) {
+    return forward_render_impl(view, P, R, radii, geom_ws, binning_ws, binning_bytes, image_ws, out_color, materialize_keys, stream_,
+                               false, nullptr);
+}
+int gsr_forward_render_capacity(const gsr_view* view, int P, uint32_t R_capacity, const int32_t* radii, void* geom_ws, void* binning_ws,
+                                size_t binning_bytes, void* image_ws, float* out_color, uint32_t* host_status4, void* stream_) {
+    if (R_capacity == 0) return gsr_set_error_msg(-1, "forward_render_capacity: capacity must be > 0");
+    return forward_render_impl(view, P, R_capacity, radii, geom_ws, binning_ws, binning_bytes, image_ws, out_color, 0, stream_, true,
+                               host_status4);
 }
 
 // Debug: workload counters of the blend stage for a finished forward (see blend.cu).

@@ -84,7 +84,8 @@ size_t gsr_tile_matrix_bytes(int grid_x, int grid_y);
 int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
                             const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
                             uint32_t* tile_base, uint2* ranges, uint32_t* point_list, uint32_t* scan_ticket /* zeroed word */,
-                            cudaStream_t stream);
+                            cudaStream_t stream, uint32_t capacity = 0 /* > 0: point_list holds this many entries; more -> *overflow = 1, empty ranges */,
+                            uint32_t* overflow = nullptr /* zeroed device word */);
 int gsr_launch_expand_tile_ids(int num_tiles, const uint2* ranges, uint32_t* tile_ids, cudaStream_t stream);
 
 // ---- training-step kernels either side of the rasterizer: loss.cu, adam.cu ----

@@ -50,11 +50,13 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_sweep_kernel(const 
                                                                          int grid_x, int grid_y,
                                                                          uint32_t* __restrict__ matrix,
                                                                          const uint32_t* __restrict__ tile_base,
-                                                                         uint32_t* __restrict__ point_list) {
+                                                                         uint32_t* __restrict__ point_list,
+                                                                         const uint32_t* __restrict__ overflow) {
     constexpr int ROWS = GSR_SWEEP_ROWS, CW = 32 / ROWS;
     extern __shared__ uint32_t s_cnt_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stripe = blockIdx.y * GSR_SWEEP_WARPS + warp;
+    if (SCATTER && overflow && *overflow) return;           // capacity mode: the list does not fit
     if (stripe >= pl.stripes) return;                       // warps are independent: no CTA barrier below
     uint32_t* cnt = s_cnt_all + warp * pl.stripe_tiles;
     const int row0 = stripe * ROWS;
@@ -154,10 +156,12 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(cons
                                                                            int grid_x, int grid_y,
                                                                            const uint32_t* __restrict__ matrix,
                                                                            const uint32_t* __restrict__ tile_base,
-                                                                           uint32_t* __restrict__ point_list) {
+                                                                           uint32_t* __restrict__ point_list,
+                                                                           const uint32_t* __restrict__ overflow) {
     constexpr int ROWS = GSR_SWEEP_ROWS, CW = 32 / ROWS;
     extern __shared__ uint32_t s_cnt_all[];                                   // [warps][stripe_tiles]
     __shared__ uint4 s_rec[GSR_SCATTER_SUB];
+    if (overflow && *overflow) return;                                        // capacity mode: the list does not fit
     __shared__ uint32_t s_bits[GSR_SWEEP_WARPS][GSR_SCATTER_SUB / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stripe = blockIdx.y * GSR_SWEEP_WARPS + warp;
@@ -233,7 +237,8 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(cons
 // segment, the 8 partial sums are scanned in shared memory, then the segment is rewritten.
 __global__ void __launch_bounds__(256) tile_column_scan_kernel(int chunks, int num_tiles, uint32_t* __restrict__ matrix,
                                                                uint32_t* __restrict__ totals, uint32_t* __restrict__ ticket,
-                                                               uint32_t* __restrict__ base, uint2* __restrict__ ranges) {
+                                                               uint32_t* __restrict__ base, uint2* __restrict__ ranges,
+                                                               uint32_t capacity, uint32_t* __restrict__ overflow) {
     __shared__ uint32_t s_part[8][33];
     __shared__ bool s_last;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -326,6 +331,13 @@ __global__ void __launch_bounds__(256) tile_column_scan_kernel(int chunks, int n
         if (threadIdx.x == 0) s_carry += all;
         __syncthreads();
     }
+    // Sync-free forward (capacity mode): the list was sized from an estimate.  If this view emits more duplicates than
+    // the workspace holds, raise the flag (the scatter returns at once, the host reads it with the view's counters) and
+    // empty every tile, so that nothing downstream reads a list entry that was never written.
+    if (capacity != 0u && s_carry > capacity) {
+        if (threadIdx.x == 0) *overflow = 1u;
+        for (int i = threadIdx.x; i < num_tiles; i += 256) ranges[i] = make_uint2(0u, 0u);
+    }
 }
 
 // Parity/debug: the sorted tile ids the reference's keys carry, rebuilt from the ranges.
@@ -367,7 +379,8 @@ size_t gsr_tile_matrix_bytes(int grid_x, int grid_y) {
 
 int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
                             const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
-                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, uint32_t* scan_ticket, cudaStream_t stream) {
+                            uint32_t* tile_base, uint2* ranges, uint32_t* point_list, uint32_t* scan_ticket, cudaStream_t stream,
+                            uint32_t capacity, uint32_t* overflow) {
     if (P <= 0) return 0;
     if (!pl.feasible) return gsr_set_error_msg(-2, "tile sweep: plan not feasible");
     const size_t smem = (size_t)GSR_SWEEP_WARPS * pl.stripe_tiles * sizeof(uint32_t);
@@ -395,12 +408,12 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order
         tile_count_kernel<<<pl.chunks, cnt_smem <= 48 * 1024 ? 256 : 1024, cnt_smem, stream>>>(n_emit, srec, pl, grid_x, matrix);
     } else {
         GsrProfScope prof_("tile_sweep_count", stream);
-        tile_sweep_kernel<false><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list);
+        tile_sweep_kernel<false><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list, nullptr);
     }
     GSR_CHECK_LAUNCH();
     { GsrProfScope prof_("tile_column_scan", stream);
     tile_column_scan_kernel<<<gsr_div_up(pl.num_tiles, 32), 256, 0, stream>>>(pl.chunks, pl.num_tiles, matrix, totals, scan_ticket,
-                                                                             tile_base, ranges); }
+                                                                             tile_base, ranges, capacity, overflow); }
     GSR_CHECK_LAUNCH();
     static const int scatter_v = env_int2("GSR_SWEEP_SCATTER_V", 2);
     if (scatter_v == 2) {
@@ -411,10 +424,10 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order
             sattr_done = true;
         }
         GsrProfScope prof_("tile_scatter", stream);
-        tile_scatter_kernel<<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list);
+        tile_scatter_kernel<<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list, overflow);
     } else {
         GsrProfScope prof_("tile_sweep_scatter", stream);
-        tile_sweep_kernel<true><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list);
+        tile_sweep_kernel<true><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list, overflow);
     }
     GSR_CHECK_LAUNCH();
     return 0;

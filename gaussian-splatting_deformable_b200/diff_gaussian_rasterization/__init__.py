@@ -19,6 +19,8 @@ flat all-reduce buffer, see view_parallel.FlatGradBuffer) and autograd receives 
 gradient for those inputs - view-batched training then needs no per-view
 accumulation pass.
 """
+import os
+import warnings
 from typing import NamedTuple
 
 import torch
@@ -98,6 +100,64 @@ def rasterize_gaussians(
         accumulate_grads,
         aux,
     )
+
+
+# ---- sync-free forward (opt-in): size the duplicate list from a capacity instead of reading num_rendered back ----------
+# The reference reads num_rendered back in the middle of every forward (rasterizer_impl.cu:281) and so does the default
+# path here: the list workspace is sized from it.  With set_sync_free(True) (or GSR_SYNC_FREE=1) the first forward of a
+# (device, P, W, H) configuration measures num_rendered the usual way; later ones size the workspace from the largest
+# num_rendered seen so far times `margin` and enqueue the whole forward - and its backward - without any host round
+# trip.  A view's real counters arrive asynchronously in pinned memory and are looked at, without waiting, at the next
+# forward of the same configuration (or, waiting, by check_sync_free()).  If a view overflowed its workspace the device
+# emptied every tile - background image, zero gradients - the capacity is raised and that later call raises GsrError.
+_SYNC_FREE = {"on": os.environ.get("GSR_SYNC_FREE", "0") == "1", "margin": float(os.environ.get("GSR_SYNC_FREE_MARGIN", "1.25"))}
+_capacity = {}
+_pending = {}          # key -> list of (event, pinned status words, capacity) of forwards not looked at yet
+
+
+def set_sync_free(on=True, margin=None):
+    _SYNC_FREE["on"] = bool(on)
+    if margin is not None:
+        _SYNC_FREE["margin"] = float(margin)
+    if not on:
+        _capacity.clear()
+        _pending.clear()
+
+
+def _note_num_rendered(key, R):
+    cap = int(R * _SYNC_FREE["margin"]) + (1 << 16)
+    if cap > _capacity.get(key, 0):
+        _capacity[key] = cap
+
+
+def _check_pending(key, blocking):
+    """Look at the status words of earlier sync-free forwards of configuration `key` (all of them if blocking, else those
+    whose copy has landed); raises GsrError if one of them overflowed its workspace."""
+    todo = _pending.get(key)
+    if not todo:
+        return
+    rest, overflowed = [], None
+    for ev, status, cap in todo:
+        if not blocking and not ev.query():
+            rest.append((ev, status, cap))
+            continue
+        ev.synchronize()
+        ov, _, _, R = (int(x) & 0xFFFFFFFF for x in status.tolist())
+        _note_num_rendered(key, R)
+        if ov:
+            overflowed = (R, cap)
+    _pending[key] = rest
+    if overflowed is not None:
+        raise _rt.GsrError("sync-free forward: an earlier view emitted %d (Gaussian, tile) pairs but its workspace was sized for %d, "
+                           "so its image was the background only and its gradients zero.  The capacity has been raised - repeat "
+                           "that step (or call diff_gaussian_rasterization.set_sync_free(False))." % overflowed)
+
+
+def check_sync_free():
+    """Wait for every sync-free forward issued so far and raise if one overflowed (call it wherever a step's results are
+    consumed on the host anyway, e.g. where the loss is logged)."""
+    for key in list(_pending):
+        _check_pending(key, blocking=True)
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -190,16 +250,38 @@ class _RasterizeGaussians(torch.autograd.Function):
             mailbox = _rt.pinned_u32(dev)
             num_rendered = 0
             dstruct = deform.c_struct()
-            if P != 0:
+            key = (dev.index, P, W, H)
+            cap = None
+            if _SYNC_FREE["on"] and P != 0 and not raster_settings.debug and not raster_settings.prefiltered:
+                _check_pending(key, blocking=False)
+                cap = _capacity.get(key)
+            if cap:
+                _rt.check(lib.gsr_forward_preprocess_async(
+                    view, P, M, _rt.ptr(means3D_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c),
+                    _rt.ptr(sh_c), _rt.ptr(cov_c), _rt.ptr(colors_c), dstruct, _rt.ptr(means_def),
+                    _rt.ptr(radii), _rt.ptr(geom), geom.numel(), stream))
+                nbytes = lib.gsr_binning_bytes(cap, W, H)
+                binning = torch.empty(_bucket(nbytes), dtype=torch.uint8, device=dev)
+                status = _rt.pinned_status(dev)
+                _rt.check(lib.gsr_forward_render_capacity(view, P, cap, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
+                                                          binning.numel(), _rt.ptr(img), _rt.ptr(color), status.data_ptr(), stream))
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                _pending.setdefault(key, []).append((ev, status, cap))
+                num_rendered = cap
+            elif P != 0:
                 _rt.check(lib.gsr_forward_preprocess(
                     view, P, M, _rt.ptr(means3D_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c),
                     _rt.ptr(sh_c), _rt.ptr(cov_c), _rt.ptr(colors_c), dstruct, _rt.ptr(means_def),
                     _rt.ptr(radii), _rt.ptr(geom), geom.numel(), mailbox.data_ptr(), 0, stream))
                 num_rendered = int(mailbox.item()) & 0xFFFFFFFF
-            nbytes = lib.gsr_binning_bytes(num_rendered, W, H)
-            binning = torch.empty(_bucket(nbytes), dtype=torch.uint8, device=dev)
-            _rt.check(lib.gsr_forward_render(view, P, num_rendered, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
-                                             binning.numel(), _rt.ptr(img), _rt.ptr(color), 0, stream))
+            if not cap:
+                if _SYNC_FREE["on"]:
+                    _note_num_rendered(key, num_rendered)
+                nbytes = lib.gsr_binning_bytes(num_rendered, W, H)
+                binning = torch.empty(_bucket(nbytes), dtype=torch.uint8, device=dev)
+                _rt.check(lib.gsr_forward_render(view, P, num_rendered, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
+                                                 binning.numel(), _rt.ptr(img), _rt.ptr(color), 0, stream))
 
         acc = dict(accumulate_grads) if accumulate_grads else {}
         shapes = {"means3D": means3D, "opacities": opacities, "shs": sh, "scales": scales, "rotations": rotations,
@@ -238,7 +320,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.mark_non_differentiable(radii)
         if aux is not None:          # per-call results for the caller (no class-level state: rasterizers may interleave)
             aux["deformed_means"] = means_def
-            aux["num_rendered"] = num_rendered
+            aux["num_rendered"] = num_rendered if not cap else None        # sync-free: not known on the host yet
         return color, radii
 
     @staticmethod

@@ -88,6 +88,11 @@ _SIGNATURES = {
                                               _P, _P, ctypes.c_size_t, _P, ctypes.c_int, _P]),
     "gsr_forward_render": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P,
                                           ctypes.c_size_t, _P, _P, ctypes.c_int, _P]),
+    "gsr_forward_preprocess_async": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_int,
+                                                    _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
+                                                    _P, _P, ctypes.c_size_t, _P]),
+    "gsr_forward_render_capacity": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P,
+                                                   ctypes.c_size_t, _P, _P, _P, _P]),
     "gsr_backward": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                     _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
                                     _P, _P, _P, _P, _P,
@@ -216,6 +221,22 @@ def pinned_u32(device):
         buf = torch.zeros(1, dtype=torch.int32).pin_memory()
         _pinned[key] = buf
     return buf
+
+
+_status_ring = {}
+
+
+def pinned_status(device, slots=512):
+    """A 4-word pinned slot for the asynchronous status read-back of a sync-free forward, from a per-device ring (a slot is
+    reused `slots` calls later, long after its copy has landed)."""
+    key = str(device)
+    ring = _status_ring.get(key)
+    if ring is None:
+        ring = [torch.zeros((slots, 4), dtype=torch.int32).pin_memory(), 0]
+        _status_ring[key] = ring
+    i = ring[1]
+    ring[1] = (i + 1) % slots
+    return ring[0][i]
 
 
 def geom_layout(P):

@@ -137,6 +137,23 @@ int gsr_forward_render(const gsr_view* view, int P, uint32_t num_rendered,
                        const int32_t* radii, void* geom_ws, void* binning_ws, size_t binning_bytes,
                        void* image_ws, float* out_color, int materialize_keys, void* stream);
 
+/* Sync-free forward.  gsr_forward_preprocess + gsr_forward_render cost one device->host read of num_rendered and a stream
+ * synchronisation between them (as does the reference, rasterizer_impl.cu:281), because the duplicate list is sized from
+ * it.  These two calls size the list from a CAPACITY the caller chooses instead (e.g. the previous step's num_rendered
+ * plus a margin): nothing is read back in between, the whole forward is enqueued at once and can be captured in a CUDA
+ * graph.  If a view emits more duplicates than the capacity, the device raises a flag, writes no list entry, empties every
+ * tile (the image is then the background) and host_status4 tells: 4 words of PINNED host memory filled asynchronously at
+ * the end of the call: [0] overflow flag, [1] prefiltered violation, [2] unused, [3] num_rendered.  The binning workspace
+ * must hold gsr_binning_bytes(R_capacity, W, H); gsr_backward takes R = R_capacity.  Images that need the radix binning
+ * path (wider than 16 384 px) are refused. */
+int gsr_forward_preprocess_async(const gsr_view* view, int P, int M, const float* means3D, const float* scales,
+                                 const float* rotations, const float* opacities, const float* shs,
+                                 const float* cov3D_precomp, const float* colors_precomp, const gsr_deform* deform,
+                                 float* means_out, int32_t* radii, void* geom_ws, size_t geom_bytes, void* stream);
+int gsr_forward_render_capacity(const gsr_view* view, int P, uint32_t R_capacity, const int32_t* radii, void* geom_ws,
+                                void* binning_ws, size_t binning_bytes, void* image_ws, float* out_color,
+                                uint32_t* host_status4, void* stream);
+
 /* ---- backward -------------------------------------------------------------
  * dL_dout_color[3,H,W] -> gradients.  Every output element is written (no
  * pre-zeroing needed) except dL_dtwist_* in rigid-body mode, which are

@@ -422,3 +422,51 @@ def test_fused_adam_state_dict_round_trips_with_torch_adam():
     bad["state"][0]["exp_avg"] = bad["state"][0]["exp_avg"][:-1]
     with pytest.raises(ValueError):
         oc.load_state_dict(bad)
+
+
+# ---------------------------------------------------------------------------
+# Sync-free forward (capacity-sized duplicate list, no host round trip in the forward)
+# ---------------------------------------------------------------------------
+def test_sync_free_forward_matches_and_reports_overflow():
+    import diff_gaussian_rasterization as dgr
+    import gsr_runtime as rt
+    import synthetic
+    from _gpu_util import make_view_settings, rel_to_max, run_ours
+    sc, cam, rs = make_view_settings(60000, 640, 400, scale_mult=1.5)
+    grad = synthetic.make_image_grad(640, 400, device="cuda")
+    a = run_ours(rs, sc, grad)
+    dgr.set_sync_free(True, margin=1.25)
+    try:
+        b0 = run_ours(rs, sc, grad)                          # first call of this configuration: measures num_rendered
+        n0 = rt.launch_count()
+        b1 = run_ours(rs, sc, grad)                          # capacity path: nothing read back inside the forward
+        assert rt.launch_count() > n0
+        key = (torch.cuda.current_device(), 60000, 640, 400)
+        assert key in dgr._capacity and dgr._capacity[key] > 0
+        for b in (b0, b1):
+            assert torch.equal(a["color"], b["color"]) and torch.equal(a["radii"], b["radii"])
+            for k in a["grads"]:
+                assert rel_to_max(b["grads"][k], a["grads"][k]) <= 1e-5, k
+        # a view that does not fit: background image, zero gradients, reported at the next look, capacity raised
+        dgr.check_sync_free()                                # (drain the status words of the calls above first)
+        dgr._capacity[key] = 1000
+        bad = run_ours(rs, sc, grad)
+        assert torch.allclose(bad["color"], rs.bg.view(3, 1, 1).expand_as(bad["color"]))
+        assert all(float(g.abs().max()) == 0.0 for g in bad["grads"].values())
+        with pytest.raises(rt.GsrError, match="sized for 1000"):
+            dgr.check_sync_free()
+        assert dgr._capacity[key] > 1000
+        c = run_ours(rs, sc, grad)
+        assert torch.equal(a["color"], c["color"])
+        # ... or at the next forward of the same configuration once the status words have landed
+        dgr.check_sync_free()
+        dgr._capacity[key] = 1000
+        run_ours(rs, sc, None)
+        torch.cuda.synchronize()
+        with pytest.raises(rt.GsrError, match="overflow|sized for"):
+            run_ours(rs, sc, None)
+        d = run_ours(rs, sc, None)
+        assert torch.equal(a["color"], d["color"])
+        dgr.check_sync_free()
+    finally:
+        dgr.set_sync_free(False)
