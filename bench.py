@@ -39,7 +39,7 @@ sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_deformable_b200"))
 
 PARAM_KEYS = ("means3D", "scales", "rotations", "opacities", "shs")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` at the default workload (profiles/)
-NCU_TRAFFIC = {"preprocess_bwd": 677.3e6, "preprocess_fwd": 274.4e6}
+NCU_TRAFFIC = {"preprocess_bwd": 581.1e6, "preprocess_fwd": 233.9e6, "blend_bwd": 110.1e6, "blend_fwd": 54.0e6}   # profiles/r02_ncu_full_metrics.csv
 
 
 # ---------------------------------------------------------------------------
@@ -181,9 +181,11 @@ def step_ours(leaves, cams, bg, grad, args):
             color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
                                shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
                                se3_S=leaves["S"], se3_theta=leaves["theta"], body_id=args.body_id, accumulate_grads=sinks)
-        loss = (color * grad).sum()
-        loss.backward()
-        return loss.detach()
+        # dL/dimage = grad is injected directly (as the reference arm does below): one reduction for the loss value, no
+        # autograd graph through a multiply
+        loss = torch.dot(color.detach().reshape(-1), grad.reshape(-1))
+        color.backward(grad)
+        return loss
 
     return view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams)
 
@@ -211,7 +213,7 @@ def step_reference(leaves, cams, bg, grad, args):
         yd = y.detach()
         f = ref_driver.forward(rs, yd, leaves["opacities"].detach(), shs=leaves["shs"].detach(),
                                scales=leaves["scales"].detach(), rotations=leaves["rotations"].detach())
-        loss = (f["color"] * grad).sum()
+        loss = torch.dot(f["color"].reshape(-1), grad.reshape(-1))
         g = ref_driver.backward(rs, f, grad, yd, shs=leaves["shs"].detach(), scales=leaves["scales"].detach(),
                                 rotations=leaves["rotations"].detach())
         if no_deform:
@@ -419,6 +421,7 @@ def deform_network_timing(impl, P, dev, steps=3):
         tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
         out["roofline"] = {"bound": "tensor", "achieved": round(3 * flops / t_f / 1e9, 1), "peak": tf32_peak, "unit": "TFLOP/s",
                            "frac": round(3 * flops / t_f / 1e9 / tf32_peak, 4),
+                           "traffic": 2.0006e9 if P == 1000000 else None,      # per hidden-layer GEMM launch (ncu, profiles/r02_ncu_gemm_metrics.csv) = its algorithmic 2 x P x 256 x 4 B
                            "note": "forward; achieved counts the 3 TF32 tensor-core products issued per fp32-grade product; peak = half of "
                                    "the measured sustained bf16 cuBLAS rate (TF32 runs at half the bf16 rate on tcgen05)"}
     return out
