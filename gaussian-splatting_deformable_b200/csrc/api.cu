@@ -4,6 +4,8 @@
 // markVisible} (rasterizer_impl.cu:141-153,198-434) behind a C ABI.
 #include "../../include/gsr_b200.h"
 #include "kernels.cuh"
+#include <atomic>
+#include <mutex>
 #include <stdio.h>
 #include <string.h>
 
@@ -22,8 +24,10 @@ int gsr_set_error_msg(int code, const char* msg) {
 namespace {
 struct ProfEntry { const char* name; unsigned long long count; double ms; };
 struct ProfPending { int slot; cudaEvent_t e0, e1; };
-bool g_prof_on = false;
-unsigned long long g_launches = 0;
+// launches may come from several host threads (one per stream): the counter is atomic, the profiler tables sit behind a mutex
+std::atomic<bool> g_prof_on{false};
+std::atomic<unsigned long long> g_launches{0};
+std::mutex g_prof_mu;
 ProfEntry g_prof[64];
 int g_prof_n = 0;
 ProfPending g_pending[4096];
@@ -50,7 +54,8 @@ void prof_collect() {
 GsrProfScope::GsrProfScope(const char* name, cudaStream_t s) : slot(-1), stream(s) {
     g_launches++;
     if (!g_prof_on) return;
-    if (g_pending_n >= 4096) prof_collect();
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (g_pending_n >= 4095) prof_collect();
     slot = prof_slot(name);
     g_prof[slot].count++;
     ProfPending& p = g_pending[g_pending_n];
@@ -58,11 +63,12 @@ GsrProfScope::GsrProfScope(const char* name, cudaStream_t s) : slot(-1), stream(
     cudaEventCreate(&p.e0);
     cudaEventCreate(&p.e1);
     cudaEventRecord(p.e0, stream);
+    pending = g_pending_n++;
 }
 GsrProfScope::~GsrProfScope() {
     if (slot < 0) return;
-    cudaEventRecord(g_pending[g_pending_n].e1, stream);
-    g_pending_n++;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (pending < g_pending_n && g_pending[pending].slot == slot) cudaEventRecord(g_pending[pending].e1, stream);
 }
 
 namespace {
@@ -169,16 +175,16 @@ extern "C" {
 const char* gsr_last_error_string(void) { return g_err; }
 
 void gsr_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     prof_collect();
     g_prof_on = on != 0;
     if (on) { g_prof_n = 0; }
 }
 unsigned long long gsr_launch_count(int reset) {
-    const unsigned long long n = g_launches;
-    if (reset) g_launches = 0;
-    return n;
+    return reset ? g_launches.exchange(0) : g_launches.load();
 }
 int gsr_profile_dump(char* out, size_t cap) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     prof_collect();
     size_t o = 0;
     if (cap) out[0] = 0;

@@ -73,7 +73,7 @@ int gsr_set_error_msg(int code, const char* msg);
 struct GsrProfScope {
     GsrProfScope(const char* name, cudaStream_t stream);
     ~GsrProfScope();
-    int slot; cudaStream_t stream;
+    int slot; cudaStream_t stream; int pending;
 };
 
 static inline int gsr_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
