@@ -342,9 +342,7 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
             return loss.detach()
 
         total = view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams)
-        if world > 1:
-            opt.grads.all_reduce()
-        opt.step()
+        opt.all_reduce_and_step(chunks=8)          # N > 1: all-reduce in 8 pieces, Adam on each piece as it arrives
         return total
     from oracle import loss_port, ref_driver, rigid_body_port
     opt.zero_grad(set_to_none=True)

@@ -99,12 +99,8 @@ class FusedAdam:
         # they are zeroed in place and stay attached (accumulate_grads / the all-reduce use the same memory)
         self.grads.zero_()
 
-    def step(self, skip=()):
-        """One Adam step on every group except those named (or indexed) in `skip`: a skipped group is what
-        torch.optim.Adam does for parameters whose .grad is None - values, moments and step count untouched."""
-        lib = _rt.load()
-        n = len(self.param_groups)
-        begin = (ctypes.c_ulonglong * (n + 1))(*self._begin)
+    def _hyper(self, skip):
+        """Per-group step sizes / bias corrections of THIS step (advances the step counts of the groups that step)."""
         ss, bc, b1s, b2s, es = [], [], [], [], []
         for i, g in enumerate(self.param_groups):
             if i in skip or g.get("name") in skip:
@@ -119,13 +115,47 @@ class FusedAdam:
             ss.append(g["lr"] / bias_correction1)
             bc.append(bias_correction2 ** 0.5)
             b1s.append(b1); b2s.append(b2); es.append(g["eps"])
+        return ss, bc, b1s, b2s, es
+
+    def _launch(self, hyper, lo=0, hi=None):
+        """The Adam kernel on elements [lo, hi) of the flat buffers (lo, hi multiples of 4)."""
+        lib = _rt.load()
+        n = len(self.param_groups)
+        total = self._begin[-1]
+        hi = total if hi is None else hi
+        ss, bc, b1s, b2s, es = hyper
+        clip = [min(max(b, lo), hi) - lo for b in self._begin]
+        begin = (ctypes.c_ulonglong * (n + 1))(*clip)
         arr = lambda v: (ctypes.c_float * n)(*v)
+        darr = lambda v: (ctypes.c_double * n)(*v)
         dev = self.flat_params.device
+        off = 4 * lo
         with torch.cuda.device(dev):
-            darr = lambda v: (ctypes.c_double * n)(*v)
-            _rt.check(lib.gsr_adam_step(self.flat_params.data_ptr(), self.grads.flat.data_ptr(), self.exp_avg.data_ptr(),
-                                        self.exp_avg_sq.data_ptr(), n, begin, arr(ss), arr(bc), darr(b1s), darr(b2s), arr(es),
-                                        _rt.stream_ptr(dev)))
+            _rt.check(lib.gsr_adam_step(self.flat_params.data_ptr() + off, self.grads.flat.data_ptr() + off,
+                                        self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off, n, begin,
+                                        arr(ss), arr(bc), darr(b1s), darr(b2s), arr(es), _rt.stream_ptr(dev)))
+
+    def step(self, skip=()):
+        """One Adam step on every group except those named (or indexed) in `skip`: a skipped group is what
+        torch.optim.Adam does for parameters whose .grad is None - values, moments and step count untouched."""
+        self._launch(self._hyper(skip))
+
+    def all_reduce_and_step(self, chunks=8, group=None, skip=()):
+        """View-parallel training: sum the flat gradient buffer over the ranks and step, PIPELINED - the buffer is
+        all-reduced in `chunks` pieces issued back to back on NCCL's stream, and the Adam kernel runs on each piece as soon
+        as it has arrived, so the optimizer pass hides under the collective instead of following it."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.step(skip)
+        total = self._begin[-1]
+        per = (total // max(1, chunks) + 7) // 8 * 8
+        bounds = [(lo, min(total, lo + per)) for lo in range(0, total, per)] if per > 0 else [(0, total)]
+        flat = self.grads.flat
+        works = [dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True) for lo, hi in bounds]
+        hyper = self._hyper(skip)
+        for w, (lo, hi) in zip(works, bounds):
+            w.wait()                                   # the current stream waits for this piece (no host block)
+            self._launch(hyper, lo, hi)
 
     # -- optimizer-state surgery of densification (scene/gaussian_model.py:1027-1100) on the flat buffers --
     def _group_views(self, buf):
