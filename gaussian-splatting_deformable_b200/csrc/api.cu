@@ -124,7 +124,7 @@ int tile_bits(uint32_t n) {
     if (n >> msb) msb++;
     return msb;
 }
-struct BinLayout { size_t tkeys_a, tkeys_b, vals_a, vals_b, sort_temp, sort_temp_bytes, keys64, matrix, totals, tile_base, bytes;
+struct BinLayout { size_t tkeys_a, tkeys_b, vals_a, vals_b, sort_temp, sort_temp_bytes, keys64, matrix, totals, tile_base, masks, bytes;
                    int tile_bits; int passes; int sweep; };
 BinLayout bin_layout(uint32_t R, int W, int H) {
     BinLayout L{};
@@ -144,6 +144,7 @@ BinLayout bin_layout(uint32_t R, int W, int H) {
     L.matrix = o; o += al(gsr_tile_matrix_bytes(gx, gy));
     L.totals = o; o += al(4 * (size_t)tiles);
     L.tile_base = o; o += al(4 * (size_t)tiles);
+    L.masks = o; o += al(4 * gsr_region_mask_words(R, (int)tiles));     // survivors of the per-region cull (blend_fwd_v2 -> blend_bwd_v2)
     L.bytes = o + 256;
     return L;
 }
@@ -400,6 +401,8 @@ static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const in
     b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
     b.bg[0] = view->bg[0]; b.bg[1] = view->bg[1]; b.bg[2] = view->bg[2];
     b.out_color = out_color;
+    if (point_list && gsr_blend_region_masks_enabled())
+        b.region_masks = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(binning_ws) + bin_layout(R, v.W, v.H).masks);
     b.final_T = reinterpret_cast<float*>(iw + IL.final_T);
     b.n_contrib = reinterpret_cast<uint32_t*>(iw + IL.n_contrib);
     if (int rc = gsr_launch_blend_fwd(b, stream)) return rc;
@@ -518,6 +521,7 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
         b.n_contrib = reinterpret_cast<const uint32_t*>(iw + IL.n_contrib);
         b.dL_dpix = dL_dout_color;
         b.grad_recs = grad_recs;
+        if (gsr_blend_region_masks_enabled()) b.region_masks = reinterpret_cast<const uint32_t*>(bw + BL.masks);
         if (int rc = gsr_launch_blend_bwd(b, stream)) return rc;
     }
     PreprocessBwdArgs a{};

@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdAr
     const uint2 range = a.ranges[tile];
     const int todo = (int)(range.y - range.x);
     float4* const q0s = s_q0[warp]; float4* const q1s = s_q1[warp]; float4* const q2s = s_q2[warp];
+    // region masks: word (batch, region) of this tile at NW * (range.x / 32 + tile + batch) + region
+    uint32_t* const mask_out = a.region_masks ? a.region_masks + (size_t)NW * ((size_t)(range.x >> 5) + (size_t)tile) + warp : nullptr;
 
     float4 n0, n1, n2;
     bool nvalid = false;
@@ -132,6 +134,8 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdAr
         if (base + 32 < todo) fetch(base + 32);
         const unsigned m = __ballot_sync(FULL, keep);
         const int n = __popc(m);
+        // the backward walks the same list for the same region: hand it the survivors of this batch (bit l = entry base + l)
+        if (mask_out && lane == 0) mask_out[(size_t)(base >> 5) * NW] = m;
         __syncwarp();                                // every lane is done reading the previous batch
         if (keep) {
             const int slot = __popc(m & ((1u << lane) - 1u));
@@ -264,9 +268,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // shared buffer and reduced together - lane (e, o) = (entry, octant) adds the 32 lane values of sum o of
 // entry e with eight LDS.128 - instead of a 14-shuffle butterfly per Gaussian (33 vs 59 instructions
 // per blended (region, Gaussian)).
-constexpr int RED_E = 4, RED_STRIDE = 36;             // entries per flush; padded row (conflict-free LDS.128)
+constexpr int RED_E = 4, RED_STRIDE = 36;             // entries per flush; padded row (ncu: bank conflicts on 1.6 % of the kernel's shared wavefronts)
 
-template <int NP, int MINB, bool SMEM_RED, bool STRAIGHT>
+template <int NP, int MINB, bool SMEM_RED, bool STRAIGHT, bool MASKS = false>
 __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdArgs a) {
     constexpr int NW = 4 / NP;
     __shared__ __align__(16) float s_red[SMEM_RED ? NW : 1][SMEM_RED ? RED_E * 9 * RED_STRIDE : 1];
@@ -314,12 +318,22 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
     float4* const q0s = s_q0[warp]; float4* const q1s = s_q1[warp]; float4* const q2s = s_q2[warp];
     float* const grad_base = reinterpret_cast<float*>(a.grad_recs);
 
+    // With the forward's region masks the list is walked in the forward's 32-entry batches (back to front: lane l takes
+    // position 32 b + 31 - l) and only the survivors of the forward's cull are fetched at all; without them the cull is
+    // repeated here on batches counted back from the deepest contributor.
+    const uint32_t* const mask_in = MASKS ? a.region_masks + (size_t)NW * ((size_t)(range.x >> 5) + (size_t)tile) + warp : nullptr;
     float4 n0, n1, n2;
     uint32_t nid = 0;
     bool nvalid = false;
+    int npos = 0;
     auto fetch = [&](int start) {          // positions start-1, start-2, ... (back to front)
         const int pos = start - 1 - lane;
+        npos = pos;
         nvalid = pos >= 0;
+        if (MASKS) {
+            const uint32_t mk = __ldg(mask_in + (size_t)((start - 1) >> 5) * NW);       // start is a multiple of 32
+            nvalid = nvalid && ((mk >> (pos & 31)) & 1u) && pos < (int)wlast;
+        }
         if (nvalid) {
             nid = a.point_list[range.x + pos];
             const float4* r = a.recs + 3 * (size_t)nid;
@@ -357,11 +371,14 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
         }
         __syncwarp();
     };
-    if (wlast > 0) fetch((int)wlast);
-    for (int start = (int)wlast; start > 0; start -= 32) {
+    const int start0 = MASKS ? (int)((wlast + 31u) & ~31u) : (int)wlast;
+    if (wlast > 0) fetch(start0);
+    for (int start = start0; start > 0; start -= 32) {
         const float4 c0 = n0, c1 = n1, c2 = n2;
         const uint32_t cid = nid;
-        const bool keep = nvalid && rect_may_contribute(c0.x, c0.y, c0.z, c0.w, c1.x, c2.y, rx0, ry0, rx1, ry1);
+        const int cpos = npos;
+        bool keep = nvalid;
+        if (!MASKS) keep = keep && rect_may_contribute(c0.x, c0.y, c0.z, c0.w, c1.x, c2.y, rx0, ry0, rx1, ry1);
         if (start - 32 > 0) fetch(start - 32);
         const unsigned m = __ballot_sync(FULL, keep);
         const int n = __popc(m);
@@ -369,7 +386,7 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
         if (keep) {
             const int slot = __popc(m & ((1u << lane) - 1u));
             q0s[slot] = make_float4(c0.x, c0.y, c0.z, -c0.w);
-            q1s[slot] = make_float4(c1.x, c1.y, c2.y, __uint_as_float((uint32_t)(start - 1 - lane)));
+            q1s[slot] = make_float4(c1.x, c1.y, c2.y, __uint_as_float((uint32_t)cpos));
             q2s[slot] = make_float4(c1.z, c1.w, c2.x, __uint_as_float(cid));
         }
         __syncwarp();
@@ -496,6 +513,15 @@ int env_int_v2(const char* name, int dflt) {
 
 }  // namespace
 
+// The forward's region masks are usable by the backward only when both run the second-generation kernels with the same
+// region shape (GSR_BLEND_MASKS=0 switches them off: the backward then repeats the cull, as in round 1).
+int gsr_blend_region_masks_enabled() {
+    static const int on = env_int_v2("GSR_BLEND_MASKS", 1) && env_int_v2("GSR_BLEND_FWD_V", 2) == 2 && env_int_v2("GSR_BLEND_BWD_V", 2) == 2 &&
+                          env_int_v2("GSR_FWD_NP", 1) == 1 && env_int_v2("GSR_BWD_NP", 1) == 1 && env_int_v2("GSR_BWD_MINB", 0) < 8 &&
+                          env_int_v2("GSR_BWD_SMEM_RED", 1) && env_int_v2("GSR_BWD_STRAIGHT", 1);      // the default backward variant reads them
+    return on;
+}
+
 int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
     dim3 grid(a.grid_x, a.grid_y, 1);
     static const int np = env_int_v2("GSR_FWD_NP", 1);
@@ -527,7 +553,8 @@ int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream) {
     } else if (minb >= 8) {
         blend_bwd_v2_kernel<1, 8, false, false><<<grid, 128, 0, stream>>>(a);
     } else if (straight && sred) {
-        blend_bwd_v2_kernel<1, 0, true, true><<<grid, 128, 0, stream>>>(a);
+        if (a.region_masks) blend_bwd_v2_kernel<1, 0, true, true, true><<<grid, 128, 0, stream>>>(a);
+        else blend_bwd_v2_kernel<1, 0, true, true><<<grid, 128, 0, stream>>>(a);
     } else {
         if (sred) blend_bwd_v2_kernel<1, 0, true, false><<<grid, 128, 0, stream>>>(a);
         else blend_bwd_v2_kernel<1, 0, false, false><<<grid, 128, 0, stream>>>(a);

@@ -120,6 +120,8 @@ struct BlendFwdArgs {
     float* out_color;        // [3,H,W]
     float* final_T;          // [H*W]
     uint32_t* n_contrib;     // [H*W]
+    uint32_t* region_masks;  // [4 (range.x / 32 + tile) ...]: survivors of the per-region cull, one bit per list entry, one word per
+                             // (8x8 region, 32-entry batch); written by blend_fwd_v2, read by blend_bwd_v2 (null: not kept)
 };
 int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream);
 int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream);      // blend_v2.cu
@@ -133,9 +135,13 @@ struct BlendBwdArgs {
     const float* final_T; const uint32_t* n_contrib;
     const float* dL_dpix;    // [3,H,W]
     float4* grad_recs;       // [P,3], zero-initialised by the caller
+    const uint32_t* region_masks;   // see BlendFwdArgs (null: the backward repeats the cull)
 };
+// words of the region-mask array for R list entries over num_tiles tiles (a tile's batches start at range.x / 32 + tile)
+static inline size_t gsr_region_mask_words(uint32_t R, int num_tiles) { return 4 * ((size_t)R / 32 + (size_t)num_tiles + 1); }
 int gsr_launch_blend_bwd(const BlendBwdArgs& a, cudaStream_t stream);
 int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream);   // blend_v2.cu
+int gsr_blend_region_masks_enabled();  // 1 when blend_fwd_v2 writes and blend_bwd_v2 reads the per-region survivor masks
 int gsr_blend_bwd_writes_moments();   // 1 when the selected blend backward writes the moment form of the gradient record
 
 // ---- fused per-Gaussian backward ------------------------------------------
