@@ -406,8 +406,26 @@ def deform_network_timing(impl, P, dev, steps=3):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / steps
     t_f, t_fb = timed(fwd), timed(fwd_bwd)
+    # ... and with the activation glue of render() (gaussian_renderer/__init__.py:79,116,122,140) between the network and the
+    # rasterizer: ours = deform_mlp.deform_glue (one kernel each way), reference = the torch ops render() uses
+    mk = lambda *sh: torch.randn(*sh, generator=g).to(dev).requires_grad_(True)
+    scaling, rotation, f_dc, f_rest = mk(P, 3), mk(P, 4), mk(P, 1, 3), mk(P, 15, 3)
+    gout = [torch.randn(sh, generator=g).to(dev) for sh in ((P, 3), (P, 3), (P, 4), (P, 16, 3))]
+
+    def fwd_bwd_glue():
+        x = x0.clone().requires_grad_(True)
+        for p in list(net.parameters()) + [scaling, rotation, f_dc, f_rest]:
+            p.grad = None
+        if impl == "ours":
+            outs = deform_mlp.deform_glue(net.heads(x, ts, 5000), x, scaling, rotation, f_dc, f_rest)
+        else:
+            dx, ds, dr, dsh = net(x, ts, 5000)
+            outs = (x + dx, torch.exp(scaling + ds), torch.nn.functional.normalize(rotation + dr),
+                    torch.cat((f_dc, f_rest), dim=1) + dsh.reshape(-1, 16, 3))
+        torch.autograd.backward(outs, gout)
+    t_fbg = timed(fwd_bwd_glue)
     flops = 2.0 * P * (64 * 256 + 6 * 256 * 256 + 320 * 256 + 256 * 58)
-    out = {"P": P, "fwd_ms": round(t_f, 3), "fwd_bwd_ms": round(t_fb, 3),
+    out = {"P": P, "fwd_ms": round(t_f, 3), "fwd_bwd_ms": round(t_fb, 3), "fwd_bwd_with_activation_glue_ms": round(t_fbg, 3),
            "fwd_fp32_equivalent_TFLOPs": round(flops / t_f / 1e9, 1),
            "what": "DirectTemporalNeRF (84 -> 8 x 256 ReLU, skip at 4 -> heads 3/3/4/48) over all P Gaussians, one time value"}
     if impl == "ours":

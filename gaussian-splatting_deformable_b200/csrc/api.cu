@@ -620,6 +620,23 @@ int gsr_densify_prune(int P, const float* opacity_raw, const float* scaling_raw,
                                     (cudaStream_t)stream_);
 }
 
+int gsr_deform_glue_forward(int P, const float* heads, const float* xyz, const float* scaling, const float* rotation, const float* f_dc,
+                            const float* f_rest, float* means3D, float* scales, float* rotations, float* shs, void* stream_) {
+    if (P > 0 && (!heads || !xyz || !scaling || !rotation || !f_dc || !f_rest || !means3D || !scales || !rotations || !shs))
+        return gsr_set_error_msg(-1, "deform_glue_forward: NULL pointer");
+    if (reinterpret_cast<uintptr_t>(heads) & 15) return gsr_set_error_msg(-2, "deform_glue_forward: heads must be 16-byte aligned");
+    return gsr_launch_deform_glue_fwd(P, heads, xyz, scaling, rotation, f_dc, f_rest, means3D, scales, rotations, shs, (cudaStream_t)stream_);
+}
+int gsr_deform_glue_backward(int P, const float* heads, const float* rotation, const float* scales, const float* g_means, const float* g_scales,
+                             const float* g_rotations, const float* g_shs, float* d_heads, float* d_xyz, float* d_scaling, float* d_rotation,
+                             float* d_f_dc, float* d_f_rest, void* stream_) {
+    if (P > 0 && (!heads || !rotation || !scales || !d_heads)) return gsr_set_error_msg(-1, "deform_glue_backward: NULL pointer");
+    if ((reinterpret_cast<uintptr_t>(heads) | reinterpret_cast<uintptr_t>(d_heads)) & 15)
+        return gsr_set_error_msg(-2, "deform_glue_backward: heads / d_heads must be 16-byte aligned");
+    return gsr_launch_deform_glue_bwd(P, heads, rotation, scales, g_means, g_scales, g_rotations, g_shs, d_heads, d_xyz, d_scaling, d_rotation,
+                                      d_f_dc, d_f_rest, (cudaStream_t)stream_);
+}
+
 size_t gsr_knn_bytes(int P) { return gsr_knn_temp_bytes(P); }
 int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream_) {
     if (P > 0 && (!points || !mean_dist2 || !temp)) return gsr_set_error_msg(-1, "knn: NULL pointer");

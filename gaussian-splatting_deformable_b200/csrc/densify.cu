@@ -116,3 +116,106 @@ int gsr_launch_densify_prune(int P, const float* opacity_raw, const float* scali
     GSR_CHECK_LAUNCH();
     return 0;
 }
+
+// ---- activation glue between the deformation network and the rasterizer (gaussian_renderer/__init__.py:79,116,122,140) ------
+// render() turns the network's four heads into the rasterizer's inputs with ~10 torch element-wise kernels per view:
+//   means3D = _xyz + dx;  scales = exp(_scaling + dscale);  rotations = normalize(_rotation + drot);
+//   shs = cat(_features_dc, _features_rest) + dshs.reshape(-1, 16, 3)
+// One pass here (488 B read, 232 B written per Gaussian), and one pass for the backward.
+namespace {
+
+__global__ void __launch_bounds__(256) glue_fwd_kernel(int P, const float* __restrict__ heads /*[P x 64]: dx 0-2, dscale 3-5, drot 6-9, dshs 10-57*/,
+                                                      const float* __restrict__ xyz, const float* __restrict__ scaling, const float* __restrict__ rotation,
+                                                      const float* __restrict__ f_dc /*[P,1,3]*/, const float* __restrict__ f_rest /*[P,15,3]*/,
+                                                      float* __restrict__ means3D, float* __restrict__ scales, float* __restrict__ rotations,
+                                                      float* __restrict__ shs /*[P,16,3]*/) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    const float4* h4 = reinterpret_cast<const float4*>(heads + 64 * (size_t)i);
+    float h[64];
+#pragma unroll
+    for (int j = 0; j < 15; j++) { const float4 q = __ldg(h4 + j); h[4 * j] = q.x; h[4 * j + 1] = q.y; h[4 * j + 2] = q.z; h[4 * j + 3] = q.w; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        means3D[3 * (size_t)i + k] = xyz[3 * (size_t)i + k] + h[k];
+        scales[3 * (size_t)i + k] = expf(scaling[3 * (size_t)i + k] + h[3 + k]);
+    }
+    float q[4], n2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { q[k] = rotation[4 * (size_t)i + k] + h[6 + k]; n2 += q[k] * q[k]; }
+    const float inv = 1.0f / fmaxf(sqrtf(n2), 1e-12f);            // torch.nn.functional.normalize: x / max(|x|, eps)
+#pragma unroll
+    for (int k = 0; k < 4; k++) rotations[4 * (size_t)i + k] = q[k] * inv;
+    float* o = shs + 48 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = f_dc[3 * (size_t)i + k] + h[10 + k];
+#pragma unroll
+    for (int k = 3; k < 48; k++) o[k] = f_rest[45 * (size_t)i + k - 3] + h[10 + k];
+}
+
+// gradients: d heads [P x 64] (columns 58-63 zero), d _xyz = g_means, d _scaling = g_scales * scales,
+// d _rotation = (g - r (r.g)) / max(|q|, eps) with r = normalised q, d features = g_shs
+__global__ void __launch_bounds__(256) glue_bwd_kernel(int P, const float* __restrict__ heads, const float* __restrict__ rotation,
+                                                      const float* __restrict__ scales, const float* __restrict__ g_means,
+                                                      const float* __restrict__ g_scales, const float* __restrict__ g_rot,
+                                                      const float* __restrict__ g_shs, float* __restrict__ d_heads,
+                                                      float* __restrict__ d_xyz, float* __restrict__ d_scaling, float* __restrict__ d_rotation,
+                                                      float* __restrict__ d_f_dc, float* __restrict__ d_f_rest) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    float d[64];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float gm = g_means ? g_means[3 * (size_t)i + k] : 0.0f;
+        const float gs = g_scales ? g_scales[3 * (size_t)i + k] * scales[3 * (size_t)i + k] : 0.0f;
+        d[k] = gm; d[3 + k] = gs;
+        if (d_xyz) d_xyz[3 * (size_t)i + k] = gm;
+        if (d_scaling) d_scaling[3 * (size_t)i + k] = gs;
+    }
+    float q[4], g[4], n2 = 0.0f, rg = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { q[k] = rotation[4 * (size_t)i + k] + heads[64 * (size_t)i + 6 + k]; n2 += q[k] * q[k]; g[k] = g_rot ? g_rot[4 * (size_t)i + k] : 0.0f; }
+    const float nrm = sqrtf(n2);
+    const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) rg += q[k] * inv * g[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float dq = nrm > 1e-12f ? (g[k] - q[k] * inv * rg) * inv : g[k] * inv;
+        d[6 + k] = dq;
+        if (d_rotation) d_rotation[4 * (size_t)i + k] = dq;
+    }
+#pragma unroll
+    for (int k = 0; k < 48; k++) {
+        const float gv = g_shs ? g_shs[48 * (size_t)i + k] : 0.0f;
+        d[10 + k] = gv;
+        if (k < 3) { if (d_f_dc) d_f_dc[3 * (size_t)i + k] = gv; }
+        else if (d_f_rest) d_f_rest[45 * (size_t)i + k - 3] = gv;
+    }
+#pragma unroll
+    for (int k = 58; k < 64; k++) d[k] = 0.0f;
+    float4* o = reinterpret_cast<float4*>(d_heads + 64 * (size_t)i);
+#pragma unroll
+    for (int j = 0; j < 16; j++) o[j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+}
+
+}  // namespace
+
+int gsr_launch_deform_glue_fwd(int P, const float* heads, const float* xyz, const float* scaling, const float* rotation, const float* f_dc,
+                               const float* f_rest, float* means3D, float* scales, float* rotations, float* shs, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    { GsrProfScope prof_("deform_glue_fwd", stream);
+    glue_fwd_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, heads, xyz, scaling, rotation, f_dc, f_rest, means3D, scales, rotations, shs); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+int gsr_launch_deform_glue_bwd(int P, const float* heads, const float* rotation, const float* scales, const float* g_means, const float* g_scales,
+                               const float* g_rot, const float* g_shs, float* d_heads, float* d_xyz, float* d_scaling, float* d_rotation,
+                               float* d_f_dc, float* d_f_rest, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    { GsrProfScope prof_("deform_glue_bwd", stream);
+    glue_bwd_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, heads, rotation, scales, g_means, g_scales, g_rot, g_shs, d_heads, d_xyz, d_scaling,
+                                                            d_rotation, d_f_dc, d_f_rest); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}

@@ -231,3 +231,8 @@ int gsr_launch_densify_split(int n, int N, const float* xyz, const float* scalin
                              float* new_scaling, cudaStream_t stream);
 int gsr_launch_densify_prune(int P, const float* opacity_raw, const float* scaling_raw, const float* max_radii, float min_opacity,
                              float max_screen_size, float world_size_limit, int use_size, uint8_t* prune, cudaStream_t stream);
+int gsr_launch_deform_glue_fwd(int P, const float* heads, const float* xyz, const float* scaling, const float* rotation, const float* f_dc,
+                               const float* f_rest, float* means3D, float* scales, float* rotations, float* shs, cudaStream_t stream);
+int gsr_launch_deform_glue_bwd(int P, const float* heads, const float* rotation, const float* scales, const float* g_means, const float* g_scales,
+                               const float* g_rot, const float* g_shs, float* d_heads, float* d_xyz, float* d_scaling, float* d_rotation,
+                               float* d_f_dc, float* d_f_rest, cudaStream_t stream);

@@ -246,6 +246,60 @@ class _DeformMLPFn(torch.autograd.Function):
         return (dx if ctx.needs_input_grad[0] else None, None, None, None, None, *gw, *gb)
 
 
+class _GlueFn(torch.autograd.Function):
+    """(heads [P x 64], _xyz, _scaling, _rotation, _features_dc, _features_rest) -> (means3D, scales, rotations, shs): the
+    reference's activation glue (gaussian_renderer/__init__.py:79,116,122,140) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, heads, xyz, scaling, rotation, f_dc, f_rest):
+        lib = _rt.load()
+        if not heads.is_cuda:
+            raise _rt.GsrError("deform_glue runs on CUDA tensors only (no CPU fallback)")
+        dev = heads.device
+        P = int(xyz.shape[0])
+        c = lambda t: t.detach().float().contiguous()
+        h, x, sc, ro, dc, fr = c(heads), c(xyz), c(scaling), c(rotation), c(f_dc), c(f_rest)
+        if h.shape != (P, EMBED) or fr.numel() != P * 45 or dc.numel() != P * 3:
+            raise _rt.GsrError("deform_glue: heads must be [P, 64] and the features [P,1,3] / [P,15,3] (SH degree 3)")
+        f32 = dict(dtype=torch.float32, device=dev)
+        means, scales, rots, shs = torch.empty((P, 3), **f32), torch.empty((P, 3), **f32), torch.empty((P, 4), **f32), torch.empty((P, 16, 3), **f32)
+        with torch.cuda.device(dev):
+            _rt.check(lib.gsr_deform_glue_forward(P, h.data_ptr(), x.data_ptr(), sc.data_ptr(), ro.data_ptr(), dc.data_ptr(), fr.data_ptr(),
+                                                  means.data_ptr(), scales.data_ptr(), rots.data_ptr(), shs.data_ptr(), _rt.stream_ptr(dev)))
+        ctx.save_for_backward(h, ro, scales)
+        ctx.shapes = (tuple(f_dc.shape), tuple(f_rest.shape))
+        return means, scales, rots, shs
+
+    @staticmethod
+    def backward(ctx, g_means, g_scales, g_rots, g_shs):
+        lib = _rt.load()
+        h, ro, scales = ctx.saved_tensors
+        dev = h.device
+        P = int(h.shape[0])
+        f32 = dict(dtype=torch.float32, device=dev)
+        c = lambda t: None if t is None else t.detach().float().contiguous()
+        gm, gs, gr, gh = c(g_means), c(g_scales), c(g_rots), c(g_shs)
+        need = ctx.needs_input_grad
+        d_heads = torch.empty((P, EMBED), **f32)
+        d_xyz = torch.empty((P, 3), **f32) if need[1] else None
+        d_sc = torch.empty((P, 3), **f32) if need[2] else None
+        d_ro = torch.empty((P, 4), **f32) if need[3] else None
+        d_dc = torch.empty(ctx.shapes[0], **f32) if need[4] else None
+        d_fr = torch.empty(ctx.shapes[1], **f32) if need[5] else None
+        with torch.cuda.device(dev):
+            _rt.check(lib.gsr_deform_glue_backward(P, h.data_ptr(), ro.data_ptr(), scales.data_ptr(), _rt.ptr(gm), _rt.ptr(gs), _rt.ptr(gr),
+                                                   _rt.ptr(gh), d_heads.data_ptr(), _rt.ptr(d_xyz), _rt.ptr(d_sc), _rt.ptr(d_ro),
+                                                   _rt.ptr(d_dc), _rt.ptr(d_fr), _rt.stream_ptr(dev)))
+        return (d_heads if need[0] else None, d_xyz, d_sc, d_ro, d_dc, d_fr)
+
+
+def deform_glue(heads, xyz, scaling, rotation, features_dc, features_rest):
+    """What render() does between `pc.get_xyz_all` and the rasterizer call (gaussian_renderer/__init__.py:79,116,122,140),
+    fused: returns (means3D, scales, rotations, shs) from the network's raw output `heads` [P x 64] (see
+    DirectTemporalNeRF.heads) and the model's pre-activation tensors."""
+    return _GlueFn.apply(heads, xyz, scaling, rotation, features_dc, features_rest)
+
+
 def _check_pipeline(err):
     if int(err.item()) != 0:
         raise _rt.GsrError("deform_mlp: a tensor-core pipeline wait timed out (workspace corrupted?)")
@@ -305,6 +359,14 @@ class DirectTemporalNeRF(_Trunk):
             return z(3), z(3), z(4), z(48)
         out = self._run(x, te, [self._time_out, self._time_out_scale, self._time_out_rot, self._time_out_shs])
         return out[:, 0:3], out[:, 3:6], out[:, 6:10], out[:, 10:58]
+
+    def heads(self, x, ts, iteration=1 << 30):
+        """The raw [P x 64] output (dx 0-2, dscale 3-5, drot 6-9, dshs 10-57, 6 zero columns) for `deform_glue`; zeros while
+        iteration < 3000 like forward()."""
+        if iteration < 3000:
+            return torch.zeros((x.shape[0], EMBED), dtype=torch.float32, device=x.device)
+        t0 = ts.reshape(-1)[:1].detach().float().to(x.device) if torch.is_tensor(ts) else float(ts)
+        return self._run(x, time_embedding(t0).to(x.device), [self._time_out, self._time_out_scale, self._time_out_rot, self._time_out_shs])
 
 
 def screw_from_raw(w_raw, v_raw, eps=0.0):

@@ -113,6 +113,8 @@ _SIGNATURES = {
     "gsr_densify_decide": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_float, ctypes.c_float, _P, _P]),
     "gsr_densify_split": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "gsr_densify_prune": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, _P, _P]),
+    "gsr_deform_glue_forward": (ctypes.c_int, [ctypes.c_int] + [_P] * 11),
+    "gsr_deform_glue_backward": (ctypes.c_int, [ctypes.c_int] + [_P] * 14),
     "gsr_mark_visible": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, _P, _P, _P]),
     "gsr_knn_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_knn_dist2": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_size_t, _P]),

@@ -268,6 +268,16 @@ int gsr_densify_split(int n, int N, const float* xyz, const float* scaling_raw, 
 int gsr_densify_prune(int P, const float* opacity_raw, const float* scaling_raw, const float* max_radii2D, float min_opacity,
                       float max_screen_size, float world_size_limit, int use_size, uint8_t* prune, void* stream);
 
+/* Activation glue between the deformation network and the rasterizer (gaussian_renderer/__init__.py:79,116,122,140), one pass:
+ *   means3D = xyz + dx;  scales = exp(scaling + dscale);  rotations = normalize(rotation + drot);  shs = [f_dc | f_rest] + dshs
+ * heads = the network's output [P x 64] (dx 0-2, dscale 3-5, drot 6-9, dshs 10-57).  The backward takes the gradients w.r.t.
+ * the four outputs (any may be NULL = zero) and writes d_heads [P x 64] and, where non-NULL, the parameters' gradients. */
+int gsr_deform_glue_forward(int P, const float* heads, const float* xyz, const float* scaling, const float* rotation, const float* f_dc,
+                            const float* f_rest, float* means3D, float* scales, float* rotations, float* shs, void* stream);
+int gsr_deform_glue_backward(int P, const float* heads, const float* rotation, const float* scales, const float* g_means, const float* g_scales,
+                             const float* g_rotations, const float* g_shs, float* d_heads, float* d_xyz, float* d_scaling, float* d_rotation,
+                             float* d_f_dc, float* d_f_rest, void* stream);
+
 size_t gsr_knn_bytes(int P);
 int gsr_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, size_t temp_bytes, void* stream);
 

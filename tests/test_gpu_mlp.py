@@ -238,3 +238,37 @@ def test_deform_mlp_inside_the_reference_render():
     for n in ("xyz", "scaling", "opacity"):
         a, b = res[1][3][n].double(), res[0][3][n].double()
         assert float((a - b).abs().mean() / b.abs().mean()) <= 1e-3, n
+
+
+def test_fused_activation_glue_matches_the_reference_render_ops():
+    """gaussian_renderer/__init__.py:79,116,122,140 as one kernel each way, against the same torch ops."""
+    import deform_mlp
+    P = 50001
+    g = torch.Generator().manual_seed(4)
+    mk = lambda *s: torch.randn(*s, generator=g).cuda()
+    xyz, scaling, rotation, f_dc, f_rest = mk(P, 3), mk(P, 3) * 0.5 - 4, mk(P, 4), mk(P, 1, 3), mk(P, 15, 3) * 0.2
+    heads = torch.zeros(P, 64, device="cuda")
+    heads[:, :58] = mk(P, 58) * 0.1
+    gout = [mk(P, 3), mk(P, 3), mk(P, 4), mk(P, 16, 3)]
+    res = []
+    for fused in (False, True):
+        leaves = [t.clone().requires_grad_(True) for t in (heads, xyz, scaling, rotation, f_dc, f_rest)]
+        h, x, sc, ro, dc, fr = leaves
+        if fused:
+            outs = deform_mlp.deform_glue(h, x, sc, ro, dc, fr)
+        else:
+            outs = (x + h[:, 0:3], torch.exp(sc + h[:, 3:6]), torch.nn.functional.normalize(ro + h[:, 6:10]),
+                    torch.cat((dc, fr), dim=1) + h[:, 10:58].reshape(-1, 16, 3))
+        torch.autograd.backward(outs, gout)
+        res.append(([o.detach() for o in outs], [l.grad for l in leaves]))
+    for a, b in zip(res[1][0], res[0][0]):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
+    for a, b in zip(res[1][1], res[0][1]):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()) + 1e-9
+    # the network's raw output feeds it directly
+    torch.manual_seed(1)
+    net = deform_mlp.DirectTemporalNeRF().cuda()
+    hh = net.heads(xyz, 0.5)
+    dx = net(xyz, 0.5, 5000)[0]
+    assert hh.shape == (P, 64) and torch.equal(hh[:, 0:3], dx) and float(hh[:, 58:].abs().max()) == 0.0
+    assert float(net.heads(xyz, 0.5, 100).abs().max()) == 0.0
