@@ -726,7 +726,6 @@ def main():
         alg = {  # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x units per launch; R = last view's)
             "preprocess_fwd": (288.0 + twist_bytes) * args.P,
             "preprocess_bwd": (516.0 + 2 * twist_bytes) * args.P,
-            "depth_sort_onesweep_pass": 16.0 * args.P,     # depth order of the Gaussians: (u32 key, u32 id)
             # radix fallback path (GSR_BINNING_RADIX=1)
             "duplicate_with_keys": 8.0 * R + 28.0 * args.P,
             "tile_sort_onesweep_pass": 16.0 * R,
@@ -747,7 +746,7 @@ def main():
         # the whole binning stage against the reference scheme's traffic model (12 B/dup
         # duplicate + 152 B/dup 6-pass pair sort + 8 B/dup ranges); an implementation that moves fewer bytes
         # reads above what HBM could deliver to that scheme
-        bin_names = ("scan_block_sums", "sort_scan_hist", "depth_sort_onesweep_pass", "depth_sort_pass", "gather_rects", "tile_count",
+        bin_names = ("scan_block_sums", "depth_sort_hist", "depth_sort_scan", "depth_sort_scatter", "depth_sort_local", "tile_count",
                      "tile_sweep_count", "tile_column_scan", "tile_base_scan", "tile_scatter", "tile_sweep_scatter",
                      "sorted_block_sums", "duplicate_with_keys", "tile_sort_onesweep_pass", "tile_ranges")
         bin_ms = sum(kernels[n]["total_ms"] for n in bin_names if n in kernels) / max(len(cams), 1)

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgsr_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "tile_sweep.cu", "radix_sort.cu", "blend.cu", "blend_v2.cu", "backward.cu", "knn.cu", "loss.cu", "adam.cu", "mlp_gemm.cu", "densify.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "tile_sweep.cu", "radix_sort.cu", "depth_sort.cu", "blend.cu", "blend_v2.cu", "backward.cu", "knn.cu", "loss.cu", "adam.cu", "mlp_gemm.cu", "densify.cu"]
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

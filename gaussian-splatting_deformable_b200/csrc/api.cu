@@ -76,10 +76,9 @@ namespace {
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct GeomLayout {
-    // the depth sort is 4 passes (even): its result lands back in the "a" buffers
-    size_t in_b_order() const { return dvals_a; }
-    size_t depths, tiles, recs, clamped, cov3d, block_sums, total, dkeys_a, dkeys_b, dvals_a, dvals_b,
-                    dsort_temp, dsort_temp_bytes, sblock_sums, rects, srec, bytes; };
+    size_t in_b_order() const { return dorder; }
+    size_t depths, tiles, recs, clamped, cov3d, block_sums, total, dkeys, dpairs_a, dpairs_b, dorder,
+                    dstate, dstate_bytes, sblock_sums, rects, srec, bytes; };
 GeomLayout geom_layout(int P) {
     GeomLayout L{};
     size_t o = 0;
@@ -91,11 +90,12 @@ GeomLayout geom_layout(int P) {
     L.cov3d = o; o += al(24 * p);
     L.block_sums = o; o += al(4 * ((p + 255) / 256 + 1));
     L.total = o; o += 256;
-    L.dkeys_a = o; o += al(4 * p);
-    L.dkeys_b = o; o += al(4 * p);
-    L.dvals_a = o; o += al(4 * p);
-    L.dvals_b = o; o += al(4 * p);
-    L.dsort_temp = o; L.dsort_temp_bytes = gsr_sort_temp_bytes((uint32_t)p, 0, 32); o += al(L.dsort_temp_bytes);
+    // depth sort (depth_sort.cu): keys, two pair buffers (bucketed pairs; scratch of the skew path), the order, the state
+    L.dkeys = o; o += al(4 * p);
+    L.dpairs_a = o; o += al(8 * p);
+    L.dpairs_b = o; o += al(8 * p);
+    L.dorder = o; o += al(4 * p);
+    L.dstate = o; L.dstate_bytes = gsr_depth_sort_state_bytes((uint32_t)p); o += al(L.dstate_bytes);
     L.sblock_sums = o; o += al(4 * ((p + 255) / 256 + 1));
     L.rects = o; o += al(8 * p);
     L.srec = o; o += al(16 * p);
@@ -259,20 +259,17 @@ static int forward_preprocess_impl(const gsr_view* view, int P, int M, const flo
     a.clamped = reinterpret_cast<uint8_t*>(ws + L.clamped);
     a.cov3D_out = debug_dump_cov3D ? reinterpret_cast<float*>(ws + L.cov3d) : nullptr;
     a.block_sums = reinterpret_cast<uint32_t*>(ws + L.block_sums);
-    a.depth_keys = reinterpret_cast<uint32_t*>(ws + L.dkeys_a);
-    a.depth_vals = reinterpret_cast<uint32_t*>(ws + L.dvals_a);
-    // the depth sort's state (histograms, tickets, look-back words) is zeroed here because the
-    // preprocess kernel accumulates the digit histograms of its depth keys
-    a.depth_hist = reinterpret_cast<uint32_t*>(ws + L.dsort_temp);
+    a.depth_keys = reinterpret_cast<uint32_t*>(ws + L.dkeys);
+    // the depth sort's state (control words, bucket counts, segment starts) is zeroed here because the preprocess
+    // kernel accumulates the key range in its control words; num_rendered, the prefiltered-violation flag and the
+    // tile-scan ticket live in spare control words of the same block (GsrDepthSortCtrl)
+    a.depth_state = reinterpret_cast<uint32_t*>(ws + L.dstate);
     a.rects = reinterpret_cast<uint2*>(ws + L.rects);
-    // num_rendered accumulates in a spare word of the (zeroed) sort state: tickets are words [0, 8), the error
-    // flag is word 63, words 61 and 62 serve the forward (tile-scan ticket, num_rendered)
-    // (word 60: prefiltered violation flag, read back together with num_rendered)
-    uint32_t* d_total = a.depth_hist + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 62;
+    uint32_t* d_total = a.depth_state + GSR_DS_NUM_RENDERED;
     a.total = d_total;
     a.prefiltered = view->prefiltered ? 1 : 0;
-    a.flags = a.depth_hist + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 60;
-    GSR_CHECK(cudaMemsetAsync(ws + L.dsort_temp, 0, L.dsort_temp_bytes, stream));
+    a.flags = a.depth_state + GSR_DS_PREFILTERED;
+    GSR_CHECK(cudaMemsetAsync(ws + L.dstate, 0, L.dstate_bytes, stream));
     if (int rc = gsr_launch_preprocess_fwd(a, v, stream)) return rc;
     if (!sync) return 0;            // capacity mode: counters and flags are read back by gsr_forward_render_capacity
     if (a.prefiltered) {
@@ -330,16 +327,15 @@ static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const in
         char* bw = reinterpret_cast<char*>(binning_ws);
         recs = reinterpret_cast<const float4*>(gw + L.recs);
         const uint32_t* tiles_touched = reinterpret_cast<const uint32_t*>(gw + L.tiles);
-        // 1. Gaussians in depth order (stable; emit-nothing Gaussians sink to the end)
-        uint32_t* dkeys_a = reinterpret_cast<uint32_t*>(gw + L.dkeys_a);
-        uint32_t* dkeys_b = reinterpret_cast<uint32_t*>(gw + L.dkeys_b);
-        uint32_t* dvals_a = reinterpret_cast<uint32_t*>(gw + L.dvals_a);
-        uint32_t* dvals_b = reinterpret_cast<uint32_t*>(gw + L.dvals_b);
-        int d_in_b = 0;
-        if (int rc = gsr_launch_sort_pairs32(dkeys_a, dkeys_b, dvals_a, dvals_b, (uint32_t)P, 0, 32, gw + L.dsort_temp,
-                                             L.dsort_temp_bytes, &d_in_b, stream, 1, true))
+        // 1. the emitting Gaussians in (depth bits, index) order, with their tile rects (srec)
+        uint32_t* const dstate = reinterpret_cast<uint32_t*>(gw + L.dstate);
+        uint32_t* const order = reinterpret_cast<uint32_t*>(gw + L.dorder);
+        if (int rc = gsr_launch_depth_sort((uint32_t)P, reinterpret_cast<const uint32_t*>(gw + L.dkeys), dstate,
+                                           reinterpret_cast<uint2*>(gw + L.dpairs_a), reinterpret_cast<uint2*>(gw + L.dpairs_b),
+                                           reinterpret_cast<const uint2*>(gw + L.rects), order, reinterpret_cast<uint4*>(gw + L.srec),
+                                           true, stream))
             return rc;
-        const uint32_t* order = d_in_b ? dvals_b : dvals_a;
+        const uint32_t* const n_emit = dstate + GSR_DS_N_EMIT;
         const uint32_t* sorted_tiles = nullptr;
         if (capacity_mode && !BL.sweep)
             return gsr_set_error_msg(-2, "forward_render_capacity: this image size takes the radix binning path, which needs the exact num_rendered");
@@ -347,16 +343,11 @@ static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const in
             // 2+3. stable counting sort of the (never materialised) duplicates by tile id
             const GsrTileBinPlan pl = gsr_make_tile_bin_plan(v.grid_x, v.grid_y);
             uint32_t* plist = reinterpret_cast<uint32_t*>(bw + BL.vals_a);
-            // emitting Gaussians = keys whose top byte is not 0xff = scanned top-digit histogram at bin 255
-            const uint32_t* n_emit = reinterpret_cast<const uint32_t*>(gw + L.dsort_temp) + 3 * GSR_SORT_RADIX + 255;
-            if (int rc = gsr_launch_tile_binning(P, n_emit, order, reinterpret_cast<const uint2*>(gw + L.rects),
-                                                 reinterpret_cast<uint4*>(gw + L.srec), pl, v.grid_x, v.grid_y,
+            if (int rc = gsr_launch_tile_binning(P, n_emit, reinterpret_cast<const uint4*>(gw + L.srec), pl, v.grid_x, v.grid_y,
                                                  reinterpret_cast<uint32_t*>(bw + BL.matrix),
                                                  reinterpret_cast<uint32_t*>(bw + BL.totals),
                                                  reinterpret_cast<uint32_t*>(bw + BL.tile_base), ranges, plist,
-                                                 reinterpret_cast<uint32_t*>(gw + L.dsort_temp) + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 61, stream,
-                                                 capacity_mode ? R : 0u,
-                                                 reinterpret_cast<uint32_t*>(gw + L.dsort_temp) + GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 59))
+                                                 dstate + GSR_DS_SCAN_TICKET, stream, capacity_mode ? R : 0u, dstate + GSR_DS_OVERFLOW))
                 return rc;
             point_list = plist;
             if (materialize_keys) {
@@ -368,7 +359,7 @@ static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const in
         // 2. offsets in that order, then the duplicates (tile id, Gaussian id)
         uint32_t* sblock = reinterpret_cast<uint32_t*>(gw + L.sblock_sums);
         uint32_t* d_total = reinterpret_cast<uint32_t*>(gw + L.total) + 1;
-        if (int rc = gsr_launch_sorted_block_sums(P, order, tiles_touched, sblock, stream)) return rc;
+        if (int rc = gsr_launch_sorted_block_sums(P, n_emit, order, tiles_touched, sblock, stream)) return rc;
         if (int rc = gsr_launch_scan_block_sums(sblock, gsr_div_up(P, 256), d_total, stream)) return rc;
         uint32_t* tkeys_a = reinterpret_cast<uint32_t*>(bw + BL.tkeys_a);
         uint32_t* tkeys_b = reinterpret_cast<uint32_t*>(bw + BL.tkeys_b);
@@ -376,7 +367,7 @@ static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const in
         uint32_t* vals_b = reinterpret_cast<uint32_t*>(bw + BL.vals_b);
         const GsrSortPlan tplan = gsr_make_sort_plan(0, BL.tile_bits);
         GSR_CHECK(cudaMemsetAsync(bw + BL.sort_temp, 0, BL.sort_temp_bytes, stream));
-        if (int rc = gsr_launch_duplicate(P, order, radii, tiles_touched, recs, sblock, tkeys_a, vals_a, v.grid_x,
+        if (int rc = gsr_launch_duplicate(P, n_emit, order, radii, tiles_touched, recs, sblock, tkeys_a, vals_a, v.grid_x,
                                           v.grid_y, tplan, reinterpret_cast<uint32_t*>(bw + BL.sort_temp), stream))
             return rc;
         // 3. stable sort by tile id only
@@ -407,10 +398,9 @@ static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const in
     b.n_contrib = reinterpret_cast<uint32_t*>(iw + IL.n_contrib);
     if (int rc = gsr_launch_blend_fwd(b, stream)) return rc;
     if (capacity_mode && host_status4 && P > 0 && geom_ws) {
-        // words 59..62 of the sort state: overflow flag, prefiltered violation, (scan ticket), num_rendered
+        // control words 59..62 of the depth-sort state: overflow flag, prefiltered violation, (scan ticket), num_rendered
         const GeomLayout L = geom_layout(P);
-        const uint32_t* st = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(geom_ws) + L.dsort_temp) +
-                             GSR_SORT_MAX_PASSES * GSR_SORT_RADIX + 59;
+        const uint32_t* st = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(geom_ws) + L.dstate) + GSR_DS_OVERFLOW;
         GSR_CHECK(cudaMemcpyAsync(host_status4, st, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     }
     return 0;
@@ -481,6 +471,51 @@ int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t R, const void* g
     b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
     GSR_CHECK(cudaMemsetAsync(out8, 0, 8 * sizeof(unsigned long long), stream));
     return gsr_launch_blend_stats(b, out8, stream);
+}
+
+// The depth sort on its own (tests, diagnostics): order[0 .. n) = indices of the keys != 0xffffffff by ascending (key, index).
+size_t gsr_depth_order_ws_bytes(int P) {
+    const size_t p = (size_t)(P > 0 ? P : 0);
+    return al(gsr_depth_sort_state_bytes((uint32_t)p)) + 2 * al(8 * p) + 256;
+}
+int gsr_depth_order(const uint32_t* keys, int P, void* ws, size_t ws_bytes, uint32_t* order, uint32_t* info2, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P < 0) return gsr_set_error_msg(-1, "depth_order: P must be >= 0");
+    if (P == 0) return 0;
+    if (!keys || !ws || !order) return gsr_set_error_msg(-1, "depth_order: NULL pointer");
+    if (ws_bytes < gsr_depth_order_ws_bytes(P)) return gsr_set_error_msg(-3, "depth_order: workspace too small");
+    char* w = reinterpret_cast<char*>(ws);
+    const size_t sb = al(gsr_depth_sort_state_bytes((uint32_t)P));
+    uint32_t* state = reinterpret_cast<uint32_t*>(w);
+    GSR_CHECK(cudaMemsetAsync(state, 0, sb, stream));
+    if (int rc = gsr_launch_depth_sort((uint32_t)P, keys, state, reinterpret_cast<uint2*>(w + sb),
+                                       reinterpret_cast<uint2*>(w + sb + al(8 * (size_t)P)), nullptr, order, nullptr, false, stream))
+        return rc;
+    if (info2) {   // device u32[2]: entries of order[], segments that took the skew path
+        GSR_CHECK(cudaMemcpyAsync(info2, state + GSR_DS_N_EMIT, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+        GSR_CHECK(cudaMemcpyAsync(info2 + 1, state + GSR_DS_SLOW_SEGMENTS, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    }
+    return 0;
+}
+
+// Debug: iteration counts of the blend walk under finer lane-group culls (blend_v2.cu: blend_group_stats_kernel); out32 = 32 u64.
+int gsr_debug_blend_group_stats(const gsr_view* view, int P, uint32_t R, const void* geom_ws, const void* binning_ws,
+                                const void* image_ws, unsigned long long* out32, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GsrView v;
+    if (int rc = fill_view(view, 0, v)) return rc;
+    if (P <= 0 || R == 0 || !geom_ws || !binning_ws || !image_ws || !out32) return gsr_set_error_msg(-1, "blend_group_stats: bad arguments");
+    const GeomLayout L = geom_layout(P);
+    const ImageLayout IL = image_layout(v.W, v.H);
+    const BinLayout BL = bin_layout(R, v.W, v.H);
+    const bool in_b = !BL.sweep && (BL.passes & 1) != 0;
+    BlendFwdArgs b{};
+    b.ranges = reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(image_ws) + IL.ranges);
+    b.point_list = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(binning_ws) + (in_b ? BL.vals_b : BL.vals_a));
+    b.recs = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(geom_ws) + L.recs);
+    b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
+    GSR_CHECK(cudaMemsetAsync(out32, 0, 32 * sizeof(unsigned long long), stream));
+    return gsr_launch_blend_group_stats(b, out32, stream);
 }
 
 int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* means3D, const float* means_deformed,

@@ -71,12 +71,12 @@ int gsr_launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* d
 // Stability makes the result identical to the reference's: inside a tile entries end
 // up ordered by (depth bits, Gaussian index), ties included.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sorted_block_sums_kernel(int P, const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(256) sorted_block_sums_kernel(int P, const uint32_t* __restrict__ n_emit, const uint32_t* __restrict__ order,
                                                                 const uint32_t* __restrict__ tiles_touched,
                                                                 uint32_t* __restrict__ block_sums) {
     __shared__ uint32_t wsum[8];
     const int i = blockIdx.x * 256 + threadIdx.x;
-    uint32_t s = (i < P) ? tiles_touched[order[i]] : 0u;
+    uint32_t s = (i < P && (uint32_t)i < *n_emit) ? tiles_touched[order[i]] : 0u;   // order[] holds the emitting Gaussians only
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(256) sorted_block_sums_kernel(int P, const uin
     }
 }
 
-int gsr_launch_sorted_block_sums(int P, const uint32_t* order, const uint32_t* tiles_touched, uint32_t* block_sums,
-                                 cudaStream_t stream) {
+int gsr_launch_sorted_block_sums(int P, const uint32_t* n_emit, const uint32_t* order, const uint32_t* tiles_touched,
+                                 uint32_t* block_sums, cudaStream_t stream) {
     if (P <= 0) return 0;
     { GsrProfScope prof_("sorted_block_sums", stream);
-    sorted_block_sums_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, order, tiles_touched, block_sums); }
+    sorted_block_sums_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, n_emit, order, tiles_touched, block_sums); }
     GSR_CHECK_LAUNCH();
     return 0;
 }
@@ -107,7 +107,7 @@ int gsr_launch_sorted_block_sums(int P, const uint32_t* order, const uint32_t* t
 // consecutive threads write consecutive words (fully coalesced), where the reference
 // has one thread serially emitting a whole rect.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* __restrict__ n_emit, const uint32_t* __restrict__ order,
                                                         const int* __restrict__ radii,
                                                         const uint32_t* __restrict__ tiles_touched,
                                                         const float4* __restrict__ recs,
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* _
     const int i = blockIdx.x * 256 + tid;
     for (int k = tid; k < 2 * GSR_SORT_RADIX; k += 256) s_hist[k] = 0;
     uint32_t cnt = 0;
-    if (i < P) {
+    if (i < P && (uint32_t)i < *n_emit) {          // order[] holds the emitting Gaussians only
         const uint32_t g = order[i];
         cnt = tiles_touched[g];
         if (cnt > 0) {
@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* _
     }
 }
 
-int gsr_launch_duplicate(int P, const uint32_t* order, const int* radii, const uint32_t* tiles_touched,
+int gsr_launch_duplicate(int P, const uint32_t* n_emit, const uint32_t* order, const int* radii, const uint32_t* tiles_touched,
                          const float4* recs, const uint32_t* block_offsets, uint32_t* tile_ids, uint32_t* vals,
                          int grid_x, int grid_y, GsrSortPlan tile_plan, uint32_t* tile_hist, cudaStream_t stream) {
     if (P <= 0) return 0;
     if (tile_plan.passes > 2) return gsr_set_error_msg(-2, "more than 65536 tiles are not supported");
     { GsrProfScope prof_("duplicate_with_keys", stream);
-    duplicate_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, order, radii, tiles_touched, recs, block_offsets,
+    duplicate_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(P, n_emit, order, radii, tiles_touched, recs, block_offsets,
                                                              tile_ids, vals, grid_x, grid_y, tile_plan, tile_hist); }
     GSR_CHECK_LAUNCH();
     return 0;

@@ -487,6 +487,130 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdAr
     if (SMEM_RED && ne) flush(ne);
 }
 
+// Debug: replay blend_fwd_v2's walk of every 8x8 region and count the loop iterations that a finer-grained cull would
+// leave, for several ways of splitting the warp's 32 lanes into groups that walk separately compacted lists.
+// Configs c (groups x shape in pixels): 0: 1 x 8x8, 1: 2 x 8x4, 2: 4 x 4x4, 3: 4 x 8x2, 4: 2 x 4x8, 5: 8 x 4x2.
+// out[4c+0] = sum over groups of surviving entries; out[4c+1] = sum over batches of the largest group count (groups in
+// lockstep per 32-entry batch); out[4c+2] = sum over regions of the largest group total (ideal queues); out[4c+3] = batches.
+// out[24] = (lane, entry) with a blending pixel, out[25] = (pixel, entry) blended, out[26] = (pixel, entry) evaluated by config 0.
+__global__ void __launch_bounds__(128) blend_group_stats_kernel(BlendFwdArgs a, unsigned long long* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.y * a.grid_x + blockIdx.x;
+    const int X0 = blockIdx.x * GSR_TILE + ((warp & 1) << 3), Y0 = blockIdx.y * GSR_TILE + ((warp >> 1) << 3);
+    if (X0 >= a.W || Y0 >= a.H) return;
+    const int col = lane & 7, prow = lane >> 3;
+    const int px = X0 + col, pyA = Y0 + 2 * prow, pyB = pyA + 1;
+    bool doneA = !(px < a.W && pyA < a.H), doneB = !(px < a.W && pyB < a.H);
+    float TA = 1.0f, TB = 1.0f;
+    constexpr int NC = 6;
+    const int ngroups[NC] = {1, 2, 4, 4, 2, 8};
+    // group of a lane / pixel rectangle of a group, per config
+    auto group_of = [&](int c, int l) -> int {
+        const int cl = l & 7, pr = l >> 3;
+        switch (c) {
+            case 0: return 0;
+            case 1: return pr >> 1;
+            case 2: return (pr >> 1) * 2 + (cl >> 2);
+            case 3: return pr;
+            case 4: return cl >> 2;
+            default: return pr * 2 + (cl >> 2);
+        }
+    };
+    auto group_rect = [&](int c, int g, float& x0, float& y0, float& x1, float& y1) {
+        int gx = 0, gy = 0, w = 8, h = 8;
+        switch (c) {
+            case 0: break;
+            case 1: gy = 4 * g; h = 4; break;
+            case 2: gx = 4 * (g & 1); gy = 4 * (g >> 1); w = 4; h = 4; break;
+            case 3: gy = 2 * g; h = 2; break;
+            case 4: gx = 4 * g; w = 4; break;
+            default: gx = 4 * (g & 1); gy = 2 * (g >> 1); w = 4; h = 2; break;
+        }
+        x0 = (float)(X0 + gx); y0 = (float)(Y0 + gy);
+        x1 = fminf(x0 + (float)(w - 1), (float)(a.W - 1)); y1 = fminf(y0 + (float)(h - 1), (float)(a.H - 1));
+    };
+    unsigned gmask[NC][8];
+    for (int c = 0; c < NC; c++)
+        for (int g = 0; g < ngroups[c]; g++) gmask[c][g] = __ballot_sync(FULL, group_of(c, lane) == g);
+    unsigned long long sum[NC], bmax[NC], tot[NC][8], batches = 0, lane_blend = 0, pix_blend = 0, pix_eval = 0;
+    for (int c = 0; c < NC; c++) { sum[c] = bmax[c] = 0; for (int g = 0; g < 8; g++) tot[c][g] = 0; }
+    const uint2 range = a.ranges[tile];
+    const int todo = (int)(range.y - range.x);
+    for (int base = 0; base < todo; base += 32) {
+        const unsigned done_m = __ballot_sync(FULL, doneA && doneB);
+        if (done_m == FULL) break;
+        batches++;
+        const bool valid = base + lane < todo;
+        float4 c0 = make_float4(0, 0, 0, 0), c1 = c0, c2 = c0;
+        if (valid) {
+            const uint32_t id = a.point_list[range.x + base + lane];
+            const float4* r = a.recs + 3 * (size_t)id;
+            c0 = r[0]; c1 = r[1]; c2 = r[2];
+        }
+        unsigned m0 = 0;
+        for (int c = 0; c < NC; c++) {
+            unsigned long long mx = 0;
+            for (int g = 0; g < ngroups[c]; g++) {
+                float x0, y0, x1, y1;
+                group_rect(c, g, x0, y0, x1, y1);
+                const bool gdone = (done_m & gmask[c][g]) == gmask[c][g];
+                const bool keep = valid && !gdone && rect_may_contribute(c0.x, c0.y, c0.z, c0.w, c1.x, c2.y, x0, y0, x1, y1);
+                const unsigned m = __ballot_sync(FULL, keep);
+                const unsigned long long n = __popc(m);
+                if (c == 0) m0 = m;
+                sum[c] += n; tot[c][g] += n; mx = n > mx ? n : mx;
+            }
+            bmax[c] += mx;
+        }
+        // blend the survivors of the whole-region cull in order, exactly as the forward does
+        for (unsigned m = m0; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const float gx = __shfl_sync(FULL, c0.x, src), gy = __shfl_sync(FULL, c0.y, src);
+            const float cx = __shfl_sync(FULL, c0.z, src), cy = __shfl_sync(FULL, c0.w, src), cz = __shfl_sync(FULL, c1.x, src);
+            const float op = __shfl_sync(FULL, c1.y, src), cut = __shfl_sync(FULL, c2.y, src);
+            const float dx = gx - (float)px;
+            bool blA = false, blB = false;
+            if (!doneA) {
+                pix_eval++;
+                const float power = blend_power_exact(dx, gy - (float)pyA, cx, cy, cz);
+                if (!(power > 0.0f || power < cut)) {
+                    const float alpha = fminf(0.99f, op * expf(power));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float t = TA * (1.0f - alpha);
+                        if (t < 0.0001f) doneA = true; else { TA = t; blA = true; }
+                    }
+                }
+            }
+            if (!doneB) {
+                pix_eval++;
+                const float power = blend_power_exact(dx, gy - (float)pyB, cx, cy, cz);
+                if (!(power > 0.0f || power < cut)) {
+                    const float alpha = fminf(0.99f, op * expf(power));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float t = TB * (1.0f - alpha);
+                        if (t < 0.0001f) doneB = true; else { TB = t; blB = true; }
+                    }
+                }
+            }
+            lane_blend += (blA || blB); pix_blend += (int)blA + (int)blB;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lane_blend += __shfl_xor_sync(FULL, lane_blend, o);
+        pix_blend += __shfl_xor_sync(FULL, pix_blend, o);
+        pix_eval += __shfl_xor_sync(FULL, pix_eval, o);
+    }
+    if (lane == 0) {
+        for (int c = 0; c < NC; c++) {
+            unsigned long long mx = 0;
+            for (int g = 0; g < ngroups[c]; g++) mx = tot[c][g] > mx ? tot[c][g] : mx;
+            atomicAdd(&out[4 * c + 0], sum[c]); atomicAdd(&out[4 * c + 1], bmax[c]); atomicAdd(&out[4 * c + 2], mx);
+            atomicAdd(&out[4 * c + 3], batches);
+        }
+        atomicAdd(&out[24], lane_blend); atomicAdd(&out[25], pix_blend); atomicAdd(&out[26], pix_eval);
+    }
+}
+
 // exhaustive check kernel: exp1_exact / exp2_exact against expf on every float in [lo_bits, hi_bits]
 __global__ void exp_check_kernel(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* mismatches) {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -559,6 +683,13 @@ int gsr_launch_blend_bwd_v2(const BlendBwdArgs& a, cudaStream_t stream) {
         if (sred) blend_bwd_v2_kernel<1, 0, true, false><<<grid, 128, 0, stream>>>(a);
         else blend_bwd_v2_kernel<1, 0, false, false><<<grid, 128, 0, stream>>>(a);
     } }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+
+int gsr_launch_blend_group_stats(const BlendFwdArgs& a, unsigned long long* out32, cudaStream_t stream) {
+    dim3 grid(a.grid_x, a.grid_y, 1);
+    blend_group_stats_kernel<<<grid, 128, 0, stream>>>(a, out32);
     GSR_CHECK_LAUNCH();
     return 0;
 }

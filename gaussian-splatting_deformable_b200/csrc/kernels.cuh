@@ -36,8 +36,7 @@ struct PreprocessArgs {
     float* cov3D_out;            // [P,6] or null (parity dumps)
     uint32_t* block_sums;        // [ceil(P/256)] sum of tiles_touched per 256-Gaussian block
     uint32_t* depth_keys;        // [P] float bits of the view depth (0xffffffff when the Gaussian emits nothing)
-    uint32_t* depth_vals;        // [P] = idx (payload of the depth sort)
-    uint32_t* depth_hist;        // [4][256] digit histograms of depth_keys (pre-zeroed), accumulated here
+    uint32_t* depth_state;       // control words of the depth sort (GsrDepthSortCtrl, pre-zeroed): ~min / max of the emitting keys accumulated here
     uint32_t* total;             // running sum of tiles_touched = num_rendered (pre-zeroed; one atomic per block)
     int prefiltered;             // GaussianRasterizationSettings.prefiltered: a culled point is an error (auxiliary.h:156-160)
     uint32_t* flags;             // bit 0 raised when prefiltered is set and a point fails the near-plane test
@@ -51,11 +50,11 @@ int gsr_launch_mark_visible(int P, const float* means, const GsrView& v, uint8_t
 // Exclusive scan of the per-block sums in place; total -> *d_total.
 int gsr_launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* d_total, cudaStream_t stream);
 // Per-256 sums of tiles_touched taken in DEPTH-SORTED order (order[] from the depth sort).
-int gsr_launch_sorted_block_sums(int P, const uint32_t* order, const uint32_t* tiles_touched, uint32_t* block_sums,
-                                 cudaStream_t stream);
+int gsr_launch_sorted_block_sums(int P, const uint32_t* n_emit /* device: entries of order[] */, const uint32_t* order,
+                                 const uint32_t* tiles_touched, uint32_t* block_sums, cudaStream_t stream);
 // rasterizer_impl.cu:70-111 duplicateWithKeys, walking the Gaussians in depth order and
 // emitting (tile id, Gaussian id) pairs (block-cooperative, balanced).
-int gsr_launch_duplicate(int P, const uint32_t* order, const int* radii, const uint32_t* tiles_touched,
+int gsr_launch_duplicate(int P, const uint32_t* n_emit /* device: entries of order[] */, const uint32_t* order, const int* radii, const uint32_t* tiles_touched,
                          const float4* recs, const uint32_t* block_offsets, uint32_t* tile_ids, uint32_t* vals,
                          int grid_x, int grid_y, GsrSortPlan tile_plan, uint32_t* tile_hist /* pre-zeroed */,
                          cudaStream_t stream);
@@ -65,6 +64,24 @@ int gsr_launch_tile_ranges(uint32_t R, const uint32_t* sorted_tile_ids, uint2* r
 // The reference's 64-bit sorted keys (tile << 32 | depth bits), for parity checks.
 int gsr_launch_materialize_keys(uint32_t R, const uint32_t* sorted_tile_ids, const uint32_t* point_list,
                                 const float* depths, uint64_t* keys64, cudaStream_t stream);
+
+// ---- depth order of the Gaussians: two-level bucket sort (depth_sort.cu) ----
+// state = u32 [GSR_DS_CTRL_WORDS control words | 2^nb bucket counts -> cursors | segment starts]; zeroed by the caller.
+#define GSR_DS_CTRL_WORDS 64
+enum GsrDepthSortCtrl {
+    GSR_DS_NOT_KMIN = 0,        // ~(smallest emitting key), by atomicMax (so that zero = "none yet")
+    GSR_DS_KMAX = 1,            // largest emitting key
+    GSR_DS_N_EMIT = 4,          // number of Gaussians that emit duplicates = length of the depth order
+    GSR_DS_SHIFT = 5, GSR_DS_KMIN = 6,
+    GSR_DS_SLOW_SEGMENTS = 7,   // segments that took the CTA-serial radix path (diagnostic)
+    // words of the forward that live in the same zeroed block
+    GSR_DS_OVERFLOW = 59, GSR_DS_PREFILTERED = 60, GSR_DS_SCAN_TICKET = 61, GSR_DS_NUM_RENDERED = 62, GSR_DS_ERROR = 63
+};
+size_t gsr_depth_sort_state_bytes(uint32_t P);
+// keys[P] (0xffffffff = emits nothing) -> order[0 .. n_emit) = ids by ascending (key, id); srec[i] = (order[i], rects[order[i]]) when given.
+// pairs_a / pairs_b: uint2[P] scratch.  minmax_ready: the control words already hold ~min / max (preprocess_fwd wrote them).
+int gsr_launch_depth_sort(uint32_t P, const uint32_t* keys, uint32_t* state, uint2* pairs_a, uint2* pairs_b, const uint2* rects,
+                          uint32_t* order, uint4* srec, bool minmax_ready, cudaStream_t stream);
 
 // ---- tile binning as one stable counting sort over the depth-ordered Gaussians (tile_sweep.cu) ----
 #define GSR_SWEEP_WARPS 8                 // warps (= tile-row stripes) per CTA
@@ -78,10 +95,10 @@ struct GsrTileBinPlan {
 };
 GsrTileBinPlan gsr_make_tile_bin_plan(int grid_x, int grid_y);
 size_t gsr_tile_matrix_bytes(int grid_x, int grid_y);
-// order[P] = Gaussian ids in depth order; rects[P]; srec[P] scratch; matrix[chunks][tiles] scratch;
+// srec[i] = (id, rect lo, rect hi, 0) of the i-th Gaussian in depth order (written by the depth sort); matrix[chunks][tiles] scratch;
 // totals/tile_base [tiles] scratch.  Writes ranges[tiles] and point_list[R].
 // n_emit (device) = number of Gaussians that emit duplicates (the depth sort puts them first).
-int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
+int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint4* srec,
                             const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
                             uint32_t* tile_base, uint2* ranges, uint32_t* point_list, uint32_t* scan_ticket /* zeroed word */,
                             cudaStream_t stream, uint32_t capacity = 0 /* > 0: point_list holds this many entries; more -> *overflow = 1, empty ranges */,
@@ -127,6 +144,7 @@ int gsr_launch_blend_fwd(const BlendFwdArgs& a, cudaStream_t stream);
 int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream);      // blend_v2.cu
 int gsr_launch_exp_check(float x_max, unsigned long long* out2, cudaStream_t stream);
 int gsr_launch_blend_stats(const BlendFwdArgs& a, unsigned long long* out8, cudaStream_t stream);
+int gsr_launch_blend_group_stats(const BlendFwdArgs& a, unsigned long long* out32, cudaStream_t stream);   // blend_v2.cu
 
 struct BlendBwdArgs {
     const uint2* ranges; const uint32_t* point_list; const float4* recs;

@@ -60,9 +60,6 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
     const int idx = blockIdx.x * 256 + threadIdx.x;
     uint32_t tiles = 0;
     uint32_t dkey = 0xffffffffu;
-    __shared__ uint32_t s_hist[4 * 256];   // digit histograms of this block's depth keys (depth sort, 4 x 8 bits)
-    for (int k = threadIdx.x; k < 4 * 256; k += 256) s_hist[k] = 0;
-    __syncthreads();
     if (idx < a.P) {
         // ---- (1) every unconditional load first: no store may sit between them (a store to a
         // non-restrict pointer pins all later loads behind it and serialises DRAM round trips) ----
@@ -153,37 +150,25 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
         a.rects[idx] = g.ok ? make_uint2(g.rmin.x | (g.rmin.y << 16), g.rmax.x | (g.rmax.y << 16)) : make_uint2(0u, 0u);
         dkey = tiles ? __float_as_uint(depth) : 0xffffffffu;
         a.depth_keys[idx] = dkey;
-        a.depth_vals[idx] = (uint32_t)idx;
     }
-    // Histograms for the depth sort, fused here so the sort never re-reads the keys.
-    // match-any aggregates equal digits (culled Gaussians all carry 0xff bytes).
-    {
-        const bool valid = idx < a.P;
-        const int lane = threadIdx.x & 31;
-#pragma unroll
-        for (int p4 = 0; p4 < 4; p4++) {
-            const uint32_t d = valid ? ((dkey >> (8 * p4)) & 255u) : 0xffffffffu;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p4 * 256 + d], (uint32_t)__popc(peers));
-        }
-    }
-    // Per-block partial sum for the offsets scan (fused: saves re-reading tiles_touched).
-    __shared__ uint32_t wsum[8];
-    uint32_t s = tiles;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    // Per-block: sum of tiles_touched (num_rendered; the radix path's offsets scan) and the range of the emitting
+    // depth keys, which the depth sort (depth_sort.cu) slices into buckets - one atomic each per block.
+    __shared__ uint32_t wsum[8], wmin[8], wmax[8];
+    const uint32_t s = __reduce_add_sync(0xffffffffu, tiles);
+    const uint32_t kmn = __reduce_min_sync(0xffffffffu, dkey);                       // culled: 0xffffffff
+    const uint32_t kmx = __reduce_max_sync(0xffffffffu, tiles ? dkey : 0u);
+    if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = s; wmin[threadIdx.x >> 5] = kmn; wmax[threadIdx.x >> 5] = kmx; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t t = 0;
+        uint32_t t = 0, mn = 0xffffffffu, mx = 0u;
 #pragma unroll
-        for (int k = 0; k < 8; k++) t += wsum[k];
+        for (int k = 0; k < 8; k++) { t += wsum[k]; mn = min(mn, wmin[k]); mx = max(mx, wmax[k]); }
         a.block_sums[blockIdx.x] = t;
-        if (t) atomicAdd(a.total, t);           // num_rendered without a scan launch in front of the host read-back
-    }
-    for (int k = threadIdx.x; k < 4 * 256; k += 256) {
-        const uint32_t c = s_hist[k];
-        if (c) atomicAdd(&a.depth_hist[k], c);
+        if (t) {
+            atomicAdd(a.total, t);              // num_rendered without a scan launch in front of the host read-back
+            atomicMax(a.depth_state + GSR_DS_NOT_KMIN, ~mn);
+            atomicMax(a.depth_state + GSR_DS_KMAX, mx);
+        }
     }
 }
 

@@ -26,18 +26,9 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// srec[i] = (Gaussian id, rect lo, rect hi, 0) of the i-th Gaussian in depth order; one
-// coalesced LDG.128 per lane in the sweeps instead of an id load + dependent gather.
-// *n_emit = number of Gaussians that emit at least one duplicate (they sort first).
-__global__ void __launch_bounds__(256) gather_rects_kernel(const uint32_t* __restrict__ n_emit_p,
-                                                           const uint32_t* __restrict__ order,
-                                                           const uint2* __restrict__ rects, uint4* __restrict__ srec) {
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= *n_emit_p) return;
-    const uint32_t id = order[i];
-    const uint2 rc = rects[id];
-    srec[i] = make_uint4(id, rc.x, rc.y, 0u);
-}
+// srec[i] = (Gaussian id, rect lo, rect hi, 0) of the i-th Gaussian in depth order, written by the depth sort
+// (depth_sort.cu): one coalesced LDG.128 per lane in the sweeps instead of an id load + dependent gather.
+// *n_emit = number of Gaussians that emit at least one duplicate = entries of srec.
 
 // One warp = (chunk of the depth order, stripe of GSR_SWEEP_ROWS tile rows).  Lane l maps to
 // cell (row l / CW, column l % CW) of a Gaussian's clipped rect, CW = 32 / GSR_SWEEP_ROWS columns
@@ -377,7 +368,7 @@ size_t gsr_tile_matrix_bytes(int grid_x, int grid_y) {
     return pl.feasible ? (size_t)pl.chunks * (size_t)pl.num_tiles * sizeof(uint32_t) : 0;
 }
 
-int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order, const uint2* rects, uint4* srec,
+int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint4* srec,
                             const GsrTileBinPlan& pl, int grid_x, int grid_y, uint32_t* matrix, uint32_t* totals,
                             uint32_t* tile_base, uint2* ranges, uint32_t* point_list, uint32_t* scan_ticket, cudaStream_t stream,
                             uint32_t capacity, uint32_t* overflow) {
@@ -392,9 +383,6 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint32_t* order
                                        GSR_SWEEP_WARPS * GSR_SWEEP_MAX_STRIPE_TILES * (int)sizeof(uint32_t)));
         attr_done = true;
     }
-    { GsrProfScope prof_("gather_rects", stream);
-    gather_rects_kernel<<<gsr_div_up(P, 256), 256, 0, stream>>>(n_emit, order, rects, srec); }
-    GSR_CHECK_LAUNCH();
     const dim3 grid(pl.chunks, pl.groups, 1);
     static const int count_v = env_int2("GSR_SWEEP_COUNT_V", 2);
     const size_t cnt_smem = (size_t)pl.num_tiles * sizeof(uint32_t);

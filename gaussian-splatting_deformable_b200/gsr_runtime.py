@@ -98,6 +98,9 @@ _SIGNATURES = {
                                     _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
     "gsr_debug_blend_stats": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P]),
+    "gsr_depth_order_ws_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "gsr_depth_order": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_size_t, _P, _P, _P]),
+    "gsr_debug_blend_group_stats": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P]),
     "gsr_debug_exp_check": (ctypes.c_int, [ctypes.c_float, _P, _P]),
     "gsr_ssim_l1_loss_forward": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_float, _P, _P, _P]),
     "gsr_ssim_l1_loss_backward": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.c_float, _P, _P,

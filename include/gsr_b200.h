@@ -182,6 +182,20 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
 int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t num_rendered, const void* geom_ws,
                           const void* binning_ws, const void* image_ws, unsigned long long* out8, void* stream);
 
+/* The depth sort of the forward on its own (csrc/depth_sort.cu; replaces the depth half of the reference's
+ * cub::DeviceRadixSort::SortPairs, rasterizer_impl.cu:303-308): keys = device u32[P], 0xffffffff marks an entry that is
+ * left out; order[0 .. n) receives the indices of the other entries by ascending (key, index) - the order a stable sort
+ * by key gives.  ws = device scratch of gsr_depth_order_ws_bytes(P); info2 (device u32[2], may be NULL) receives n and the
+ * number of segments that needed the skew path. */
+size_t gsr_depth_order_ws_bytes(int P);
+int gsr_depth_order(const uint32_t* keys, int P, void* ws, size_t ws_bytes, uint32_t* order, uint32_t* info2, void* stream);
+
+/* Debug/measurement aid: replays blend_fwd_v2's walk per 8x8 region and counts the loop iterations that would remain if
+ * the warp's lanes were split into groups (1 x 8x8, 2 x 8x4, 4 x 4x4, 4 x 8x2, 2 x 4x8, 8 x 4x2 pixels) walking separately
+ * culled lists; out32 = device u64[32] (layout in csrc/blend_v2.cu: blend_group_stats_kernel). */
+int gsr_debug_blend_group_stats(const gsr_view* view, int P, uint32_t num_rendered, const void* geom_ws,
+                                const void* binning_ws, const void* image_ws, unsigned long long* out32, void* stream);
+
 /* Debug/parity aid: compares the library's restatements of CUDA's expf (scalar and packed
  * FP32x2, csrc/f32x2.cuh) with expf itself on EVERY float in [-x_max, -0]; writes the two
  * mismatch counts to out2 (device u64[2]).  Both must be 0 for the blend to be bit-exact. */

@@ -172,5 +172,19 @@ def sort_pairs(keys, vals, begin_bit, end_bit):
     return (kb, vb) if in_b.value else (ka, va)
 
 
+def depth_order(keys):
+    """gsr_depth_order: indices of the keys != 0xffffffff by ascending (key, index); returns (order[:n], skew_segments)."""
+    lib = rt.load()
+    n = keys.numel()
+    nbytes = lib.gsr_depth_order_ws_bytes(n)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=keys.device)
+    order = torch.full((max(n, 1),), -1, dtype=torch.int32, device=keys.device)
+    info = torch.zeros(2, dtype=torch.int32, device=keys.device)
+    rt.check(lib.gsr_depth_order(rt.ptr(keys), n, rt.ptr(ws), nbytes, rt.ptr(order), rt.ptr(info), rt.stream_ptr()))
+    torch.cuda.synchronize()
+    cnt, slow = info.tolist()
+    return order[:cnt], slow
+
+
 def load_golden():
     return np.load(os.path.join(GOLD, "raster_golden.npz"))

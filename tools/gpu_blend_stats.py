@@ -30,6 +30,17 @@ def main():
     names = ["staged_entries", "cull_survivors", "warp_iterations", "warp_iter_any_power", "warp_iter_any_blend", "pixel_pairs_evaluated", "pixel_pairs_blended", "list_entries_total"]
     d = dict(zip(names, out.tolist())); d.update(P=P, W=W, H=H, R=R, visible=int((radii > 0).sum()))
     print(json.dumps(d))
+    out = torch.zeros(32, dtype=torch.int64, device=dev)
+    rt.check(lib.gsr_debug_blend_group_stats(view, P, R, rt.ptr(geom), rt.ptr(binning), rt.ptr(img), rt.ptr(out), st))
+    torch.cuda.synchronize()
+    o = out.tolist()
+    cfg = ["1x(8x8)", "2x(8x4)", "4x(4x4)", "4x(8x2)", "2x(4x8)", "8x(4x2)"]
+    base = o[0]
+    for c, nm in enumerate(cfg):
+        print("%-8s sum_of_groups %11d  lockstep/batch %11d (%.3f of now)  ideal queues %11d (%.3f)  batches %d" % (
+            nm, o[4 * c], o[4 * c + 1], o[4 * c + 1] / base, o[4 * c + 2], o[4 * c + 2] / base, o[4 * c + 3]))
+    print("lane-iterations with a blending pixel %d (%.3f of 32 x iterations), pixels blended %d, evaluated %d" % (
+        o[24], o[24] / (32.0 * base), o[25], o[26]))
 
 if __name__ == "__main__":
     main()
