@@ -162,19 +162,26 @@ def step_ours(leaves, cams, bg, grad, args):
     issue-bound blend kernels (view_parallel.render_views)."""
     import synthetic
     import view_parallel
-    from diff_gaussian_rasterization import GaussianRasterizer
+    from diff_gaussian_rasterization import GaussianRasterizer, GaussianBackwardBatch
     buf = flat_buffer(leaves)
     buf.zero_()
     sinks = {"means3D": leaves["means3D"].grad, "opacities": leaves["opacities"].grad, "shs": leaves["shs"].grad,
              "scales": leaves["scales"].grad, "rotations": leaves["rotations"].grad,
              "se3_S": leaves["S"].grad, "se3_theta": leaves["theta"].grad}
+    no_deform = getattr(args, "no_deform", False)
+    if no_deform:
+        sinks = {k: v for k, v in sinks.items() if not k.startswith("se3_")}
+    # the per-Gaussian half of the backward runs once for all views of the step (--batched-backward 0: once per view)
+    batch = GaussianBackwardBatch(sinks) if getattr(args, "batched_backward", 1) else None
+    if batch is not None:
+        sinks = batch
 
     def render_view(i):
         rs = synthetic.raster_settings(cams[i], bg, sh_degree=3)
         ras = GaussianRasterizer(rs)
         means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-        if getattr(args, "no_deform", False):
-            snk = {k: v for k, v in sinks.items() if not k.startswith("se3_")}
+        if no_deform:
+            snk = sinks
             color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
                                shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"], accumulate_grads=snk)
         else:
@@ -187,7 +194,7 @@ def step_ours(leaves, cams, bg, grad, args):
         color.backward(grad)
         return loss
 
-    return view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams)
+    return view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams, batch=batch)
 
 
 def _ref_deform(leaves, args):
@@ -330,6 +337,10 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
         sinks = {"means3D": leaves["means3D"].grad, "opacities": leaves["opacities"].grad, "shs": leaves["shs"].grad,
                  "scales": leaves["scales"].grad, "rotations": leaves["rotations"].grad,
                  "se3_S": leaves["S"].grad, "se3_theta": leaves["theta"].grad}
+        batch = None
+        if getattr(args, "batched_backward", 1):
+            from diff_gaussian_rasterization import GaussianBackwardBatch
+            batch = sinks = GaussianBackwardBatch(sinks)
 
         def render_view(i):
             ras = GaussianRasterizer(synthetic.raster_settings(cams[i], bg, sh_degree=3))
@@ -341,7 +352,7 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
             loss.backward()
             return loss.detach()
 
-        total = view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams)
+        total = view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams, batch=batch)
         opt.all_reduce_and_step(chunks=8)          # N > 1: all-reduce in 8 pieces, Adam on each piece as it arrives
         return total
     from oracle import loss_port, ref_driver, rigid_body_port
@@ -482,6 +493,9 @@ def main():
     ap.add_argument("--W", type=int, default=None)
     ap.add_argument("--H", type=int, default=None)
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are spread over (ours)")
+    ap.add_argument("--batched-backward", type=int, default=1, dest="batched_backward",
+                    help="ours: 1 = the per-Gaussian half of the backward runs once per step for all views "
+                         "(GaussianBackwardBatch), 0 = once per view")
     ap.add_argument("--train", action="store_true",
                     help="also time the whole C5-style training step: per-view loss 0.8 L1 + 0.2 (1 - SSIM) against a fixed "
                          "target, gradient all-reduce, Adam step (ours: fused kernels; reference: its torch ops)")
@@ -726,6 +740,9 @@ def main():
         alg = {  # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x units per launch; R = last view's)
             "preprocess_fwd": (288.0 + twist_bytes) * args.P,
             "preprocess_bwd": (516.0 + 2 * twist_bytes) * args.P,
+            # view-batched form (GaussianBackwardBatch): parameters read and gradients read-modify-written ONCE per step,
+            # per view only the radius, the 48-byte moment record, conic + opacity, clamp bits and the view-space gradient
+            "preprocess_bwd_batched": (252.0 + twist_bytes + 2 * (236.0 + twist_bytes)) * args.P + len(cams) * (4.0 + 48.0 + 24.0 + 1.0 + 12.0) * args.P,
             # radix fallback path (GSR_BINNING_RADIX=1)
             "duplicate_with_keys": 8.0 * R + 28.0 * args.P,
             "tile_sort_onesweep_pass": 16.0 * R,

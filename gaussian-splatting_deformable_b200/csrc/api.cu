@@ -518,6 +518,113 @@ int gsr_debug_blend_group_stats(const gsr_view* view, int P, uint32_t R, const v
     return gsr_launch_blend_group_stats(b, out32, stream);
 }
 
+// renderCUDA backward of one view: zeroes the per-Gaussian gradient records and lets blend_bwd reduce into them.
+static int backward_blend_impl(const gsr_view* view, const GsrView& v, int P, uint32_t R, const void* geom_ws, const void* binning_ws,
+                               const void* image_ws, float4* grad_recs, const float* dL_dout_color, cudaStream_t stream) {
+    const GeomLayout L = geom_layout(P);
+    const ImageLayout IL = image_layout(v.W, v.H);
+    const char* gw = reinterpret_cast<const char*>(geom_ws);
+    const char* iw = reinterpret_cast<const char*>(image_ws);
+    GSR_CHECK(cudaMemsetAsync(grad_recs, 0, 48 * (size_t)P, stream));
+    if (R > 0) {
+        if (!binning_ws) return gsr_set_error_msg(-1, "backward: binning workspace is NULL");
+        const BinLayout BL = bin_layout(R, v.W, v.H);
+        const char* bw = reinterpret_cast<const char*>(binning_ws);
+        const bool in_b = !BL.sweep && (BL.passes & 1) != 0;
+        BlendBwdArgs b{};
+        b.ranges = reinterpret_cast<const uint2*>(iw + IL.ranges);
+        b.point_list = reinterpret_cast<const uint32_t*>(bw + (in_b ? BL.vals_b : BL.vals_a));
+        b.recs = reinterpret_cast<const float4*>(gw + L.recs);
+        b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
+        b.bg[0] = view->bg[0]; b.bg[1] = view->bg[1]; b.bg[2] = view->bg[2];
+        b.final_T = reinterpret_cast<const float*>(iw + IL.final_T);
+        b.n_contrib = reinterpret_cast<const uint32_t*>(iw + IL.n_contrib);
+        b.dL_dpix = dL_dout_color;
+        b.grad_recs = grad_recs;
+        if (gsr_blend_region_masks_enabled()) b.region_masks = reinterpret_cast<const uint32_t*>(bw + BL.masks);
+        if (int rc = gsr_launch_blend_bwd(b, stream)) return rc;
+    }
+    return 0;
+}
+
+// ---- view-batched backward: gsr_backward_blend per view, then ONE gsr_backward_gaussians_batched over the Gaussians ----
+int gsr_backward_blend(const gsr_view* view, int P, uint32_t R, const void* geom_ws, const void* binning_ws, const void* image_ws,
+                       void* grad_ws, const float* dL_dout_color, void* stream_) {
+    if (P <= 0) return 0;
+    GsrView v;
+    if (int rc = fill_view(view, 0, v)) return rc;
+    if (!geom_ws || !image_ws || !grad_ws || !dL_dout_color) return gsr_set_error_msg(-1, "backward_blend: required pointer is NULL");
+    return backward_blend_impl(view, v, P, R, geom_ws, binning_ws, image_ws, reinterpret_cast<float4*>(grad_ws), dL_dout_color,
+                               (cudaStream_t)stream_);
+}
+
+size_t gsr_backward_batched_slots_bytes(int n_views) { return sizeof(BwdViewSlot) * (size_t)(n_views > 0 ? n_views : 0); }
+
+// Pure host function: slots_host[j] = what the batched kernel needs of view j (camera constants + pointers into its workspaces).
+int gsr_backward_batched_fill_slots(int n_views, const gsr_view_grads* views, int P, int M, void* slots_host, size_t slots_bytes) {
+    if (n_views <= 0 || !views || !slots_host) return gsr_set_error_msg(-1, "batched backward: no views");
+    if (slots_bytes < gsr_backward_batched_slots_bytes(n_views)) return gsr_set_error_msg(-3, "batched backward: slot buffer too small");
+    const GeomLayout L = geom_layout(P);
+    BwdViewSlot* out = reinterpret_cast<BwdViewSlot*>(slots_host);
+    for (int j = 0; j < n_views; j++) {
+        const gsr_view_grads& g = views[j];
+        if (!g.view || !g.radii || !g.geom_ws || !g.grad_ws || !g.dL_dmeans2D) return gsr_set_error_msg(-1, "batched backward: NULL pointer in a view");
+        BwdViewSlot sl{};
+        if (int rc = fill_view(g.view, M, sl.v)) return rc;
+        if (sl.v.scale_modifier != views[0].view->scale_modifier)
+            return gsr_set_error_msg(-1, "batched backward: the views of a batch must share scale_modifier");
+        const char* gw = reinterpret_cast<const char*>(g.geom_ws);
+        sl.radii = g.radii;
+        sl.clamped = reinterpret_cast<const uint8_t*>(gw + L.clamped);
+        sl.grad_recs = reinterpret_cast<const float4*>(g.grad_ws);
+        sl.recs = reinterpret_cast<const float4*>(gw + L.recs);
+        sl.dL_dmeans2D = g.dL_dmeans2D;
+        out[j] = sl;
+    }
+    return 0;
+}
+
+int gsr_backward_gaussians_batched(int n_views, const void* slots_device, float scale_modifier, int P, int M, const float* means3D,
+                                   const float* means_deformed, const float* scales, const float* rotations, const float* shs,
+                                   const gsr_deform* deform, float* dL_dmeans3D, float* dL_dopacity, float* dL_dsh, float* dL_dscales,
+                                   float* dL_drots, float* dL_dtwist_S, float* dL_dtwist_theta, int accumulate_mask, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P <= 0 || n_views <= 0) return 0;
+    if (!slots_device || !means3D || !scales || !rotations || !shs || !dL_dmeans3D || !dL_dopacity || !dL_dsh || !dL_dscales || !dL_drots)
+        return gsr_set_error_msg(-1, "batched backward: required pointer is NULL");
+    if (M != 16 || ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dsh)) & 31))
+        return gsr_set_error_msg(-1, "batched backward: needs M = 16 SH coefficients and 32-byte aligned shs / dL_dsh");
+    const int all_acc = GSR_ACC_MEANS3D | GSR_ACC_OPACITY | GSR_ACC_SH | GSR_ACC_SCALES | GSR_ACC_ROTS;
+    if (n_views > GSR_BATCH_MAX_VIEWS && (accumulate_mask & all_acc) != all_acc)
+        return gsr_set_error_msg(-1, "batched backward: more than 8 views need every output accumulated");
+    PreprocessBwdBatchArgs a{};
+    a.P = P; a.means = means3D;
+    a.deform_mode = deform ? deform->mode : GSR_DEFORM_NONE;
+    a.means_deformed = (a.deform_mode != GSR_DEFORM_NONE) ? means_deformed : nullptr;
+    if (a.deform_mode != GSR_DEFORM_NONE) {
+        if (!means_deformed || !deform->S || !deform->theta) return gsr_set_error_msg(-1, "batched backward: deform inputs missing");
+        a.twist_S = deform->S; a.twist_theta = deform->theta; a.body_id = deform->body_id; a.num_bodies = deform->num_bodies;
+        if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && (!deform->body_id || deform->num_bodies <= 0))
+            return gsr_set_error_msg(-1, "batched backward: body_id / num_bodies required");
+        if ((dL_dtwist_S == nullptr) != (dL_dtwist_theta == nullptr))
+            return gsr_set_error_msg(-1, "batched backward: give both twist gradients or neither");
+        if (n_views > GSR_BATCH_MAX_VIEWS && dL_dtwist_S && a.deform_mode == GSR_DEFORM_PER_GAUSSIAN && !(accumulate_mask & GSR_ACC_TWIST))
+            return gsr_set_error_msg(-1, "batched backward: more than 8 views need every output accumulated");
+    }
+    a.scales = scales; a.rotations = rotations; a.shs = shs;
+    a.scale_modifier = scale_modifier;
+    a.grad_moments = gsr_blend_bwd_writes_moments();
+    a.dL_dmeans3D = dL_dmeans3D; a.dL_dopacity = dL_dopacity; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drots = dL_drots;
+    a.dL_dtwist_S = dL_dtwist_S; a.dL_dtwist_theta = dL_dtwist_theta;
+    a.acc = accumulate_mask;
+    const BwdViewSlot* slots = reinterpret_cast<const BwdViewSlot*>(slots_device);
+    for (int j0 = 0; j0 < n_views; j0 += GSR_BATCH_MAX_VIEWS) {
+        a.n_views = n_views - j0 < GSR_BATCH_MAX_VIEWS ? n_views - j0 : GSR_BATCH_MAX_VIEWS;
+        if (int rc = gsr_launch_preprocess_bwd_batched(a, slots + j0, stream)) return rc;
+    }
+    return 0;
+}
+
 int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* means3D, const float* means_deformed,
                  const float* scales, const float* rotations, const float* shs, const float* cov3D_precomp,
                  const float* colors_precomp, const gsr_deform* deform, const int32_t* radii, const void* geom_ws,
@@ -540,25 +647,7 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
     const char* gw = reinterpret_cast<const char*>(geom_ws);
     const char* iw = reinterpret_cast<const char*>(image_ws);
     float4* grad_recs = reinterpret_cast<float4*>(grad_ws);
-    GSR_CHECK(cudaMemsetAsync(grad_recs, 0, 48 * (size_t)P, stream));
-    if (R > 0) {
-        if (!binning_ws) return gsr_set_error_msg(-1, "backward: binning workspace is NULL");
-        const BinLayout BL = bin_layout(R, v.W, v.H);
-        const char* bw = reinterpret_cast<const char*>(binning_ws);
-        const bool in_b = !BL.sweep && (BL.passes & 1) != 0;
-        BlendBwdArgs b{};
-        b.ranges = reinterpret_cast<const uint2*>(iw + IL.ranges);
-        b.point_list = reinterpret_cast<const uint32_t*>(bw + (in_b ? BL.vals_b : BL.vals_a));
-        b.recs = reinterpret_cast<const float4*>(gw + L.recs);
-        b.W = v.W; b.H = v.H; b.grid_x = v.grid_x; b.grid_y = v.grid_y;
-        b.bg[0] = view->bg[0]; b.bg[1] = view->bg[1]; b.bg[2] = view->bg[2];
-        b.final_T = reinterpret_cast<const float*>(iw + IL.final_T);
-        b.n_contrib = reinterpret_cast<const uint32_t*>(iw + IL.n_contrib);
-        b.dL_dpix = dL_dout_color;
-        b.grad_recs = grad_recs;
-        if (gsr_blend_region_masks_enabled()) b.region_masks = reinterpret_cast<const uint32_t*>(bw + BL.masks);
-        if (int rc = gsr_launch_blend_bwd(b, stream)) return rc;
-    }
+    if (int rc = backward_blend_impl(view, v, P, R, geom_ws, binning_ws, image_ws, grad_recs, dL_dout_color, stream)) return rc;
     PreprocessBwdArgs a{};
     a.P = P; a.means = means3D;
     a.deform_mode = deform ? deform->mode : GSR_DEFORM_NONE;

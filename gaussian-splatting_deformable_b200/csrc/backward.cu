@@ -436,6 +436,380 @@ __global__ void __launch_bounds__(256, MINB) preprocess_bwd_kernel(PreprocessBwd
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// View-batched per-Gaussian backward.  A training step renders several views of the SAME parameters and sums their
+// gradients; run per view, the chain rule above re-reads every parameter record (330 B) and read-modify-writes the 264-byte
+// running gradient for each view.  Here one thread takes a Gaussian through ALL views of the batch: the parameters are
+// read once, only the view's 84 bytes (moment record, conic + opacity, clamp bits, radius) per view, and the gradient is
+// updated once.  What makes the sum cheap: for fixed scale / rotation / twist the cov3D and SE3 backward are LINEAR in
+// dL/dSigma and dL/d(deformed mean), so those are summed over the views and pushed through cov3D / SE3 once.
+// Same formulas as preprocess_bwd_kernel; supported configuration: scales + rotations, SH colours (M = 16, 32-byte
+// aligned), any deform mode.  dL_dmeans2D is written per view (zeros where the view culled the Gaussian).
+// ---------------------------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) preprocess_bwd_batched_kernel(PreprocessBwdBatchArgs a, const BwdViewSlot* __restrict__ g_slots) {
+    extern __shared__ float s_body[];
+    // the views' camera constants and workspace pointers: shared memory (broadcast reads, no pointer chase through global)
+    __shared__ __align__(16) BwdViewSlot slots[GSR_BATCH_MAX_VIEWS];
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    const bool body_smem = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) && a.dL_dtwist_S && (a.num_bodies * 7 * 4 <= 32768);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g_slots);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(slots);
+        const int words = a.n_views * (int)(sizeof(BwdViewSlot) / 4);
+        for (int k = threadIdx.x; k < words; k += 128) dst[k] = __ldg(src + k);
+    }
+    if (body_smem)
+        for (int k = threadIdx.x; k < a.num_bodies * 7; k += 128) s_body[k] = 0.0f;
+    __syncthreads();
+    const int acc = a.acc;
+    unsigned vis = 0;
+    if (idx < a.P) {
+        for (int j = 0; j < a.n_views; j++) vis |= (__ldg(slots[j].radii + idx) > 0 ? 1u : 0u) << j;
+        for (int j = 0; j < a.n_views; j++) {
+            if (!((vis >> j) & 1u)) {
+                float* m2 = slots[j].dL_dmeans2D + 3 * (size_t)idx;
+                m2[0] = 0.0f; m2[1] = 0.0f; m2[2] = 0.0f;
+            }
+        }
+    }
+    if (idx < a.P && vis == 0u) {
+        // culled by every view: zeros to the outputs that are not running sums
+        if (!(acc & GSR_ACC_OPACITY)) a.dL_dopacity[idx] = 0.0f;
+        if (!(acc & GSR_ACC_SH)) {
+            const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 6; k++) st256(a.dL_dsh + 48 * (size_t)idx + 8 * k, z8);
+        }
+        if (!(acc & GSR_ACC_SCALES)) { a.dL_dscales[3 * idx] = 0.0f; a.dL_dscales[3 * idx + 1] = 0.0f; a.dL_dscales[3 * idx + 2] = 0.0f; }
+        if (!(acc & GSR_ACC_ROTS)) st_rec4(a.dL_drots, idx, make_float4(0.f, 0.f, 0.f, 0.f), false);
+        if (a.dL_dtwist_S && a.deform_mode == GSR_DEFORM_PER_GAUSSIAN && !(acc & GSR_ACC_TWIST)) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) a.dL_dtwist_S[6 * (size_t)idx + k] = 0.0f;
+            a.dL_dtwist_theta[idx] = 0.0f;
+        }
+        if (!(acc & GSR_ACC_MEANS3D)) { a.dL_dmeans3D[3 * idx] = 0.0f; a.dL_dmeans3D[3 * idx + 1] = 0.0f; a.dL_dmeans3D[3 * idx + 2] = 0.0f; }
+    }
+    if (vis != 0u) {
+        // ---- the Gaussian's own records, once ----
+        const float* mp = (a.means_deformed ? a.means_deformed : a.means) + 3 * (size_t)idx;
+        const float3 mean = make_float3(mp[0], mp[1], mp[2]);
+        const float3 s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+        const float4 q = ld_rec4(a.rotations, idx);
+        float shv[48];
+        {
+            const float* shp = a.shs + 48 * (size_t)idx;
+#pragma unroll
+            for (int k = 0; k < 6; k++) ld256_nc(shp + 8 * k, shv + 8 * k);
+        }
+        const int tix = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) ? a.body_id[idx] : idx;
+        float3 w = make_float3(0, 0, 0), tv = w, x0 = w;
+        float th = 0.0f;
+        if (a.deform_mode != GSR_DEFORM_NONE) {
+            const float* S = a.twist_S + 6 * (size_t)tix;
+            w = make_float3(S[0], S[1], S[2]); tv = make_float3(S[3], S[4], S[5]);
+            th = a.twist_theta[tix];
+            x0 = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
+        }
+        float cov6[6];
+        cov3d_exact(s, a.scale_modifier, q, cov6);
+        const float V00 = cov6[0], V01 = cov6[1], V02 = cov6[2], V11 = cov6[3], V12 = cov6[4], V22 = cov6[5];
+
+        // ---- sums over the views ----
+        float gm[3] = {0, 0, 0};                 // dL/d(deformed mean)
+        float dcov[6] = {0, 0, 0, 0, 0, 0};      // dL/dSigma
+        float dsh[48];
+#pragma unroll
+        for (int k = 0; k < 48; k++) dsh[k] = 0.0f;
+        float dop = 0.0f;
+        // the view's records (84 B) are requested one view ahead of the math that consumes them
+        float4 n_g0, n_g1, n_sp0 = make_float4(0, 0, 0, 0);
+        float2 n_sp1 = make_float2(0, 0);
+        float n_g2x;
+        uint8_t n_cl;
+        auto fetch = [&](int j) {
+            const BwdViewSlot* sl = slots + j;
+            const float4* gr = sl->grad_recs + 3 * (size_t)idx;
+            n_g0 = gr[0]; n_g1 = gr[1];
+            n_g2x = reinterpret_cast<const float*>(gr + 2)[0];
+            n_cl = sl->clamped[idx];
+            if (a.grad_moments) {
+                const float4* sp = sl->recs + 3 * (size_t)idx;
+                n_sp0 = sp[0];
+                n_sp1 = *reinterpret_cast<const float2*>(sp + 1);
+            }
+        };
+        fetch(__ffs(vis) - 1);
+        for (unsigned rest = vis; rest; rest &= rest - 1) {
+            const int j = __ffs(rest) - 1;
+            const BwdViewSlot* sl = slots + j;
+            const GsrView& v = sl->v;
+            float4 g0 = n_g0, g1 = n_g1;
+            const float g2x = n_g2x;
+            const uint8_t cl = n_cl;
+            const float4 sp0 = n_sp0;
+            const float2 sp1 = n_sp1;
+            if (rest & (rest - 1)) fetch(__ffs(rest & (rest - 1)) - 1);
+            if (a.grad_moments) {
+                const float M0 = g0.x, Mx = g0.y, My = g0.z, Mxx = g0.w, Mxy = g1.x, Myy = g1.y;
+                const float cx = sp0.z, cy = sp0.w, cz = sp1.x, op = sp1.y;
+                const float hop = -0.5f * op;
+                g0.x = -op * (0.5f * v.W) * (cx * Mx + cy * My);
+                g0.y = -op * (0.5f * v.H) * (cz * My + cy * Mx);
+                g0.z = hop * Mxx; g0.w = hop * Mxy; g1.x = hop * Myy;
+                g1.y = M0;
+            }
+            {
+                float* m2 = sl->dL_dmeans2D + 3 * (size_t)idx;
+                m2[0] = g0.x; m2[1] = g0.y; m2[2] = 0.0f;
+            }
+            dop += g1.y;
+            // ---- computeCov2DCUDA (backward.cu:144-274) ----
+            // (gradients carry a 1e-4 tolerance: reciprocals by MUFU.RCP + multiply here, where the per-view kernel and the
+            // forward keep IEEE divisions for bit-exact geometry - this loop is issue-bound, ~1000 instructions per pair)
+            float3 t = make_float3(xform_row(v.view, 0, mean), xform_row(v.view, 1, mean), xform_row(v.view, 2, mean));
+            const float limx = 1.3f * v.tan_fovx, limy = 1.3f * v.tan_fovy;
+            const float tz = __frcp_rn(t.z);
+            const float txtz = t.x * tz, tytz = t.y * tz;
+            const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
+            const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
+            t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+            t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+            const float tz2 = tz * tz, tz3 = tz2 * tz;
+            EwaT e;
+            {
+                const float J00 = v.focal_x * tz, J02 = -v.focal_x * t.x * tz2, J11 = v.focal_y * tz, J12 = -v.focal_y * t.y * tz2;
+                const float* V = v.view;
+                e.T00 = V[2] * J02 + V[0] * J00; e.T01 = V[6] * J02 + V[4] * J00; e.T02 = V[10] * J02 + V[8] * J00;
+                e.T10 = V[2] * J12 + J11 * V[1]; e.T11 = V[6] * J12 + J11 * V[5]; e.T12 = V[10] * J12 + J11 * V[9];
+            }
+            const float3 cov = cov2d_exact(e, cov6);
+            const float ca = cov.x, cb = cov.y, cc = cov.z;
+            const float denom = ca * cc - cb * cb;
+            const float denom2inv = __frcp_rn((denom * denom) + 0.0000001f);
+            const float dcx = g0.z, dcy = g0.w, dcz = g1.x;
+            float dL_da = 0, dL_db = 0, dL_dc = 0;
+            const float T00 = e.T00, T01 = e.T01, T02 = e.T02, T10 = e.T10, T11 = e.T11, T12 = e.T12;
+            if (denom2inv != 0) {
+                dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
+                dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
+                dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
+                dcov[0] += (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
+                dcov[3] += (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
+                dcov[5] += (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
+                dcov[1] += 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
+                dcov[2] += 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
+                dcov[4] += 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
+            }
+            const float dL_dT00 = 2 * (T00 * V00 + T01 * V01 + T02 * V02) * dL_da + (T10 * V00 + T11 * V01 + T12 * V02) * dL_db;
+            const float dL_dT01 = 2 * (T00 * V01 + T01 * V11 + T02 * V12) * dL_da + (T10 * V01 + T11 * V11 + T12 * V12) * dL_db;
+            const float dL_dT02 = 2 * (T00 * V02 + T01 * V12 + T02 * V22) * dL_da + (T10 * V02 + T11 * V12 + T12 * V22) * dL_db;
+            const float dL_dT10 = 2 * (T10 * V00 + T11 * V01 + T12 * V02) * dL_dc + (T00 * V00 + T01 * V01 + T02 * V02) * dL_db;
+            const float dL_dT11 = 2 * (T10 * V01 + T11 * V11 + T12 * V12) * dL_dc + (T00 * V01 + T01 * V11 + T02 * V12) * dL_db;
+            const float dL_dT12 = 2 * (T10 * V02 + T11 * V12 + T12 * V22) * dL_dc + (T00 * V02 + T01 * V12 + T02 * V22) * dL_db;
+            const float* Vm = v.view;
+            const float dL_dJ00 = Vm[0] * dL_dT00 + Vm[4] * dL_dT01 + Vm[8] * dL_dT02;
+            const float dL_dJ02 = Vm[2] * dL_dT00 + Vm[6] * dL_dT01 + Vm[10] * dL_dT02;
+            const float dL_dJ11 = Vm[1] * dL_dT10 + Vm[5] * dL_dT11 + Vm[9] * dL_dT12;
+            const float dL_dJ12 = Vm[2] * dL_dT10 + Vm[6] * dL_dT11 + Vm[10] * dL_dT12;
+            const float h_x = v.focal_x, h_y = v.focal_y;
+            const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+            const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+            const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
+                                 (2 * h_y * t.y) * tz3 * dL_dJ12;
+            float gv[3];
+            gv[0] = Vm[0] * dL_dtx + Vm[1] * dL_dty + Vm[2] * dL_dtz;
+            gv[1] = Vm[4] * dL_dtx + Vm[5] * dL_dty + Vm[6] * dL_dtz;
+            gv[2] = Vm[8] * dL_dtx + Vm[9] * dL_dty + Vm[10] * dL_dtz;
+            // ---- projection part (backward.cu:370-387) ----
+            const float* proj = v.proj;
+            const float m_hom_w = proj[3] * mean.x + proj[7] * mean.y + proj[11] * mean.z + proj[15];
+            const float m_w = __frcp_rn(m_hom_w + 0.0000001f);
+            const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+            const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+            gv[0] += (proj[0] * m_w - proj[3] * mul1) * g0.x + (proj[1] * m_w - proj[3] * mul2) * g0.y;
+            gv[1] += (proj[4] * m_w - proj[7] * mul1) * g0.x + (proj[5] * m_w - proj[7] * mul2) * g0.y;
+            gv[2] += (proj[8] * m_w - proj[11] * mul1) * g0.x + (proj[9] * m_w - proj[11] * mul2) * g0.y;
+            // ---- SH backward (backward.cu:20-139) ----
+            {
+                const int deg = v.sh_degree;
+                const V3 dRGB = {(cl & 1) ? 0.0f : g1.z, (cl & 2) ? 0.0f : g1.w, (cl & 4) ? 0.0f : g2x};
+                // dL/ddir = sum_k (d coef_k / d dir) (sh_k . dRGB): the dot products first (one scalar per coefficient)
+                float pk[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) pk[k] = shv[3 * k] * dRGB.x + shv[3 * k + 1] * dRGB.y + shv[3 * k + 2] * dRGB.z;
+                const V3 dir_orig = {mean.x - v.campos[0], mean.y - v.campos[1], mean.z - v.campos[2]};
+                const float sum2 = dot(dir_orig, dir_orig);
+                const float rlen = rsqrtf(sum2);
+                const float x = dir_orig.x * rlen, y = dir_orig.y * rlen, z = dir_orig.z * rlen;
+                float ddx = 0.0f, ddy = 0.0f, ddz = 0.0f;
+                float coef[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) coef[k] = 0.0f;
+                coef[0] = bSH_C0;
+                if (deg > 0) {
+                    coef[1] = -bSH_C1 * y; coef[2] = bSH_C1 * z; coef[3] = -bSH_C1 * x;
+                    ddx = -bSH_C1 * pk[3]; ddy = -bSH_C1 * pk[1]; ddz = bSH_C1 * pk[2];
+                    if (deg > 1) {
+                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                        coef[4] = bSH_C2[0] * xy; coef[5] = bSH_C2[1] * yz; coef[6] = bSH_C2[2] * (2.f * zz - xx - yy);
+                        coef[7] = bSH_C2[3] * xz; coef[8] = bSH_C2[4] * (xx - yy);
+                        ddx += (bSH_C2[0] * y) * pk[4] + (bSH_C2[2] * 2.f * -x) * pk[6] + (bSH_C2[3] * z) * pk[7] + (bSH_C2[4] * 2.f * x) * pk[8];
+                        ddy += (bSH_C2[0] * x) * pk[4] + (bSH_C2[1] * z) * pk[5] + (bSH_C2[2] * 2.f * -y) * pk[6] + (bSH_C2[4] * 2.f * -y) * pk[8];
+                        ddz += (bSH_C2[1] * y) * pk[5] + (bSH_C2[2] * 2.f * 2.f * z) * pk[6] + (bSH_C2[3] * x) * pk[7];
+                        if (deg > 2) {
+                            coef[9] = bSH_C3[0] * y * (3.f * xx - yy); coef[10] = bSH_C3[1] * xy * z;
+                            coef[11] = bSH_C3[2] * y * (4.f * zz - xx - yy);
+                            coef[12] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                            coef[13] = bSH_C3[4] * x * (4.f * zz - xx - yy); coef[14] = bSH_C3[5] * z * (xx - yy);
+                            coef[15] = bSH_C3[6] * x * (xx - 3.f * yy);
+                            ddx += (bSH_C3[0] * 3.f * 2.f * xy) * pk[9] + (bSH_C3[1] * yz) * pk[10] + (bSH_C3[2] * -2.f * xy) * pk[11] +
+                                   (bSH_C3[3] * -3.f * 2.f * xz) * pk[12] + (bSH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * pk[13] +
+                                   (bSH_C3[5] * 2.f * xz) * pk[14] + (bSH_C3[6] * 3.f * (xx - yy)) * pk[15];
+                            ddy += (bSH_C3[0] * 3.f * (xx - yy)) * pk[9] + (bSH_C3[1] * xz) * pk[10] +
+                                   (bSH_C3[2] * (-3.f * yy + 4.f * zz - xx)) * pk[11] + (bSH_C3[3] * -3.f * 2.f * yz) * pk[12] +
+                                   (bSH_C3[4] * -2.f * xy) * pk[13] + (bSH_C3[5] * -2.f * yz) * pk[14] + (bSH_C3[6] * -3.f * 2.f * xy) * pk[15];
+                            ddz += (bSH_C3[1] * xy) * pk[10] + (bSH_C3[2] * 4.f * 2.f * yz) * pk[11] +
+                                   (bSH_C3[3] * 3.f * (2.f * zz - xx - yy)) * pk[12] + (bSH_C3[4] * 4.f * 2.f * xz) * pk[13] +
+                                   (bSH_C3[5] * (xx - yy)) * pk[14];
+                        }
+                    }
+                }
+                // dnormvdv (auxiliary.h:107-117) with 1 / |dir|^3 from the reciprocal square root
+                {
+                    const float inv32 = rlen * rlen * rlen;
+                    const V3 d = dir_orig;
+                    gv[0] += ((sum2 - d.x * d.x) * ddx - d.y * d.x * ddy - d.z * d.x * ddz) * inv32;
+                    gv[1] += (-d.x * d.y * ddx + (sum2 - d.y * d.y) * ddy - d.z * d.y * ddz) * inv32;
+                    gv[2] += (-d.x * d.z * ddx - d.y * d.z * ddy + (sum2 - d.z * d.z) * ddz) * inv32;
+                }
+                const float dr[3] = {dRGB.x, dRGB.y, dRGB.z};
+#pragma unroll
+                for (int k = 0; k < 48; k++) dsh[k] = fmaf(coef[k / 3], dr[k % 3], dsh[k]);
+            }
+            gm[0] += gv[0]; gm[1] += gv[1]; gm[2] += gv[2];
+        }
+
+        // ---- cov3D backward (backward.cu:278-341), once, on the summed dL/dSigma ----
+        float dscale[3], drot[4];
+        {
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            const float R[3][3] = {
+                {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+            const float sv[3] = {a.scale_modifier * s.x, a.scale_modifier * s.y, a.scale_modifier * s.z};
+            float Mm[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) Mm[c][rr] = sv[rr] * R[c][rr];
+            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            float dM[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++)
+                    dM[c][rr] = 2.0f * (Mm[0][rr] * dS[c][0] + Mm[1][rr] * dS[c][1] + Mm[2][rr] * dS[c][2]);
+            float dMt[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) dMt[k][j] = dM[j][k];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                dscale[k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) dMt[k][j] *= sv[k];
+            drot[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+            drot[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+            drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+            drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
+        }
+        // ---- SE3 backward (closed form), once, on the summed dL/d(deformed mean) ----
+        float gx[3] = {gm[0], gm[1], gm[2]};
+        float dS6[6] = {0, 0, 0, 0, 0, 0};
+        float dth = 0.0f;
+        if (a.deform_mode != GSR_DEFORM_NONE) {
+            const float3 g = make_float3(gm[0], gm[1], gm[2]);
+            float sn, cs;
+            sincosf(th, &sn, &cs);
+            const float ka = sn, kb = 1.0f - cs, kc = th - sn;
+            const float3 wg = cross3(w, g), wwg = skew2(w, g);
+            gx[0] = g.x - ka * wg.x + kb * wwg.x;
+            gx[1] = g.y - ka * wg.y + kb * wwg.y;
+            gx[2] = g.z - ka * wg.z + kb * wwg.z;
+            dS6[3] = th * g.x - kb * wg.x + kc * wwg.x;
+            dS6[4] = th * g.y - kb * wg.y + kc * wwg.y;
+            dS6[5] = th * g.z - kb * wg.z + kc * wwg.z;
+            const float3 wx = cross3(w, x0), wwx = skew2(w, x0), wv = cross3(w, tv), wwv = skew2(w, tv);
+            dth = g.x * (cs * wx.x + sn * wwx.x + tv.x + sn * wv.x + kb * wwv.x) +
+                  g.y * (cs * wx.y + sn * wwx.y + tv.y + sn * wv.y + kb * wwv.y) +
+                  g.z * (cs * wx.z + sn * wwx.z + tv.z + sn * wv.z + kb * wwv.z);
+            const float3 xg = cross3(x0, g), vg = cross3(tv, g);
+            const float wdx = dot3(w, x0), wdv = dot3(w, tv), wdg = dot3(w, g), gdx = dot3(g, x0), gdv = dot3(g, tv);
+            const float3 Dx = make_float3(g.x * wdx + x0.x * wdg - 2.f * w.x * gdx, g.y * wdx + x0.y * wdg - 2.f * w.y * gdx,
+                                          g.z * wdx + x0.z * wdg - 2.f * w.z * gdx);
+            const float3 Dv = make_float3(g.x * wdv + tv.x * wdg - 2.f * w.x * gdv, g.y * wdv + tv.y * wdg - 2.f * w.y * gdv,
+                                          g.z * wdv + tv.z * wdg - 2.f * w.z * gdv);
+            dS6[0] = ka * xg.x + kb * Dx.x + kb * vg.x + kc * Dv.x;
+            dS6[1] = ka * xg.y + kb * Dx.y + kb * vg.y + kc * Dv.y;
+            dS6[2] = ka * xg.z + kb * Dx.z + kb * vg.z + kc * Dv.z;
+        }
+        // ---- stores: running sums by fire-and-forget RED (measured: a plain load-add-store per output is 12 % slower -
+        // the extra DRAM round trip at the end of every thread outweighs the atomics) ----
+        auto upd = [&](float* p, float val, bool accumulate) { emit(p, val, accumulate); };
+        {
+            float* dst = a.dL_dsh + 48 * (size_t)idx;
+            if (acc & GSR_ACC_SH) {
+#pragma unroll
+                for (int k = 0; k < 12; k++)
+                    atomicAdd(reinterpret_cast<float4*>(dst) + k, make_float4(dsh[4 * k], dsh[4 * k + 1], dsh[4 * k + 2], dsh[4 * k + 3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) st256(dst + 8 * k, dsh + 8 * k);
+            }
+        }
+        upd(a.dL_dopacity + idx, dop, acc & GSR_ACC_OPACITY);
+#pragma unroll
+        for (int k = 0; k < 3; k++) upd(a.dL_dscales + 3 * idx + k, dscale[k], acc & GSR_ACC_SCALES);
+        st_rec4(a.dL_drots, idx, make_float4(drot[0], drot[1], drot[2], drot[3]), (acc & GSR_ACC_ROTS) != 0);
+        if (a.dL_dtwist_S && a.deform_mode != GSR_DEFORM_NONE) {
+            if (a.deform_mode == GSR_DEFORM_PER_GAUSSIAN) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) upd(a.dL_dtwist_S + 6 * (size_t)idx + k, dS6[k], acc & GSR_ACC_TWIST);
+                upd(a.dL_dtwist_theta + idx, dth, acc & GSR_ACC_TWIST);
+            } else if (body_smem) {
+                float* dstS = s_body + 7 * tix;
+#pragma unroll
+                for (int k = 0; k < 6; k++) atomicAdd(dstS + k, dS6[k]);
+                atomicAdd(dstS + 6, dth);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) atomicAdd(a.dL_dtwist_S + 6 * (size_t)tix + k, dS6[k]);
+                atomicAdd(a.dL_dtwist_theta + tix, dth);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) upd(a.dL_dmeans3D + 3 * idx + k, gx[k], acc & GSR_ACC_MEANS3D);
+    }
+    if (body_smem) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < a.num_bodies * 7; k += 128) {
+            const float val = s_body[k];
+            if (val != 0.0f) {
+                const int b = k / 7, c = k % 7;
+                if (c < 6) atomicAdd(a.dL_dtwist_S + 6 * (size_t)b + c, val);
+                else atomicAdd(a.dL_dtwist_theta + b, val);
+            }
+        }
+    }
+}
+
 // ---- standalone exp_se3: S[N,6], theta[N] -> T[N,4,4] (rigid_body.exp_se3) ----
 __global__ void __launch_bounds__(256) se3_matrices_kernel(int N, const float* __restrict__ S,
                                                            const float* __restrict__ theta, float* __restrict__ T44) {
@@ -528,6 +902,21 @@ __global__ void __launch_bounds__(256) se3_matrices_bwd_kernel(int N, const floa
 }
 
 }  // namespace
+
+int gsr_launch_preprocess_bwd_batched(const PreprocessBwdBatchArgs& a, const BwdViewSlot* d_slots, cudaStream_t stream) {
+    if (a.P <= 0 || a.n_views <= 0) return 0;
+    size_t smem = 0;
+    if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && a.dL_dtwist_S && a.num_bodies * 7 * 4 <= 32768)
+        smem = (size_t)a.num_bodies * 7 * 4;
+    { GsrProfScope prof_("preprocess_bwd_batched", stream);
+    // measured at C2 (8 views): 234 registers / 2 CTAs per SM 0.376 ms, 168 / 3 (spills) 0.447 ms, 128 / 4 0.530 ms: issue-bound
+    static const int minb = getenv("GSR_PRE_BWDB_MINB") ? atoi(getenv("GSR_PRE_BWDB_MINB")) : 2;
+    if (minb >= 4) preprocess_bwd_batched_kernel<4><<<gsr_div_up(a.P, 128), 128, smem, stream>>>(a, d_slots);
+    else if (minb == 2) preprocess_bwd_batched_kernel<2><<<gsr_div_up(a.P, 128), 128, smem, stream>>>(a, d_slots);
+    else preprocess_bwd_batched_kernel<3><<<gsr_div_up(a.P, 128), 128, smem, stream>>>(a, d_slots); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
 
 int gsr_launch_preprocess_bwd(const PreprocessBwdArgs& a, const GsrView& v, cudaStream_t stream) {
     if (a.P <= 0) return 0;

@@ -196,6 +196,26 @@ struct PreprocessBwdArgs {
 #define GSR_ACC_TWIST 32
 int gsr_launch_preprocess_bwd(const PreprocessBwdArgs& a, const GsrView& v, cudaStream_t stream);
 
+// View-batched variant (backward.cu): one pass over the Gaussians for up to GSR_BATCH_MAX_VIEWS views of the same parameters.
+#define GSR_BATCH_MAX_VIEWS 8
+struct BwdViewSlot {                  // per view, in device memory
+    GsrView v;
+    const int* radii; const uint8_t* clamped;
+    const float4* grad_recs;         // [P,3] from the view's blend backward
+    const float4* recs;              // [P,3] the view's splat records
+    float* dL_dmeans2D;              // [P,3] written for every Gaussian (zeros where the view culled it)
+};
+struct PreprocessBwdBatchArgs {
+    int P, n_views;
+    const float* means; const float* means_deformed; const float* scales; const float* rotations; const float* shs;
+    int deform_mode; const float* twist_S; const float* twist_theta; const int* body_id; int num_bodies;
+    float scale_modifier; int grad_moments;
+    float* dL_dmeans3D; float* dL_dopacity; float* dL_dsh; float* dL_dscales; float* dL_drots;
+    float* dL_dtwist_S; float* dL_dtwist_theta;
+    int acc;
+};
+int gsr_launch_preprocess_bwd_batched(const PreprocessBwdBatchArgs& a, const BwdViewSlot* d_slots, cudaStream_t stream);
+
 // ---- standalone SE3 (rigid_body drop-in) ------------------------------------
 int gsr_launch_se3_matrices(int N, const float* S, const float* theta, float* T44, cudaStream_t stream);
 int gsr_launch_se3_matrices_bwd(int N, const float* S, const float* theta, const float* dT44, float* dS,

@@ -19,6 +19,7 @@ flat all-reduce buffer, see view_parallel.FlatGradBuffer) and autograd receives 
 gradient for those inputs - view-batched training then needs no per-view
 accumulation pass.
 """
+import ctypes
 import os
 import warnings
 from typing import NamedTuple
@@ -178,6 +179,93 @@ def _bucket(nbytes):
     return b
 
 
+class GaussianBackwardBatch:
+    """`accumulate_grads=` target that also BATCHES the per-Gaussian half of the backward over the views of a step.
+
+    A training step renders several views of the same parameters and sums their gradients.  Passed as `accumulate_grads`
+    (in place of the plain {input name: gradient buffer} dict it wraps), this object makes each view's backward run only
+    the blend backward (per-pixel work -> the view's 48-byte per-Gaussian records); `flush()` then runs ONE kernel over
+    the Gaussians for all pending views (libgsr_b200: gsr_backward_gaussians_batched): every parameter record is read
+    once and the running gradients are updated once per step instead of once per view.  The result equals the per-view
+    path up to fp32 summation order.
+
+    Requirements (checked): SH colours with 16 coefficients, scales + rotations (no precomputed colours / covariances),
+    every differentiable Gaussian input present in `targets`, 32-byte aligned SH tensors, and all views of a batch given
+    the SAME input tensors (a view with other inputs flushes the pending ones first).  The view-space gradients
+    (`means2D`'s, which the reference reads for its densification statistics) are not returned through autograd in this
+    mode: after `flush()` they are in `viewspace_grads`, one [P, 3] tensor per view in the order the backwards ran."""
+
+    def __init__(self, targets):
+        self.targets = dict(targets)
+        self.viewspace_grads = []
+        self._items = []
+        self._shared = None
+        self._key = None
+
+    def __len__(self):
+        return len(self._items)
+
+    # dict protocol used by the forward's argument checks
+    def items(self):
+        return self.targets.items()
+
+    def _add(self, key, shared, item):
+        if self._items and key != self._key:
+            self.flush()
+        if not self._items:
+            self.viewspace_grads = []
+        self._key, self._shared = key, shared
+        self._items.append(item)
+
+    def flush(self):
+        """Run the batched per-Gaussian backward for the pending views on the current stream (which is made to wait for
+        the streams the views ran on).  No-op when nothing is pending."""
+        items, sh = self._items, self._shared
+        self._items, self._shared, self._key = [], None, None
+        if not items:
+            return
+        lib = _rt.load()
+        dev = sh["means3D"].device
+        P, M = sh["P"], sh["M"]
+        n = len(items)
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            arr = (_rt.gsr_view_grads * n)()
+            for j, it in enumerate(items):
+                cur.wait_event(it["event"])
+                arr[j].view = ctypes.pointer(it["view"])
+                arr[j].radii = it["radii"].data_ptr()
+                arr[j].geom_ws = it["geom"].data_ptr()
+                arr[j].grad_ws = it["grad_ws"].data_ptr()
+                arr[j].dL_dmeans2D = it["grad_means2D"].data_ptr()
+            nbytes = lib.gsr_backward_batched_slots_bytes(n)
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            _rt.check(lib.gsr_backward_batched_fill_slots(n, arr, P, M, host.data_ptr(), nbytes))
+            slots = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            slots.copy_(host, non_blocking=True)
+            t = self.targets
+            mask = 0
+            for k in t:
+                mask |= _ACC_BITS[k]
+            deform = _Deform(sh["tw_S"], sh["tw_theta"], sh["body_id"])
+            means_def = items[0]["means_def"]
+            _rt.check(lib.gsr_backward_gaussians_batched(
+                n, _rt.ptr(slots), float(items[0]["view"].scale_modifier), P, M, _rt.ptr(sh["means3D"]), _rt.ptr(means_def),
+                _rt.ptr(sh["scales"]), _rt.ptr(sh["rotations"]), _rt.ptr(sh["sh"]), deform.c_struct(),
+                _rt.ptr(t["means3D"]), _rt.ptr(t["opacities"]), _rt.ptr(t["shs"]), _rt.ptr(t["scales"]), _rt.ptr(t["rotations"]),
+                _rt.ptr(t.get("se3_S")), _rt.ptr(t.get("se3_theta")), mask, _rt.stream_ptr(dev)))
+            # The views' workspaces were allocated on the views' streams and are read here on another one.  Instead of
+            # record_stream (which parks the blocks until an event is polled and sends the allocator to cudaMalloc when
+            # the host runs ahead), every view stream is ordered after this kernel: whatever reuses the blocks there
+            # comes after their last use.
+            done = torch.cuda.Event()
+            done.record(cur)
+            for st in {it["stream"] for it in items}:
+                if st != cur:
+                    st.wait_event(done)
+        self.viewspace_grads = [it["grad_means2D"] for it in items]
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(
@@ -283,7 +371,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _rt.check(lib.gsr_forward_render(view, P, num_rendered, _rt.ptr(radii), _rt.ptr(geom), _rt.ptr(binning),
                                                  binning.numel(), _rt.ptr(img), _rt.ptr(color), 0, stream))
 
-        acc = dict(accumulate_grads) if accumulate_grads else {}
+        batch = accumulate_grads if isinstance(accumulate_grads, GaussianBackwardBatch) else None
+        acc = dict(batch.targets) if batch is not None else (dict(accumulate_grads) if accumulate_grads else {})
         shapes = {"means3D": means3D, "opacities": opacities, "shs": sh, "scales": scales, "rotations": rotations,
                   "se3_S": se3_S, "se3_theta": se3_theta}
         for k, buf in acc.items():
@@ -300,6 +389,18 @@ class _RasterizeGaussians(torch.autograd.Function):
                                    "gradients of leaves (pass the activated tensor without accumulate_grads instead)" % k)
         if ("se3_S" in acc) != ("se3_theta" in acc):
             raise _rt.GsrError("accumulate_grads: give both se3_S and se3_theta or neither")
+        if batch is not None:
+            need = {"means3D", "opacities", "shs", "scales", "rotations"} | ({"se3_S", "se3_theta"} if deform.mode else set())
+            if (sh_c is None or sh_c.numel() == 0 or M != 16 or scales_c is None or scales_c.numel() == 0 or
+                    (colors_c is not None and colors_c.numel()) or (cov_c is not None and cov_c.numel())):
+                raise _rt.GsrError("GaussianBackwardBatch needs SH colours with 16 coefficients and scales + rotations")
+            if not need <= set(acc):
+                raise _rt.GsrError("GaussianBackwardBatch: targets must hold a gradient buffer for each of %s" % sorted(need))
+            if (sh_c.data_ptr() | acc["shs"].data_ptr()) & 31:
+                raise _rt.GsrError("GaussianBackwardBatch: shs and its gradient buffer must be 32-byte aligned")
+            if raster_settings.debug:
+                raise _rt.GsrError("GaussianBackwardBatch: not available with debug=True")
+        ctx.batch = batch
         ctx.acc = acc
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered
@@ -349,6 +450,29 @@ class _RasterizeGaussians(torch.autograd.Function):
         has_sh, has_colors, has_scales, has_cov = ctx.flags
         f32 = dict(dtype=torch.float32, device=dev)
         acc = ctx.acc
+        if ctx.batch is not None and P != 0:
+            # view-batched backward: the blend half now, the per-Gaussian half at GaussianBackwardBatch.flush()
+            g = grad_out_color
+            if g.dtype != torch.float32:
+                g = g.float()
+            g = g.contiguous()
+            with torch.cuda.device(dev):
+                grad_ws = torch.empty(lib.gsr_grad_bytes(P), dtype=torch.uint8, device=dev)
+                _rt.check(lib.gsr_backward_blend(ctx.view, P, ctx.num_rendered, _rt.ptr(geom), _rt.ptr(binning), _rt.ptr(img),
+                                                 _rt.ptr(grad_ws), _rt.ptr(g), _rt.stream_ptr(dev)))
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+            dm = ctx.deform_mode
+            shared = dict(P=P, M=M, means3D=means3D, scales=scales, rotations=rotations, sh=sh,
+                          tw_S=tw_S if dm else None, tw_theta=tw_theta if dm else None,
+                          body_id=body_id if dm == _rt.DEFORM_RIGID_BODIES else None)
+            key = (P, M, dm, means3D.data_ptr(), scales.data_ptr(), rotations.data_ptr(), sh.data_ptr(),
+                   tw_S.data_ptr() if dm else 0, tw_theta.data_ptr() if dm else 0,
+                   body_id.data_ptr() if dm == _rt.DEFORM_RIGID_BODIES else 0, float(ctx.view.scale_modifier))
+            ctx.batch._add(key, shared, dict(view=ctx.view, radii=radii, geom=geom, grad_ws=grad_ws, event=ev,
+                                             stream=torch.cuda.current_stream(dev),
+                                             grad_means2D=torch.empty((P, 3), **f32), means_def=means_def if dm else None))
+            return (None,) * 14
         mask = 0
         for k in acc:
             mask |= _ACC_BITS[k]

@@ -66,6 +66,12 @@ class gsr_gemm(ctypes.Structure):
     ]
 
 
+class gsr_view_grads(ctypes.Structure):
+    """include/gsr_b200.h: one view of a view-batched backward."""
+    _fields_ = [("view", ctypes.POINTER(gsr_view)), ("radii", ctypes.c_void_p), ("geom_ws", ctypes.c_void_p),
+                ("grad_ws", ctypes.c_void_p), ("dL_dmeans2D", ctypes.c_void_p)]
+
+
 GEMM_RELU_SPLIT, GEMM_SPLIT, GEMM_PLAIN, GEMM_ATOMIC = 0, 1, 2, 3
 DEFORM_NONE, DEFORM_PER_GAUSSIAN, DEFORM_RIGID_BODIES = 0, 1, 2
 
@@ -97,6 +103,11 @@ _SIGNATURES = {
                                     _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
                                     _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
+    "gsr_backward_blend": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P, _P]),
+    "gsr_backward_batched_slots_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "gsr_backward_batched_fill_slots": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(gsr_view_grads), ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t]),
+    "gsr_backward_gaussians_batched": (ctypes.c_int, [ctypes.c_int, _P, ctypes.c_float, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P,
+                                                       ctypes.POINTER(gsr_deform), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
     "gsr_debug_blend_stats": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P]),
     "gsr_depth_order_ws_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_depth_order": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_size_t, _P, _P, _P]),

@@ -96,19 +96,23 @@ def reduce_densification_stats(xyz_gradient_accum, denom, max_radii2D, group=Non
 _streams = {}
 
 
-def render_views(render_view, views, num_streams=2):
+def render_views(render_view, views, num_streams=2, batch=None):
     """Run `render_view(i)` (forward + backward of local view i, accumulating into shared gradient
     buffers) for every i in `views`, spreading the views round-robin over `num_streams` CUDA streams.
     The views of one step only meet in the gradient sums (atomic adds), so they may overlap: the
     latency-bound part of one view (depth sort passes, scans, launch gaps, kernel tails) runs under
     the issue-bound blend kernels of another.  Returns the summed loss (tensor on the current stream).
-    `render_view` must allocate per-view state itself (the rasterizer does) and return a detached loss."""
+    `render_view` must allocate per-view state itself (the rasterizer does) and return a detached loss.
+    `batch`: the diff_gaussian_rasterization.GaussianBackwardBatch the views were given as `accumulate_grads`, if any - its
+    pending per-Gaussian backward runs here, once for all views, after the views' streams have been joined."""
     views = list(views)
     if num_streams <= 1 or len(views) <= 1 or not torch.cuda.is_available():
         total = None
         for i in views:
             loss = render_view(i)
             total = loss if total is None else total + loss
+        if batch is not None:
+            batch.flush()
         return total
     dev = torch.cuda.current_device()
     key = (dev, num_streams)
@@ -124,6 +128,8 @@ def render_views(render_view, views, num_streams=2):
             losses.append(render_view(i))
     for s in side:
         main.wait_stream(s)
+    if batch is not None:
+        batch.flush()
     total = losses[0]
     for l in losses[1:]:
         total = total + l

@@ -182,6 +182,35 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
 int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t num_rendered, const void* geom_ws,
                           const void* binning_ws, const void* image_ws, unsigned long long* out8, void* stream);
 
+/* ---- view-batched backward (training steps that render several views of the SAME parameters) -----------------------
+ * gsr_backward = renderCUDA backward + the per-Gaussian chain rule (computeCov2DCUDA / preprocessCUDA backward,
+ * cuda_rasterizer/backward.cu:144-396, + the SE3 autograd of scene/rigid_body.py).  The second half reads every parameter
+ * record and read-modify-writes the running gradient once per view.  Split in two, the first half runs per view
+ * (gsr_backward_blend: fills the view's grad_ws) and the second ONCE for up to all views of the step
+ * (gsr_backward_gaussians_batched): parameters read once, gradients updated once; cov3D and SE3 backward are linear in
+ * their upstream gradients, which are summed over the views first.  Requires scales + rotations, SH colours with M = 16
+ * and 32-byte aligned shs / dL_dsh, one scale_modifier for the batch; results equal the per-view path up to fp32
+ * summation order.  dL_dmeans2D is per view.
+ *   gsr_backward_batched_fill_slots   host-only: packs the views' constants and workspace pointers into slots_host
+ *                                     (gsr_backward_batched_slots_bytes(n) bytes, e.g. pinned memory) - copy them to the
+ *                                     device in stream order and pass the device copy as slots_device. */
+typedef struct gsr_view_grads {
+    const gsr_view* view;
+    const int32_t* radii;      /* of the view's forward */
+    const void* geom_ws;       /* the view's geometry workspace */
+    const void* grad_ws;       /* filled by gsr_backward_blend for this view */
+    float* dL_dmeans2D;        /* [P,3], written for every Gaussian */
+} gsr_view_grads;
+int gsr_backward_blend(const gsr_view* view, int P, uint32_t num_rendered, const void* geom_ws, const void* binning_ws,
+                       const void* image_ws, void* grad_ws, const float* dL_dout_color, void* stream);
+size_t gsr_backward_batched_slots_bytes(int n_views);
+int gsr_backward_batched_fill_slots(int n_views, const gsr_view_grads* views, int P, int M, void* slots_host, size_t slots_bytes);
+int gsr_backward_gaussians_batched(int n_views, const void* slots_device, float scale_modifier, int P, int M, const float* means3D,
+                                   const float* means_deformed, const float* scales, const float* rotations, const float* shs,
+                                   const gsr_deform* deform, float* dL_dmeans3D, float* dL_dopacity, float* dL_dsh,
+                                   float* dL_dscales, float* dL_drots, float* dL_dtwist_S, float* dL_dtwist_theta,
+                                   int accumulate_mask, void* stream);
+
 /* The depth sort of the forward on its own (csrc/depth_sort.cu; replaces the depth half of the reference's
  * cub::DeviceRadixSort::SortPairs, rasterizer_impl.cu:303-308): keys = device u32[P], 0xffffffff marks an entry that is
  * left out; order[0 .. n) receives the indices of the other entries by ascending (key, index) - the order a stable sort

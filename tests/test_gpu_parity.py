@@ -438,6 +438,65 @@ def test_accumulate_grads_matches_autograd_sum():
         assert rel_to_max(a[k], b[k]) <= GRAD_TOL, k
 
 
+@pytest.mark.parametrize("mode", ["per_gaussian", "rigid_bodies", "none"])
+def test_batched_backward_matches_per_view_backward(mode):
+    """GaussianBackwardBatch: the per-Gaussian half of the backward run ONCE for all views of a step (parameters read
+    once, gradients updated once; cov3D / SE3 backward applied to the view-summed upstream gradients) must give the
+    per-view accumulate path's gradients, and the per-view view-space gradients, up to fp32 summation order."""
+    import synthetic
+    import view_parallel as vp
+    from _gpu_util import make_view_settings, rel_to_max
+    from diff_gaussian_rasterization import GaussianRasterizer, GaussianBackwardBatch
+    P, W, H, V = 60003, 320, 240, 5          # P not a multiple of 4: the flat buffer's 32-byte alignment is what counts
+    sc, _, _ = make_view_settings(P, W, H, scale_mult=1.5)
+    B = 16
+    if mode == "rigid_bodies":
+        S, th = synthetic.make_twists(B, device="cuda")
+        body = (torch.arange(P, device="cuda") % B).to(torch.int32)
+    else:
+        S, th = synthetic.make_twists(P, device="cuda")
+        body = None
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    bg = torch.tensor([0.2, 0.1, 0.3], device="cuda")
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+
+    def run(batched):
+        leaves = {k: sc[k].clone().requires_grad_(True) for k in names}
+        if mode != "none":
+            leaves["se3_S"], leaves["se3_theta"] = S.clone().requires_grad_(True), th.clone().requires_grad_(True)
+        buf = vp.FlatGradBuffer(list(leaves.values()))
+        sinks = {k: v.grad for k, v in leaves.items()}
+        batch = GaussianBackwardBatch(sinks) if batched else None
+        m2ds = []
+
+        def render_view(k):
+            cam = synthetic.make_camera(k, 8, W, H, device="cuda")
+            rs = synthetic.raster_settings(cam, bg)
+            m2d = torch.zeros(P, 3, device="cuda", requires_grad=True)
+            m2ds.append(m2d)
+            extra = {} if mode == "none" else dict(se3_S=leaves["se3_S"], se3_theta=leaves["se3_theta"], body_id=body)
+            color, _ = GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                              shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
+                                              accumulate_grads=batch if batched else sinks, **extra)
+            color.backward(grad)
+            return color.detach().sum()
+        vp.render_views(render_view, range(V), num_streams=2, batch=batch)
+        torch.cuda.synchronize()
+        if batched:
+            assert len(batch) == 0 and len(batch.viewspace_grads) == V
+            vs = [g.clone() for g in batch.viewspace_grads]
+        else:
+            vs = [m.grad.clone() for m in m2ds]
+        return {k: v.grad.clone() for k, v in leaves.items()}, vs, buf
+    (a, va, _), (b, vb, _) = run(True), run(False)
+    for k in a:
+        assert float(b[k].abs().max()) > 0, k
+        assert rel_to_max(a[k], b[k]) <= 2e-5, (mode, k, rel_to_max(a[k], b[k]))
+    # streams may finish the views in any order: match each batched view-space gradient to its per-view counterpart
+    for g in va:
+        assert min(rel_to_max(g, h) for h in vb) <= 2e-5
+
+
 def test_packed_expf_is_cudas_expf_on_every_float():
     """The blend kernels evaluate expf on packed FP32x2 values (csrc/f32x2.cuh) with CUDA's own algorithm restated;
     it must be bit-identical to expf (what forward.cu:342 / backward.cu:472 compile to) on the whole range
