@@ -172,9 +172,18 @@ def step_ours(leaves, cams, bg, grad, args):
     if no_deform:
         sinks = {k: v for k, v in sinks.items() if not k.startswith("se3_")}
     # the per-Gaussian half of the backward runs once for all views of the step (--batched-backward 0: once per view)
-    batch = GaussianBackwardBatch(sinks) if getattr(args, "batched_backward", 1) else None
-    if batch is not None:
+    batch = None
+    overlap = False
+    if getattr(args, "batched_backward", 1):
+        # N > 1: the batched kernel runs over 4 ranges of Gaussians and each range's all-reduce starts as soon as the range
+        # is enqueued (NCCL's stream), so only the last range's collective is exposed
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        overlap = world > 1 and bool(getattr(args, "overlap_allreduce", 0))
+        P = leaves["means3D"].shape[0]
+        batch = GaussianBackwardBatch(sinks, chunks=4 if overlap else 1,
+                                      after_chunk=(lambda first, count: buf.all_reduce_rows(first, count, P)) if overlap else None)
         sinks = batch
+    args._reduced_in_step = overlap
 
     def render_view(i):
         rs = synthetic.raster_settings(cams[i], bg, sh_degree=3)
@@ -194,7 +203,10 @@ def step_ours(leaves, cams, bg, grad, args):
         color.backward(grad)
         return loss
 
-    return view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams, batch=batch)
+    total = view_parallel.render_views(render_view, range(len(cams)), num_streams=args.streams, batch=batch)
+    if overlap:
+        buf.wait()
+    return total
 
 
 def _ref_deform(leaves, args):
@@ -493,6 +505,10 @@ def main():
     ap.add_argument("--W", type=int, default=None)
     ap.add_argument("--H", type=int, default=None)
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are spread over (ours)")
+    ap.add_argument("--overlap-allreduce", type=int, default=0, dest="overlap_allreduce",
+                    help="ours, N > 1, with --batched-backward 1: all-reduce the gradients by ranges of Gaussians while the "
+                         "batched kernel computes the next range (0: one all-reduce after the step).  Measured at N = 2: "
+                         "9.59 vs 9.65 ms/step - the step's exposed cost is rank skew, not the collective - so off by default")
     ap.add_argument("--batched-backward", type=int, default=1, dest="batched_backward",
                     help="ours: 1 = the per-Gaussian half of the backward runs once per step for all views "
                          "(GaussianBackwardBatch), 0 = once per view")
@@ -552,7 +568,7 @@ def main():
     def run_step():
         if args.impl == "ours":
             loss = step_fn(leaves, cams, bg, grad, args)     # zeroes + fills the flat gradient buffer
-            if world > 1:
+            if world > 1 and not getattr(args, "_reduced_in_step", False):
                 flat_buffer(leaves).all_reduce()                # ONE collective over 66 floats/Gaussian
         else:
             zero_grads(leaves)
@@ -721,8 +737,9 @@ def main():
         rt.profile_enable(True)
         zero_grads(leaves)
         n_streams, args.streams = args.streams, 1       # kernels timed one at a time, not overlapping another view's
+        ov, args.overlap_allreduce = getattr(args, "overlap_allreduce", 0), 0
         step_fn(leaves, cams, bg, grad, args)          # rank-local: NO collective here (other ranks are done)
-        args.streams = n_streams
+        args.streams, args.overlap_allreduce = n_streams, ov
         torch.cuda.synchronize()
         prof = rt.profile_dump()
         rt.profile_enable(False)

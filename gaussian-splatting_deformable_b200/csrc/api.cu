@@ -584,12 +584,13 @@ int gsr_backward_batched_fill_slots(int n_views, const gsr_view_grads* views, in
     return 0;
 }
 
-int gsr_backward_gaussians_batched(int n_views, const void* slots_device, float scale_modifier, int P, int M, const float* means3D,
+int gsr_backward_gaussians_batched(int n_views, const void* slots_device, float scale_modifier, int P, int first, int count, int M, const float* means3D,
                                    const float* means_deformed, const float* scales, const float* rotations, const float* shs,
                                    const gsr_deform* deform, float* dL_dmeans3D, float* dL_dopacity, float* dL_dsh, float* dL_dscales,
                                    float* dL_drots, float* dL_dtwist_S, float* dL_dtwist_theta, int accumulate_mask, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (P <= 0 || n_views <= 0) return 0;
+    if (P <= 0 || n_views <= 0 || count == 0) return 0;
+    if (first < 0 || count < 0 || (long long)first + count > P) return gsr_set_error_msg(-1, "batched backward: Gaussian range outside [0, P)");
     if (!slots_device || !means3D || !scales || !rotations || !shs || !dL_dmeans3D || !dL_dopacity || !dL_dsh || !dL_dscales || !dL_drots)
         return gsr_set_error_msg(-1, "batched backward: required pointer is NULL");
     if (M != 16 || ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dsh)) & 31))
@@ -598,7 +599,7 @@ int gsr_backward_gaussians_batched(int n_views, const void* slots_device, float 
     if (n_views > GSR_BATCH_MAX_VIEWS && (accumulate_mask & all_acc) != all_acc)
         return gsr_set_error_msg(-1, "batched backward: more than 8 views need every output accumulated");
     PreprocessBwdBatchArgs a{};
-    a.P = P; a.means = means3D;
+    a.P = first + count; a.first = first; a.means = means3D;
     a.deform_mode = deform ? deform->mode : GSR_DEFORM_NONE;
     a.means_deformed = (a.deform_mode != GSR_DEFORM_NONE) ? means_deformed : nullptr;
     if (a.deform_mode != GSR_DEFORM_NONE) {

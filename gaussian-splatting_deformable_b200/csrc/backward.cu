@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(128, MINB) preprocess_bwd_batched_kernel(Prepr
     extern __shared__ float s_body[];
     // the views' camera constants and workspace pointers: shared memory (broadcast reads, no pointer chase through global)
     __shared__ __align__(16) BwdViewSlot slots[GSR_BATCH_MAX_VIEWS];
-    const int idx = blockIdx.x * 128 + threadIdx.x;
+    const int idx = a.first + blockIdx.x * 128 + threadIdx.x;       // this launch covers Gaussians [first, P)
     const bool body_smem = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) && a.dL_dtwist_S && (a.num_bodies * 7 * 4 <= 32768);
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(g_slots);
@@ -904,16 +904,17 @@ __global__ void __launch_bounds__(256) se3_matrices_bwd_kernel(int N, const floa
 }  // namespace
 
 int gsr_launch_preprocess_bwd_batched(const PreprocessBwdBatchArgs& a, const BwdViewSlot* d_slots, cudaStream_t stream) {
-    if (a.P <= 0 || a.n_views <= 0) return 0;
+    if (a.P <= a.first || a.n_views <= 0) return 0;
     size_t smem = 0;
     if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && a.dL_dtwist_S && a.num_bodies * 7 * 4 <= 32768)
         smem = (size_t)a.num_bodies * 7 * 4;
     { GsrProfScope prof_("preprocess_bwd_batched", stream);
     // measured at C2 (8 views): 234 registers / 2 CTAs per SM 0.376 ms, 168 / 3 (spills) 0.447 ms, 128 / 4 0.530 ms: issue-bound
     static const int minb = getenv("GSR_PRE_BWDB_MINB") ? atoi(getenv("GSR_PRE_BWDB_MINB")) : 2;
-    if (minb >= 4) preprocess_bwd_batched_kernel<4><<<gsr_div_up(a.P, 128), 128, smem, stream>>>(a, d_slots);
-    else if (minb == 2) preprocess_bwd_batched_kernel<2><<<gsr_div_up(a.P, 128), 128, smem, stream>>>(a, d_slots);
-    else preprocess_bwd_batched_kernel<3><<<gsr_div_up(a.P, 128), 128, smem, stream>>>(a, d_slots); }
+    const int blocks = gsr_div_up(a.P - a.first, 128);
+    if (minb >= 4) preprocess_bwd_batched_kernel<4><<<blocks, 128, smem, stream>>>(a, d_slots);
+    else if (minb == 2) preprocess_bwd_batched_kernel<2><<<blocks, 128, smem, stream>>>(a, d_slots);
+    else preprocess_bwd_batched_kernel<3><<<blocks, 128, smem, stream>>>(a, d_slots); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

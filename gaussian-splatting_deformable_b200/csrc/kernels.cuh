@@ -206,7 +206,8 @@ struct BwdViewSlot {                  // per view, in device memory
     float* dL_dmeans2D;              // [P,3] written for every Gaussian (zeros where the view culled it)
 };
 struct PreprocessBwdBatchArgs {
-    int P, n_views;
+    int P, n_views;                  // the launch covers Gaussians [first, P)
+    int first;
     const float* means; const float* means_deformed; const float* scales; const float* rotations; const float* shs;
     int deform_mode; const float* twist_S; const float* twist_theta; const int* body_id; int num_bodies;
     float scale_modifier; int grad_moments;

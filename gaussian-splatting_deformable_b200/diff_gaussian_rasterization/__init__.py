@@ -195,8 +195,13 @@ class GaussianBackwardBatch:
     (`means2D`'s, which the reference reads for its densification statistics) are not returned through autograd in this
     mode: after `flush()` they are in `viewspace_grads`, one [P, 3] tensor per view in the order the backwards ran."""
 
-    def __init__(self, targets):
+    def __init__(self, targets, chunks=1, after_chunk=None):
+        """`chunks` > 1: flush() runs the kernel over that many consecutive ranges of Gaussians and calls
+        `after_chunk(first, count)` after enqueueing each - e.g. to start the all-reduce of that range of the gradient
+        buffers (view_parallel.FlatGradBuffer.all_reduce_rows) while the next range is computed."""
         self.targets = dict(targets)
+        self.chunks = max(1, int(chunks))
+        self.after_chunk = after_chunk
         self.viewspace_grads = []
         self._items = []
         self._shared = None
@@ -249,11 +254,17 @@ class GaussianBackwardBatch:
                 mask |= _ACC_BITS[k]
             deform = _Deform(sh["tw_S"], sh["tw_theta"], sh["body_id"])
             means_def = items[0]["means_def"]
-            _rt.check(lib.gsr_backward_gaussians_batched(
-                n, _rt.ptr(slots), float(items[0]["view"].scale_modifier), P, M, _rt.ptr(sh["means3D"]), _rt.ptr(means_def),
-                _rt.ptr(sh["scales"]), _rt.ptr(sh["rotations"]), _rt.ptr(sh["sh"]), deform.c_struct(),
-                _rt.ptr(t["means3D"]), _rt.ptr(t["opacities"]), _rt.ptr(t["shs"]), _rt.ptr(t["scales"]), _rt.ptr(t["rotations"]),
-                _rt.ptr(t.get("se3_S")), _rt.ptr(t.get("se3_theta")), mask, _rt.stream_ptr(dev)))
+            chunks = min(self.chunks, max(1, P // 4096))
+            step = ((P + chunks - 1) // chunks + 127) // 128 * 128
+            for first in range(0, P, step):
+                count = min(step, P - first)
+                _rt.check(lib.gsr_backward_gaussians_batched(
+                    n, _rt.ptr(slots), float(items[0]["view"].scale_modifier), P, first, count, M, _rt.ptr(sh["means3D"]),
+                    _rt.ptr(means_def), _rt.ptr(sh["scales"]), _rt.ptr(sh["rotations"]), _rt.ptr(sh["sh"]), deform.c_struct(),
+                    _rt.ptr(t["means3D"]), _rt.ptr(t["opacities"]), _rt.ptr(t["shs"]), _rt.ptr(t["scales"]), _rt.ptr(t["rotations"]),
+                    _rt.ptr(t.get("se3_S")), _rt.ptr(t.get("se3_theta")), mask, _rt.stream_ptr(dev)))
+                if self.after_chunk is not None:
+                    self.after_chunk(first, count)
             # The views' workspaces were allocated on the views' streams and are read here on another one.  Instead of
             # record_stream (which parks the blocks until an event is polled and sends the allocator to cudaMalloc when
             # the host runs ahead), every view stream is ordered after this kernel: whatever reuses the blocks there

@@ -106,7 +106,7 @@ _SIGNATURES = {
     "gsr_backward_blend": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P, _P]),
     "gsr_backward_batched_slots_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_backward_batched_fill_slots": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(gsr_view_grads), ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t]),
-    "gsr_backward_gaussians_batched": (ctypes.c_int, [ctypes.c_int, _P, ctypes.c_float, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P,
+    "gsr_backward_gaussians_batched": (ctypes.c_int, [ctypes.c_int, _P, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P,
                                                        ctypes.POINTER(gsr_deform), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
     "gsr_debug_blend_stats": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P]),
     "gsr_depth_order_ws_bytes": (ctypes.c_size_t, [ctypes.c_int]),

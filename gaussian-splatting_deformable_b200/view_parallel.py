@@ -49,6 +49,7 @@ class FlatGradBuffer:
         self.offsets, total = flat_layout(self.params)
         first = self.params[0]
         self.flat = torch.zeros(total, dtype=torch.float32, device=first.device)
+        self._works = []
         self._attach()
 
     def _attach(self, only_if_replaced=False):
@@ -79,6 +80,47 @@ class FlatGradBuffer:
             if average:
                 self.flat.div_(dist.get_world_size(group))
         return self.flat.numel() * 4
+
+
+    # ---- all-reduce by ranges of Gaussians, overlapped with the kernel that produces the gradients -------------------
+    def all_reduce_rows(self, first, count, rows, group=None):
+        """Start (asynchronously) the all-reduce of rows [first, first + count) of every per-Gaussian gradient (the tensors
+        whose leading dimension is `rows`); the other tensors (e.g. the twists of a few rigid bodies) go with the range
+        that ends at `rows`.  Meant as GaussianBackwardBatch's `after_chunk`: the range just enqueued on the current
+        stream is reduced on the collective's stream while the next range is computed.  Call wait() before the gradients
+        are used.  Returns the number of elements reduced."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return 0
+        pieces = []
+        for p, off in zip(self.params, self.offsets):
+            if p.dim() >= 1 and p.shape[0] == rows:
+                per = p.numel() // rows
+                piece = self.flat[off + first * per: off + (first + count) * per]
+            elif first + count == rows:
+                piece = self.flat[off: off + p.numel()]
+            else:
+                continue
+            if piece.numel():
+                pieces.append(piece)
+        if not pieces:
+            return 0
+        cm = getattr(dist, "_coalescing_manager", None) if self.flat.is_cuda else None
+        if cm is not None:
+            # one NCCL group (one kernel) for the range's pieces instead of one collective per tensor
+            with cm(group=group, device=self.flat.device, async_ops=True) as work:
+                for piece in pieces:
+                    dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group)
+            self._works.append(work)
+        else:
+            for piece in pieces:
+                self._works.append(dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        return sum(piece.numel() for piece in pieces)
+
+    def wait(self):
+        """Order the current stream after every all-reduce started by all_reduce_rows."""
+        for w in self._works:
+            w.wait()
+        self._works = []
 
 
 def reduce_densification_stats(xyz_gradient_accum, denom, max_radii2D, group=None):

@@ -190,7 +190,8 @@ int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t num_rendered, co
  * (gsr_backward_gaussians_batched): parameters read once, gradients updated once; cov3D and SE3 backward are linear in
  * their upstream gradients, which are summed over the views first.  Requires scales + rotations, SH colours with M = 16
  * and 32-byte aligned shs / dL_dsh, one scale_modifier for the batch; results equal the per-view path up to fp32
- * summation order.  dL_dmeans2D is per view.
+ * summation order.  dL_dmeans2D is per view.  A call covers the Gaussians [first, first + count) (all pointers are those of
+ * the whole arrays), so that a caller can start the all-reduce of one range of the gradients while the next is computed.
  *   gsr_backward_batched_fill_slots   host-only: packs the views' constants and workspace pointers into slots_host
  *                                     (gsr_backward_batched_slots_bytes(n) bytes, e.g. pinned memory) - copy them to the
  *                                     device in stream order and pass the device copy as slots_device. */
@@ -205,7 +206,7 @@ int gsr_backward_blend(const gsr_view* view, int P, uint32_t num_rendered, const
                        const void* image_ws, void* grad_ws, const float* dL_dout_color, void* stream);
 size_t gsr_backward_batched_slots_bytes(int n_views);
 int gsr_backward_batched_fill_slots(int n_views, const gsr_view_grads* views, int P, int M, void* slots_host, size_t slots_bytes);
-int gsr_backward_gaussians_batched(int n_views, const void* slots_device, float scale_modifier, int P, int M, const float* means3D,
+int gsr_backward_gaussians_batched(int n_views, const void* slots_device, float scale_modifier, int P, int first, int count, int M, const float* means3D,
                                    const float* means_deformed, const float* scales, const float* rotations, const float* shs,
                                    const gsr_deform* deform, float* dL_dmeans3D, float* dL_dopacity, float* dL_dsh,
                                    float* dL_dscales, float* dL_drots, float* dL_dtwist_S, float* dL_dtwist_theta,

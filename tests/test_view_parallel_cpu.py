@@ -105,3 +105,39 @@ def test_two_rank_allreduce_equals_single_process_sum(tmp_path):
     torch.testing.assert_close(got, flat_ref, rtol=1e-5, atol=1e-5 * float(flat_ref.abs().max()))
     assert abs(float(r0["loss"]) - loss) <= 1e-4 * abs(loss)
     assert torch.equal(r0["stats"]["denom"].reshape(-1), seen)
+
+
+def _rows_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    rows = 1003                                                     # not a multiple of anything
+    shapes = [(rows, 3), (rows, 1), (rows, 16, 3), (rows, 4), (5, 6), (5,)]     # per-Gaussian tensors + a few body twists
+    params = [torch.zeros(s, requires_grad=True) for s in shapes]
+    a, b = vp.FlatGradBuffer(params), None
+    a.flat.copy_(torch.randn(a.flat.numel(), generator=g))
+    whole = a.flat.clone()
+    # by ranges of rows, asynchronously (what GaussianBackwardBatch's after_chunk does), against one all-reduce of everything
+    n = 0
+    for first in range(0, rows, 256):
+        n += a.all_reduce_rows(first, min(256, rows - first), rows)
+    a.wait()
+    dist.all_reduce(whole)
+    offs, _ = vp.flat_layout(params)
+    used = torch.zeros_like(whole, dtype=torch.bool)
+    for p, o in zip(params, offs):
+        used[o:o + p.numel()] = True
+    assert n == int(used.sum())                                     # every element exactly once, padding never sent
+    torch.save(dict(rows=a.flat.clone(), whole=whole, used=used), os.path.join(out_dir, "rows%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_all_reduce_by_row_ranges_equals_one_all_reduce(tmp_path):
+    world = 2
+    mp.spawn(_rows_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "rows0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "rows1.pt"))
+    u = r0["used"]
+    assert torch.equal(r0["rows"][u], r0["whole"][u]) and torch.equal(r1["rows"][u], r1["whole"][u])
+    assert torch.equal(r0["rows"][u], r1["rows"][u])
