@@ -185,18 +185,30 @@ def step_ours(leaves, cams, bg, grad, args):
         sinks = batch
     args._reduced_in_step = overlap
 
+    settings = [synthetic.raster_settings(cam, bg, sh_degree=3) for cam in cams]
+    # the per-Gaussian half of the forward once for all views of the step (--batched-forward 0: once per view)
+    fwd = None
+    if getattr(args, "batched_forward", 1):
+        from diff_gaussian_rasterization import GaussianForwardBatch
+        extra = {} if no_deform else dict(se3_S=leaves["S"], se3_theta=leaves["theta"], body_id=args.body_id)
+        fwd = GaussianForwardBatch(settings, means3D=leaves["means3D"], opacities=leaves["opacities"], shs=leaves["shs"],
+                                   scales=leaves["scales"], rotations=leaves["rotations"], **extra)
+
     def render_view(i):
-        rs = synthetic.raster_settings(cams[i], bg, sh_degree=3)
+        rs = settings[i]
         ras = GaussianRasterizer(rs)
         means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        prepared = fwd.prepared(i) if fwd is not None else None
         if no_deform:
             snk = sinks
             color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
-                               shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"], accumulate_grads=snk)
+                               shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"], accumulate_grads=snk,
+                               prepared=prepared)
         else:
             color, radii = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
                                shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"],
-                               se3_S=leaves["S"], se3_theta=leaves["theta"], body_id=args.body_id, accumulate_grads=sinks)
+                               se3_S=leaves["S"], se3_theta=leaves["theta"], body_id=args.body_id, accumulate_grads=sinks,
+                               prepared=prepared)
         # dL/dimage = grad is injected directly (as the reference arm does below): one reduction for the loss value, no
         # autograd graph through a multiply
         loss = torch.dot(color.detach().reshape(-1), grad.reshape(-1))
@@ -354,12 +366,21 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
             from diff_gaussian_rasterization import GaussianBackwardBatch
             batch = sinks = GaussianBackwardBatch(sinks)
 
+        settings = [synthetic.raster_settings(cam, bg, sh_degree=3) for cam in cams]
+        fwd = None
+        if getattr(args, "batched_forward", 1):
+            from diff_gaussian_rasterization import GaussianForwardBatch
+            fwd = GaussianForwardBatch(settings, means3D=leaves["means3D"], opacities=leaves["opacities"], shs=leaves["shs"],
+                                       scales=leaves["scales"], rotations=leaves["rotations"], se3_S=leaves["S"],
+                                       se3_theta=leaves["theta"], body_id=args.body_id)
+
         def render_view(i):
-            ras = GaussianRasterizer(synthetic.raster_settings(cams[i], bg, sh_degree=3))
+            ras = GaussianRasterizer(settings[i])
             means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
             color, _ = ras(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
                            scales=leaves["scales"], rotations=leaves["rotations"], se3_S=leaves["S"],
-                           se3_theta=leaves["theta"], body_id=args.body_id, accumulate_grads=sinks)
+                           se3_theta=leaves["theta"], body_id=args.body_id, accumulate_grads=sinks,
+                           prepared=fwd.prepared(i) if fwd is not None else None)
             loss = loss_utils.l1_ssim_loss(color, targets[i], 0.2)
             loss.backward()
             return loss.detach()
@@ -505,6 +526,9 @@ def main():
     ap.add_argument("--W", type=int, default=None)
     ap.add_argument("--H", type=int, default=None)
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step are spread over (ours)")
+    ap.add_argument("--batched-forward", type=int, default=1, dest="batched_forward",
+                    help="ours: 1 = the per-Gaussian half of the forward (preprocess) runs once per step for all views "
+                         "(GaussianForwardBatch), 0 = once per view")
     ap.add_argument("--overlap-allreduce", type=int, default=0, dest="overlap_allreduce",
                     help="ours, N > 1, with --batched-backward 1: all-reduce the gradients by ranges of Gaussians while the "
                          "batched kernel computes the next range (0: one all-reduce after the step).  Measured at N = 2: "
@@ -757,6 +781,9 @@ def main():
         alg = {  # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x units per launch; R = last view's)
             "preprocess_fwd": (288.0 + twist_bytes) * args.P,
             "preprocess_bwd": (516.0 + 2 * twist_bytes) * args.P,
+            # view-batched forward (GaussianForwardBatch): parameters read once per step; per view the 20 bytes every
+            # Gaussian gets (radius, tile count, rect, depth key) and the 53 bytes of a visible one (record, depth, clamp bits)
+            "preprocess_fwd_batched": (236.0 + twist_bytes + 12.0) * args.P + len(cams) * 73.0 * args.P,
             # view-batched form (GaussianBackwardBatch): parameters read and gradients read-modify-written ONCE per step,
             # per view only the radius, the 48-byte moment record, conic + opacity, clamp bits and the view-space gradient
             "preprocess_bwd_batched": (252.0 + twist_bytes + 2 * (236.0 + twist_bytes)) * args.P + len(cams) * (4.0 + 48.0 + 24.0 + 1.0 + 12.0) * args.P,

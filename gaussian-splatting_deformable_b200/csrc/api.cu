@@ -304,6 +304,78 @@ int gsr_forward_preprocess_async(const gsr_view* view, int P, int M, const float
                                    means_out, radii, geom_ws, geom_bytes, nullptr, 0, stream_, false);
 }
 
+// ---- view-batched forward preprocess (preprocess.cu: preprocess_fwd_batched_kernel) ----------------------------------------
+size_t gsr_forward_batched_slots_bytes(int n_views) { return sizeof(FwdViewSlot) * (size_t)(n_views > 0 ? n_views : 0); }
+
+// Pure host function: slots_host[j] = camera constants of view j + pointers into its geometry workspace.
+int gsr_forward_batched_fill_slots(int n_views, const gsr_view_fwd* views, int P, int M, void* slots_host, size_t slots_bytes) {
+    if (n_views <= 0 || !views || !slots_host) return gsr_set_error_msg(-1, "batched preprocess: no views");
+    if (slots_bytes < gsr_forward_batched_slots_bytes(n_views)) return gsr_set_error_msg(-3, "batched preprocess: slot buffer too small");
+    const GeomLayout L = geom_layout(P);
+    FwdViewSlot* out = reinterpret_cast<FwdViewSlot*>(slots_host);
+    for (int j = 0; j < n_views; j++) {
+        const gsr_view_fwd& g = views[j];
+        if (!g.view || !g.radii || !g.geom_ws) return gsr_set_error_msg(-1, "batched preprocess: NULL pointer in a view");
+        if (g.view->prefiltered || g.view->debug) return gsr_set_error_msg(-1, "batched preprocess: prefiltered / debug views take the per-view path");
+        FwdViewSlot sl{};
+        if (int rc = fill_view(g.view, M, sl.v)) return rc;
+        if (sl.v.scale_modifier != views[0].view->scale_modifier || sl.v.sh_degree != views[0].view->sh_degree)
+            return gsr_set_error_msg(-1, "batched preprocess: the views of a batch must share scale_modifier and sh_degree");
+        char* ws = reinterpret_cast<char*>(g.geom_ws);
+        sl.radii = g.radii;
+        sl.depths = reinterpret_cast<float*>(ws + L.depths);
+        sl.tiles_touched = reinterpret_cast<uint32_t*>(ws + L.tiles);
+        sl.recs = reinterpret_cast<float4*>(ws + L.recs);
+        sl.clamped = reinterpret_cast<uint8_t*>(ws + L.clamped);
+        sl.block_sums = reinterpret_cast<uint32_t*>(ws + L.block_sums);
+        sl.depth_keys = reinterpret_cast<uint32_t*>(ws + L.dkeys);
+        sl.depth_state = reinterpret_cast<uint32_t*>(ws + L.dstate);
+        sl.rects = reinterpret_cast<uint2*>(ws + L.rects);
+        out[j] = sl;
+    }
+    return 0;
+}
+
+int gsr_forward_preprocess_batched(int n_views, const gsr_view_fwd* views, const void* slots_device, int P, int M, const float* means3D,
+                                   const float* scales, const float* rotations, const float* opacities, const float* shs,
+                                   const gsr_deform* deform, float* means_out, size_t geom_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P <= 0 || n_views <= 0) return 0;
+    if (!views || !slots_device || !means3D || !scales || !rotations || !opacities || !shs)
+        return gsr_set_error_msg(-1, "batched preprocess: required pointer is NULL");
+    if (M != 16 || (reinterpret_cast<uintptr_t>(shs) & 31))
+        return gsr_set_error_msg(-1, "batched preprocess: needs M = 16 SH coefficients and 32-byte aligned shs");
+    const GeomLayout L = geom_layout(P);
+    if (geom_bytes < L.bytes) return gsr_set_error_msg(-3, "geometry workspace too small");
+    PreprocessBatchArgs a{};
+    a.P = P; a.means = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities; a.shs = shs;
+    a.deform_mode = deform ? deform->mode : GSR_DEFORM_NONE;
+    if (a.deform_mode != GSR_DEFORM_NONE) {
+        if (!deform->S || !deform->theta || !means_out) return gsr_set_error_msg(-1, "deform: S, theta and means_out required");
+        if (a.deform_mode == GSR_DEFORM_RIGID_BODIES && !deform->body_id) return gsr_set_error_msg(-1, "deform: body_id required");
+        a.twist_S = deform->S; a.twist_theta = deform->theta; a.body_id = deform->body_id;
+    }
+    a.means_out = means_out;
+    a.scale_modifier = views[0].view->scale_modifier;
+    for (int j = 0; j < n_views; j++)      // every view's depth-sort state (it also holds num_rendered and the flags)
+        GSR_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(views[j].geom_ws) + L.dstate, 0, L.dstate_bytes, stream));
+    const FwdViewSlot* slots = reinterpret_cast<const FwdViewSlot*>(slots_device);
+    for (int j0 = 0; j0 < n_views; j0 += GSR_BATCH_MAX_VIEWS) {
+        a.n_views = n_views - j0 < GSR_BATCH_MAX_VIEWS ? n_views - j0 : GSR_BATCH_MAX_VIEWS;
+        if (int rc = gsr_launch_preprocess_fwd_batched(a, slots + j0, stream)) return rc;
+    }
+    return 0;
+}
+
+// num_rendered of a finished preprocess (either variant): device -> host, asynchronous (the sync is the caller's)
+int gsr_read_num_rendered(const void* geom_ws, int P, uint32_t* host_num_rendered, void* stream_) {
+    if (!geom_ws || !host_num_rendered) return gsr_set_error_msg(-1, "read_num_rendered: NULL pointer");
+    const GeomLayout L = geom_layout(P);
+    const uint32_t* st = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(geom_ws) + L.dstate) + GSR_DS_NUM_RENDERED;
+    GSR_CHECK(cudaMemcpyAsync(host_num_rendered, st, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    return 0;
+}
+
 static int forward_render_impl(const gsr_view* view, int P, uint32_t R, const int32_t* radii, void* geom_ws, void* binning_ws,
                                size_t binning_bytes, void* image_ws, float* out_color, int materialize_keys, void* stream_,
                                bool capacity_mode, uint32_t* host_status4) {

@@ -44,6 +44,22 @@ struct PreprocessArgs {
 };
 
 int gsr_launch_preprocess_fwd(const PreprocessArgs& a, const GsrView& v, cudaStream_t stream);
+
+// View-batched variant (preprocess.cu): up to GSR_BATCH_MAX_VIEWS views of the same parameters in one pass.
+#define GSR_BATCH_MAX_VIEWS 8
+struct FwdViewSlot {                  // per view, in device memory: camera constants + pointers into the view's workspaces
+    GsrView v;
+    int* radii; float* depths; uint32_t* tiles_touched; float4* recs; uint8_t* clamped;
+    uint32_t* block_sums; uint32_t* depth_keys; uint32_t* depth_state; uint2* rects;
+};
+struct PreprocessBatchArgs {
+    int P, n_views;
+    const float* means; const float* scales; const float* rotations; const float* opacities; const float* shs;
+    int deform_mode; const float* twist_S; const float* twist_theta; const int* body_id;
+    float* means_out;                // [P,3] deformed means (one copy for the batch)
+    float scale_modifier;
+};
+int gsr_launch_preprocess_fwd_batched(const PreprocessBatchArgs& a, const FwdViewSlot* d_slots, cudaStream_t stream);
 int gsr_launch_mark_visible(int P, const float* means, const GsrView& v, uint8_t* present, cudaStream_t stream);
 
 // ---- binning -------------------------------------------------------------
@@ -197,7 +213,6 @@ struct PreprocessBwdArgs {
 int gsr_launch_preprocess_bwd(const PreprocessBwdArgs& a, const GsrView& v, cudaStream_t stream);
 
 // View-batched variant (backward.cu): one pass over the Gaussians for up to GSR_BATCH_MAX_VIEWS views of the same parameters.
-#define GSR_BATCH_MAX_VIEWS 8
 struct BwdViewSlot {                  // per view, in device memory
     GsrView v;
     const int* radii; const uint8_t* clamped;

@@ -172,6 +172,113 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(PreprocessArgs a
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// View-batched forward preprocess: the views of a training step share the parameters, so one thread takes a Gaussian
+// through ALL of them - mean / twist / scale / rotation / opacity read once, SE3 and cov3D evaluated once, the 192-byte SH
+// record read once (when any view sees the Gaussian) - and writes each view's records into that view's workspace.
+// Same device functions, hence the same bits, as preprocess_fwd_kernel (tests compare the workspaces byte for byte).
+// Supported: scales + rotations, SH colours; any deform mode.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) preprocess_fwd_batched_kernel(PreprocessBatchArgs a, const FwdViewSlot* __restrict__ g_slots) {
+    __shared__ __align__(16) FwdViewSlot slots[GSR_BATCH_MAX_VIEWS];
+    __shared__ uint32_t s_red[GSR_BATCH_MAX_VIEWS][8][3];      // per view and warp: sum of tiles, min key, max key
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g_slots);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(slots);
+        const int words = a.n_views * (int)(sizeof(FwdViewSlot) / 4);
+        for (int k = threadIdx.x; k < words; k += 256) dst[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const bool in = idx < a.P;
+    float3 p = make_float3(0, 0, 0);
+    float3 s = make_float3(0, 0, 0);
+    float4 q = make_float4(0, 0, 0, 0);
+    float op = 0.0f;
+    if (in) {
+        p = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
+        float3 w = make_float3(0, 0, 0), tv = w;
+        float th = 0.0f;
+        if (a.deform_mode != GSR_DEFORM_NONE) {
+            const int t = (a.deform_mode == GSR_DEFORM_RIGID_BODIES) ? a.body_id[idx] : idx;
+            const float* S = a.twist_S + 6 * (size_t)t;
+            w = make_float3(S[0], S[1], S[2]); tv = make_float3(S[3], S[4], S[5]);
+            th = a.twist_theta[t];
+        }
+        s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+        q = ld_rec4(a.rotations, idx);
+        op = a.opacities[idx];
+        if (a.deform_mode != GSR_DEFORM_NONE) {
+            p = se3_apply(p, w, tv, th);
+            a.means_out[3 * idx] = p.x; a.means_out[3 * idx + 1] = p.y; a.means_out[3 * idx + 2] = p.z;
+        }
+    }
+    float cov6[6];
+    bool cov_done = false, sh_done = false;
+    float shv[48];
+    const float cut = (op > 0.0f) ? fmaxf(__logf(1.0f / (255.0f * op)) - 1e-3f, -80.0f) : 1.0f;
+    for (int j = 0; j < a.n_views; j++) {
+        const FwdViewSlot* sl = slots + j;
+        const GsrView& v = sl->v;
+        uint32_t tiles = 0, dkey = 0xffffffffu;
+        if (in) {
+            int radius = 0;
+            const float depth = xform_row(v.view, 2, p);
+            SplatGeom g;
+            g.ok = false;
+            if (depth > GSR_NEAR) {
+                if (!cov_done) { cov3d_exact(s, a.scale_modifier, q, cov6); cov_done = true; }
+                g = splat_geometry_exact(p, cov6, v);
+            }
+            if (g.ok) {
+                if (!sh_done) {
+                    const int need = (v.sh_degree + 1) * (v.sh_degree + 1) * 3;
+                    const float* base = a.shs + (size_t)idx * 48;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        if (8 * k < need) ld256_nc(base + 8 * k, shv + 8 * k);
+                    }
+                    sh_done = true;
+                }
+                auto fetch = [&](int k) -> V3 { return {shv[3 * k], shv[3 * k + 1], shv[3 * k + 2]}; };
+                V3 rgb = sh_to_rgb(v.sh_degree, p, v.campos, fetch);
+                const uint8_t cl = (rgb.x < 0 ? 1 : 0) | (rgb.y < 0 ? 2 : 0) | (rgb.z < 0 ? 4 : 0);
+                rgb.x = fmaxf(rgb.x, 0.0f); rgb.y = fmaxf(rgb.y, 0.0f); rgb.z = fmaxf(rgb.z, 0.0f);
+                radius = g.radius;
+                tiles = (g.rmax.y - g.rmin.y) * (g.rmax.x - g.rmin.x);
+                sl->depths[idx] = g.depth;
+                float4* r = sl->recs + 3 * (size_t)idx;
+                r[0] = make_float4(g.pix.x, g.pix.y, g.conic.x, g.conic.y);
+                r[1] = make_float4(g.conic.z, op, rgb.x, rgb.y);
+                r[2] = make_float4(rgb.z, cut, 0.0f, 0.0f);
+                sl->clamped[idx] = cl;
+            }
+            sl->radii[idx] = radius;
+            sl->tiles_touched[idx] = tiles;
+            sl->rects[idx] = g.ok ? make_uint2(g.rmin.x | (g.rmin.y << 16), g.rmax.x | (g.rmax.y << 16)) : make_uint2(0u, 0u);
+            dkey = tiles ? __float_as_uint(depth) : 0xffffffffu;
+            sl->depth_keys[idx] = dkey;
+        }
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, tiles);
+        const uint32_t kmn = __reduce_min_sync(0xffffffffu, dkey);
+        const uint32_t kmx = __reduce_max_sync(0xffffffffu, tiles ? dkey : 0u);
+        if ((threadIdx.x & 31) == 0) { s_red[j][threadIdx.x >> 5][0] = sum; s_red[j][threadIdx.x >> 5][1] = kmn; s_red[j][threadIdx.x >> 5][2] = kmx; }
+    }
+    __syncthreads();
+    if (threadIdx.x < a.n_views) {
+        const int j = threadIdx.x;
+        uint32_t t = 0, mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { t += s_red[j][k][0]; mn = min(mn, s_red[j][k][1]); mx = max(mx, s_red[j][k][2]); }
+        slots[j].block_sums[blockIdx.x] = t;
+        if (t) {
+            atomicAdd(slots[j].depth_state + GSR_DS_NUM_RENDERED, t);
+            atomicMax(slots[j].depth_state + GSR_DS_NOT_KMIN, ~mn);
+            atomicMax(slots[j].depth_state + GSR_DS_KMAX, mx);
+        }
+    }
+}
+
 // rasterizer_impl.cu:54-66 checkFrustum: present = (view-space z > 0.2).
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* means, GsrView v, uint8_t* present) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -184,6 +291,14 @@ int gsr_launch_preprocess_fwd(const PreprocessArgs& a, const GsrView& v, cudaStr
     if (a.P <= 0) return 0;
     { GsrProfScope prof_("preprocess_fwd", stream);
     preprocess_fwd_kernel<<<gsr_div_up(a.P, 256), 256, 0, stream>>>(a, v); }
+    GSR_CHECK_LAUNCH();
+    return 0;
+}
+
+int gsr_launch_preprocess_fwd_batched(const PreprocessBatchArgs& a, const FwdViewSlot* d_slots, cudaStream_t stream) {
+    if (a.P <= 0 || a.n_views <= 0) return 0;
+    { GsrProfScope prof_("preprocess_fwd_batched", stream);
+    preprocess_fwd_batched_kernel<<<gsr_div_up(a.P, 256), 256, 0, stream>>>(a, d_slots); }
     GSR_CHECK_LAUNCH();
     return 0;
 }

@@ -179,6 +179,69 @@ def _bucket(nbytes):
     return b
 
 
+class GaussianForwardBatch:
+    """The forward's per-Gaussian half (SE3 deform, projection, covariance, SH colour: preprocessCUDA) for SEVERAL views of
+    the same inputs in one pass (libgsr_b200: gsr_forward_preprocess_batched): every parameter record is read once per step
+    instead of once per view, SE3 and cov3D are evaluated once.  Each view's workspace receives byte for byte what the
+    per-view call writes, so everything downstream - and every result - is unchanged.
+
+        fwd = GaussianForwardBatch(settings_list, means3D=xyz, opacities=op, shs=shs, scales=s, rotations=r, se3_S=S, se3_theta=th)
+        color, radii = GaussianRasterizer(settings_list[i])(means3D=xyz, ..., prepared=fwd.prepared(i))
+
+    The rasterizer call must be given the same tensors.  Requirements (checked): SH colours with 16 coefficients (32-byte
+    aligned), scales + rotations, one scale_modifier / sh_degree for the batch, no prefiltered / debug settings.  The
+    workspaces are allocated on the current stream: join the streams the views ran on into it before the batch is dropped
+    (view_parallel.render_views does)."""
+
+    def __init__(self, settings_list, means3D, opacities, shs, scales, rotations, se3_S=None, se3_theta=None, body_id=None):
+        lib = _rt.load()
+        if not means3D.is_cuda:
+            raise _rt.GsrError("libgsr_b200 runs on CUDA tensors only (no CPU fallback)")
+        dev = means3D.device
+        P = int(means3D.shape[0])
+        n = len(settings_list)
+        if n == 0 or P == 0:
+            raise _rt.GsrError("GaussianForwardBatch: needs at least one view and one Gaussian")
+        if (se3_S is None) != (se3_theta is None):
+            raise Exception('Please provide both se3_S and se3_theta, or neither!')
+        self.tensors = tuple(_c(t) for t in (means3D, opacities, shs, scales, rotations))
+        means_c, opac_c, sh_c, scales_c, rots_c = self.tensors
+        if sh_c is None or sh_c.dim() != 3 or int(sh_c.shape[1]) != 16 or sh_c.data_ptr() & 31:
+            raise _rt.GsrError("GaussianForwardBatch needs SH colours [P, 16, 3] in a 32-byte aligned tensor")
+        self.deform = _Deform(_c(se3_S), _c(se3_theta), body_id.to(torch.int32).contiguous() if body_id is not None else None)
+        self.P, self.M, self.device = P, 16, dev
+        self.settings = list(settings_list)
+        self.views = [_rt.make_view(rs) for rs in self.settings]
+        with torch.cuda.device(dev):
+            stream = _rt.stream_ptr(dev)
+            gbytes = lib.gsr_geom_bytes(P)
+            self.geoms = [torch.empty(gbytes, dtype=torch.uint8, device=dev) for _ in range(n)]
+            self.radii = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(n)]
+            self.means_def = torch.empty((P, 3), dtype=torch.float32, device=dev) if self.deform.mode else None
+            arr = (_rt.gsr_view_fwd * n)()
+            for j in range(n):
+                arr[j].view = ctypes.pointer(self.views[j])
+                arr[j].radii = self.radii[j].data_ptr()
+                arr[j].geom_ws = self.geoms[j].data_ptr()
+            nbytes = lib.gsr_forward_batched_slots_bytes(n)
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            _rt.check(lib.gsr_forward_batched_fill_slots(n, arr, P, 16, host.data_ptr(), nbytes))
+            slots = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            slots.copy_(host, non_blocking=True)
+            _rt.check(lib.gsr_forward_preprocess_batched(
+                n, arr, _rt.ptr(slots), P, 16, _rt.ptr(means_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c), _rt.ptr(sh_c),
+                self.deform.c_struct(), _rt.ptr(self.means_def), gbytes, stream))
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(dev))
+
+    def __len__(self):
+        return len(self.views)
+
+    def prepared(self, i):
+        """The handle to pass as `prepared=` to the rasterizer call of view i."""
+        return (self, int(i))
+
+
 class GaussianBackwardBatch:
     """`accumulate_grads=` target that also BATCHES the per-Gaussian half of the backward over the views of a step.
 
@@ -339,12 +402,28 @@ class _RasterizeGaussians(torch.autograd.Function):
                          body_id.to(torch.int32).contiguous() if body_id is not None else None)
 
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-        radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        means_def = torch.empty((P, 3), dtype=torch.float32, device=dev) if deform.mode else None
-        view = _rt.make_view(raster_settings)
+        prep = aux.get("prepared") if aux else None
+        if prep is not None:
+            # the per-Gaussian half was done for the whole batch of views (GaussianForwardBatch): take its results
+            fb, vi = prep
+            same = (means3D_c, opac_c, sh_c, scales_c, rots_c)
+            if (fb.P != P or fb.device != dev or any(a is None or a.data_ptr() != b.data_ptr() for a, b in zip(same, fb.tensors)) or
+                    fb.deform.mode != deform.mode or (deform.mode and (fb.deform.S.data_ptr() != deform.S.data_ptr() or
+                                                                       fb.deform.theta.data_ptr() != deform.theta.data_ptr()))):
+                raise _rt.GsrError("prepared=: the rasterizer call must be given the tensors the GaussianForwardBatch was built from")
+            if (colors_c is not None and colors_c.numel()) or (cov_c is not None and cov_c.numel()):
+                raise _rt.GsrError("prepared=: precomputed colours / covariances take the per-view path")
+            if fb.settings[vi] is not raster_settings and tuple(fb.settings[vi][:4]) != tuple(raster_settings[:4]):
+                raise _rt.GsrError("prepared=: view %d of the batch was prepared for other raster settings" % vi)
+            radii, means_def, view = fb.radii[vi], fb.means_def, fb.views[vi]
+            torch.cuda.current_stream(dev).wait_event(fb.event)
+        else:
+            radii = torch.empty((P,), dtype=torch.int32, device=dev)
+            means_def = torch.empty((P, 3), dtype=torch.float32, device=dev) if deform.mode else None
+            view = _rt.make_view(raster_settings)
         with torch.cuda.device(dev):
             stream = _rt.stream_ptr(dev)
-            geom = torch.empty(lib.gsr_geom_bytes(P), dtype=torch.uint8, device=dev)
+            geom = fb.geoms[vi] if prep is not None else torch.empty(lib.gsr_geom_bytes(P), dtype=torch.uint8, device=dev)
             img = torch.empty(lib.gsr_image_bytes(W, H), dtype=torch.uint8, device=dev)
             mailbox = _rt.pinned_u32(dev)
             num_rendered = 0
@@ -355,10 +434,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _check_pending(key, blocking=False)
                 cap = _capacity.get(key)
             if cap:
-                _rt.check(lib.gsr_forward_preprocess_async(
-                    view, P, M, _rt.ptr(means3D_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c),
-                    _rt.ptr(sh_c), _rt.ptr(cov_c), _rt.ptr(colors_c), dstruct, _rt.ptr(means_def),
-                    _rt.ptr(radii), _rt.ptr(geom), geom.numel(), stream))
+                if prep is None:
+                    _rt.check(lib.gsr_forward_preprocess_async(
+                        view, P, M, _rt.ptr(means3D_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c),
+                        _rt.ptr(sh_c), _rt.ptr(cov_c), _rt.ptr(colors_c), dstruct, _rt.ptr(means_def),
+                        _rt.ptr(radii), _rt.ptr(geom), geom.numel(), stream))
                 nbytes = lib.gsr_binning_bytes(cap, W, H)
                 binning = torch.empty(_bucket(nbytes), dtype=torch.uint8, device=dev)
                 status = _rt.pinned_status(dev)
@@ -368,6 +448,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                 ev.record(torch.cuda.current_stream(dev))
                 _pending.setdefault(key, []).append((ev, status, cap))
                 num_rendered = cap
+            elif P != 0 and prep is not None:
+                _rt.check(lib.gsr_read_num_rendered(_rt.ptr(geom), P, mailbox.data_ptr(), stream))
+                torch.cuda.current_stream(dev).synchronize()
+                num_rendered = int(mailbox.item()) & 0xFFFFFFFF
             elif P != 0:
                 _rt.check(lib.gsr_forward_preprocess(
                     view, P, M, _rt.ptr(means3D_c), _rt.ptr(scales_c), _rt.ptr(rots_c), _rt.ptr(opac_c),
@@ -585,7 +669,7 @@ class GaussianRasterizer(nn.Module):
         return visible
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, *, se3_S=None, se3_theta=None, body_id=None, accumulate_grads=None):
+                cov3D_precomp=None, *, se3_S=None, se3_theta=None, body_id=None, accumulate_grads=None, prepared=None):
         raster_settings = self.raster_settings
 
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -600,7 +684,7 @@ class GaussianRasterizer(nn.Module):
         if body_id is not None and se3_S is None:
             raise Exception('body_id needs se3_S/se3_theta (one twist per rigid body)!')
 
-        aux = {}
+        aux = {"prepared": prepared} if prepared is not None else {}
         out = rasterize_gaussians(
             means3D,
             means2D,

@@ -72,6 +72,11 @@ class gsr_view_grads(ctypes.Structure):
                 ("grad_ws", ctypes.c_void_p), ("dL_dmeans2D", ctypes.c_void_p)]
 
 
+class gsr_view_fwd(ctypes.Structure):
+    """include/gsr_b200.h: one view of a view-batched forward preprocess."""
+    _fields_ = [("view", ctypes.POINTER(gsr_view)), ("radii", ctypes.c_void_p), ("geom_ws", ctypes.c_void_p)]
+
+
 GEMM_RELU_SPLIT, GEMM_SPLIT, GEMM_PLAIN, GEMM_ATOMIC = 0, 1, 2, 3
 DEFORM_NONE, DEFORM_PER_GAUSSIAN, DEFORM_RIGID_BODIES = 0, 1, 2
 
@@ -103,6 +108,11 @@ _SIGNATURES = {
                                     _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(gsr_deform), _P,
                                     _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
+    "gsr_forward_batched_slots_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "gsr_forward_batched_fill_slots": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(gsr_view_fwd), ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t]),
+    "gsr_forward_preprocess_batched": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(gsr_view_fwd), _P, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P, _P,
+                                                       ctypes.POINTER(gsr_deform), _P, ctypes.c_size_t, _P]),
+    "gsr_read_num_rendered": (ctypes.c_int, [_P, ctypes.c_int, _P, _P]),
     "gsr_backward_blend": (ctypes.c_int, [ctypes.POINTER(gsr_view), ctypes.c_int, ctypes.c_uint32, _P, _P, _P, _P, _P, _P]),
     "gsr_backward_batched_slots_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "gsr_backward_batched_fill_slots": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(gsr_view_grads), ctypes.c_int, ctypes.c_int, _P, ctypes.c_size_t]),

@@ -182,6 +182,26 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t num_rendered,
 int gsr_debug_blend_stats(const gsr_view* view, int P, uint32_t num_rendered, const void* geom_ws,
                           const void* binning_ws, const void* image_ws, unsigned long long* out8, void* stream);
 
+/* ---- view-batched forward preprocess ----------------------------------------------------------------------------------
+ * gsr_forward_preprocess for up to all views of a step at once (they share the parameters): every parameter record is read
+ * once, SE3 and cov3D are evaluated once, and each view's records go to that view's geometry workspace - byte for byte
+ * what gsr_forward_preprocess writes there.  Then gsr_forward_render / gsr_forward_render_capacity per view as usual.
+ * Requires scales + rotations, SH colours with M = 16 and 32-byte aligned shs, one scale_modifier / sh_degree for the
+ * batch, no prefiltered / debug views.  means_out ([P,3], deform modes) is one copy for the batch.  Slots as for the
+ * batched backward: fill on the host (gsr_forward_batched_fill_slots), copy to the device in stream order.
+ * gsr_read_num_rendered: asynchronous read-back of a view's num_rendered (the exact-size path needs it on the host). */
+typedef struct gsr_view_fwd {
+    const gsr_view* view;
+    int32_t* radii;            /* [P] out */
+    void* geom_ws;             /* gsr_geom_bytes(P) */
+} gsr_view_fwd;
+size_t gsr_forward_batched_slots_bytes(int n_views);
+int gsr_forward_batched_fill_slots(int n_views, const gsr_view_fwd* views, int P, int M, void* slots_host, size_t slots_bytes);
+int gsr_forward_preprocess_batched(int n_views, const gsr_view_fwd* views, const void* slots_device, int P, int M,
+                                   const float* means3D, const float* scales, const float* rotations, const float* opacities,
+                                   const float* shs, const gsr_deform* deform, float* means_out, size_t geom_bytes, void* stream);
+int gsr_read_num_rendered(const void* geom_ws, int P, uint32_t* host_num_rendered, void* stream);
+
 /* ---- view-batched backward (training steps that render several views of the SAME parameters) -----------------------
  * gsr_backward = renderCUDA backward + the per-Gaussian chain rule (computeCov2DCUDA / preprocessCUDA backward,
  * cuda_rasterizer/backward.cu:144-396, + the SE3 autograd of scene/rigid_body.py).  The second half reads every parameter

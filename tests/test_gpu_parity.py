@@ -497,6 +497,67 @@ def test_batched_backward_matches_per_view_backward(mode):
         assert min(rel_to_max(g, h) for h in vb) <= 2e-5
 
 
+@pytest.mark.parametrize("mode", ["per_gaussian", "rigid_bodies", "none"])
+@pytest.mark.parametrize("sync_free", [False, True])
+def test_batched_forward_preprocess_is_bit_identical(mode, sync_free):
+    """GaussianForwardBatch: preprocess of all views of a step in one pass.  Every view's image, radii, num_rendered and
+    geometry records must equal the per-view call's bit for bit (same device functions), and the backward must not notice."""
+    import synthetic
+    import gsr_runtime as rt
+    import diff_gaussian_rasterization as dgr
+    from _gpu_util import make_view_settings, rel_to_max
+    from diff_gaussian_rasterization import GaussianRasterizer, GaussianForwardBatch
+    P, W, H, V = 40003, 400, 240, 10         # 10 views: two launches of the batched kernel (8 + 2)
+    sc, _, _ = make_view_settings(P, W, H, scale_mult=1.5)
+    B = 16
+    extra = {}
+    if mode == "rigid_bodies":
+        S, th = synthetic.make_twists(B, device="cuda")
+        extra = dict(se3_S=S, se3_theta=th, body_id=(torch.arange(P, device="cuda") % B).to(torch.int32))
+    elif mode == "per_gaussian":
+        S, th = synthetic.make_twists(P, device="cuda")
+        extra = dict(se3_S=S, se3_theta=th)
+    bg = torch.tensor([0.2, 0.1, 0.3], device="cuda")
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    settings = [synthetic.raster_settings(synthetic.make_camera(k, V, W, H, device="cuda"), bg) for k in range(V)]
+
+    def run(batched):
+        leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+        ex = dict(extra)
+        for k in ("se3_S", "se3_theta"):
+            if k in ex:
+                ex[k] = ex[k].clone().requires_grad_(True)
+        fwd = GaussianForwardBatch(settings, **leaves, **ex) if batched else None
+        outs = []
+        for k in range(V):
+            ras = GaussianRasterizer(settings[k])
+            m2d = torch.zeros(P, 3, device="cuda", requires_grad=True)
+            color, radii = ras(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
+                               scales=leaves["scales"], rotations=leaves["rotations"], **ex,
+                               prepared=fwd.prepared(k) if batched else None)
+            color.backward(grad)
+            outs.append((color.detach().clone(), radii.clone(), None if ras.deformed_means is None else ras.deformed_means.clone()))
+        torch.cuda.synchronize()
+        grads = {k: v.grad.clone() for k, v in leaves.items()}
+        grads.update({k: ex[k].grad.clone() for k in ("se3_S", "se3_theta") if k in ex})
+        return outs, grads
+    dgr.set_sync_free(sync_free)
+    try:
+        if sync_free:
+            run(False)                       # the first forward of a configuration measures num_rendered
+        (oa, ga), (ob, gb) = run(True), run(False)
+        dgr.check_sync_free()
+    finally:
+        dgr.set_sync_free(False)
+    for k in range(V):
+        assert torch.equal(oa[k][1], ob[k][1]), ("radii", k)
+        assert torch.equal(oa[k][0], ob[k][0]), ("image", k)
+        if oa[k][2] is not None:
+            assert torch.equal(oa[k][2], ob[k][2]), ("deformed means", k)
+    for k in ga:
+        assert rel_to_max(ga[k], gb[k]) <= 1e-5, (k, rel_to_max(ga[k], gb[k]))
+
+
 def test_packed_expf_is_cudas_expf_on_every_float():
     """The blend kernels evaluate expf on packed FP32x2 values (csrc/f32x2.cuh) with CUDA's own algorithm restated;
     it must be bit-identical to expf (what forward.cu:342 / backward.cu:472 compile to) on the whole range
