@@ -273,6 +273,11 @@ class GaussianBackwardBatch:
     def __len__(self):
         return len(self._items)
 
+    def __del__(self):
+        if getattr(self, "_items", None):
+            warnings.warn("GaussianBackwardBatch dropped with %d view(s) pending: flush() was never called, their per-Gaussian "
+                          "gradients were not computed" % len(self._items))
+
     # dict protocol used by the forward's argument checks
     def items(self):
         return self.targets.items()
