@@ -218,7 +218,7 @@ __device__ void cta_lsd_pass(const uint2* src, uint2* dst, uint32_t n, int which
 }
 
 // Fast path of a segment that fits shared memory, pairs held in registers (EPT per thread).  Returns false (nothing
-// written) when a sub-bucket is too large for all-pairs ranking; *bits_out = varying key bits of the segment.
+// written) when a sub-bucket is too large for all-pairs ranking; *bits_out = key bits the LSD path has to sort on.
 template <int EPT>
 __device__ __forceinline__ bool local_sort_fast(LocalSmem& s, const uint2* __restrict__ A, uint32_t n, uint32_t lo,
                                                 const uint2* __restrict__ rects, uint32_t* __restrict__ order,
@@ -245,7 +245,7 @@ __device__ __forceinline__ bool local_sort_fast(LocalSmem& s, const uint2* __res
 #pragma unroll
     for (int w = 0; w < 8; w++) { kmn = min(kmn, s.red[w]); kmx = max(kmx, s.red[8 + w]); }
     const int bits = key_bits(kmx - kmn);
-    *bits_out = bits;
+    *bits_out = key_bits(kmx ^ kmn);                                   // highest bit in which two keys of the segment can differ
     const int s2 = bits > DS_NSB_BITS ? bits - DS_NSB_BITS : 0;
     uint32_t r[EPT];                                                   // arrival rank inside the sub-bucket
 #pragma unroll
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(DS_THREADS, 4) ds_local_sort_kernel(uint2* pai
         __syncthreads();
 #pragma unroll
         for (int w = 0; w < 8; w++) { kmn = min(kmn, s.red[w]); kmx = max(kmx, s.red[8 + w]); }
-        bits = key_bits(kmx - kmn);
+        bits = key_bits(kmx ^ kmn);       // NOT the range: 0x..ff and 0x..100 are 1 apart and differ in bit 8
     }
     // ---- slow path: stable LSD radix sort of the segment in global memory, by this CTA alone ----
     __syncthreads();

@@ -358,6 +358,11 @@ def test_depth_order_is_the_stable_sort_by_depth_bits():
     cases.append(("all equal", bits(torch.full((70000,), 2.5)), "slow"))
     cases.append(("all equal, small", bits(torch.full((3000,), 2.5)), "slow"))
     cases.append(("two values", bits(torch.tensor([1.0, 2.0]).repeat(40)), None))
+    # neighbouring keys on either side of a byte / 16-bit boundary: 1 apart, yet they differ in bit 8 / bit 16
+    for lo_key in (0x404000FF, 0x4040FFFF, 0x40FFFFFF):
+        k2 = torch.tensor([lo_key + 1, lo_key], dtype=torch.int64).repeat(5000).to(torch.int32)
+        cases.append(("straddle %x" % lo_key, k2, "slow"))
+        cases.append(("straddle %x, small" % lo_key, k2[:400], "slow"))
     d = torch.randn((600000,), generator=g).abs() * 0.05 + 4.0   # peaked density
     cases.append(("peaked", bits(d), None))
     cases.append(("raw bits", torch.randint(0, 2 ** 31 - 1, (500000,), generator=g, dtype=torch.int32), None))
