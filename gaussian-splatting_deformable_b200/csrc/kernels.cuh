@@ -108,7 +108,9 @@ struct GsrTileBinPlan {
     int feasible;          // 0: fall back to the radix path
     int chunks;            // rows of the matrix (<= GSR_SWEEP_MAX_CHUNKS); a chunk is ceil(n_emit / chunks) Gaussians
     int stripes, groups, stripe_tiles, num_tiles;
+    int scatter_warps, scatter_groups;   // tile_scatter: stripes spread evenly over as few CTAs per chunk as shared memory allows
 };
+#define GSR_SCATTER_MAX_WARPS 24          // 768 threads
 GsrTileBinPlan gsr_make_tile_bin_plan(int grid_x, int grid_y);
 size_t gsr_tile_matrix_bytes(int grid_x, int grid_y);
 // srec[i] = (id, rect lo, rect hi, 0) of the i-th Gaussian in depth order (written by the depth sort); matrix[chunks][tiles] scratch;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(1024) tile_count_kernel(const uint32_t* __rest
 // thus only ever visits the Gaussians that reach its stripe (1 in 9 at 1080p) instead of scanning
 // the whole chunk, and the rect arrives by one broadcast LDS.128 instead of three shuffles.
 #define GSR_SCATTER_SUB 1024
-__global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(const uint32_t* __restrict__ n_emit_p,
+__global__ void __launch_bounds__(32 * GSR_SCATTER_MAX_WARPS) tile_scatter_kernel(const uint32_t* __restrict__ n_emit_p,
                                                                            const uint4* __restrict__ srec, GsrTileBinPlan pl,
                                                                            int grid_x, int grid_y,
                                                                            const uint32_t* __restrict__ matrix,
@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(cons
     extern __shared__ uint32_t s_cnt_all[];                                   // [warps][stripe_tiles]
     __shared__ uint4 s_rec[GSR_SCATTER_SUB];
     if (overflow && *overflow) return;                                        // capacity mode: the list does not fit
-    __shared__ uint32_t s_bits[GSR_SWEEP_WARPS][GSR_SCATTER_SUB / 32];
+    __shared__ uint32_t s_bits[GSR_SCATTER_MAX_WARPS][GSR_SCATTER_SUB / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int stripe = blockIdx.y * GSR_SWEEP_WARPS + warp;
+    const int NWARPS = pl.scatter_warps;                                       // = blockDim.x / 32
+    const int stripe = blockIdx.y * NWARPS + warp;
     const bool live = stripe < pl.stripes;
     uint32_t* cnt = s_cnt_all + warp * pl.stripe_tiles;
     const int row0 = stripe * ROWS;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(cons
     if (g_begin >= g_end) return;
     const uint32_t* mrow = matrix + (size_t)chunk * pl.num_tiles + tile0;
     for (int i = lane; i < ntile; i += 32) cnt[i] = tile_base[tile0 + i] + mrow[i];
-    const int grow0 = blockIdx.y * GSR_SWEEP_WARPS * ROWS;                    // first tile row of this CTA's stripes
+    const int grow0 = blockIdx.y * NWARPS * ROWS;                             // first tile row of this CTA's stripes
     const int lrow = lane / CW, lcol = lane % CW;
     uint32_t* const cnt_lane = cnt + (lrow - row0) * grid_x + lcol;
 
@@ -176,15 +177,14 @@ __global__ void __launch_bounds__(32 * GSR_SWEEP_WARPS) tile_scatter_kernel(cons
         const uint32_t sn = min((uint32_t)GSR_SCATTER_SUB, g_end - sb);
         __syncthreads();                                                      // previous sub-batch fully consumed
         // (1) stage + bitmaps: warp w takes Gaussians w*32 + lane, + 256, ...
-        for (uint32_t i0 = warp * 32; i0 < sn; i0 += 32 * GSR_SWEEP_WARPS) {
+        for (uint32_t i0 = warp * 32; i0 < sn; i0 += 32 * NWARPS) {
             const uint32_t i = i0 + lane;
             uint4 rec = make_uint4(0, 0, 0, 0);
             if (i < sn) rec = srec[sb + i];
             s_rec[i0 + lane] = rec;
             const int y0 = rec.y >> 16, y1 = rec.z >> 16;
             const bool any = (rec.z & 0xffffu) > (rec.y & 0xffffu);
-#pragma unroll
-            for (int s = 0; s < GSR_SWEEP_WARPS; s++) {
+            for (int s = 0; s < NWARPS; s++) {
                 const int r0 = grow0 + s * ROWS;
                 const unsigned m = __ballot_sync(FULL, any && y0 < r0 + ROWS && y1 > r0);
                 if (lane == 0) s_bits[s][i0 >> 5] = m;
@@ -360,6 +360,16 @@ GsrTileBinPlan gsr_make_tile_bin_plan(int grid_x, int grid_y) {
     pl.stripes = (grid_y + GSR_SWEEP_ROWS - 1) / GSR_SWEEP_ROWS;
     pl.groups = (pl.stripes + GSR_SWEEP_WARPS - 1) / GSR_SWEEP_WARPS;
     pl.stripe_tiles = GSR_SWEEP_ROWS * grid_x;
+    // tile_scatter: every CTA of a chunk stages the chunk's records, and the stripes are spread EVENLY over the CTAs of a
+    // chunk (1080p, 17 stripes: 8 + 8 + 1 warps - the third CTA with one live warp - 83 us; 6 + 6 + 5: 77 us;
+    // 9 + 8: 74 us; one CTA of 17 warps: 87 us).  At most 12 warps per CTA unless GSR_SCATTER_WARPS says otherwise.
+    static const int w_env = env_int2("GSR_SCATTER_WARPS", 12);
+    int wmax = (160 * 1024) / (pl.stripe_tiles * (int)sizeof(uint32_t));
+    if (wmax > GSR_SCATTER_MAX_WARPS) wmax = GSR_SCATTER_MAX_WARPS;
+    if (w_env > 0 && w_env < wmax) wmax = w_env;
+    if (wmax < 1) wmax = 1;
+    pl.scatter_groups = (pl.stripes + wmax - 1) / wmax;
+    pl.scatter_warps = (pl.stripes + pl.scatter_groups - 1) / pl.scatter_groups;
     return pl;
 }
 
@@ -407,12 +417,13 @@ int gsr_launch_tile_binning(int P, const uint32_t* n_emit, const uint4* srec,
     if (scatter_v == 2) {
         static bool sattr_done = false;
         if (!sattr_done) {
-            GSR_CHECK(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           GSR_SWEEP_WARPS * GSR_SWEEP_MAX_STRIPE_TILES * (int)sizeof(uint32_t)));
+            GSR_CHECK(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
             sattr_done = true;
         }
         GsrProfScope prof_("tile_scatter", stream);
-        tile_scatter_kernel<<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list, overflow);
+        const dim3 sgrid(pl.chunks, pl.scatter_groups, 1);
+        const size_t ssmem = (size_t)pl.scatter_warps * pl.stripe_tiles * sizeof(uint32_t);
+        tile_scatter_kernel<<<sgrid, 32 * pl.scatter_warps, ssmem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list, overflow);
     } else {
         GsrProfScope prof_("tile_sweep_scatter", stream);
         tile_sweep_kernel<true><<<grid, 32 * GSR_SWEEP_WARPS, smem, stream>>>(n_emit, srec, pl, grid_x, grid_y, matrix, tile_base, point_list, overflow);

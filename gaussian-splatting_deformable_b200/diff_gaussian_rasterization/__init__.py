@@ -204,6 +204,11 @@ class GaussianForwardBatch:
             raise _rt.GsrError("GaussianForwardBatch: needs at least one view and one Gaussian")
         if (se3_S is None) != (se3_theta is None):
             raise Exception('Please provide both se3_S and se3_theta, or neither!')
+        for name, t in (("means3D", means3D), ("opacities", opacities), ("shs", shs), ("scales", scales), ("rotations", rotations),
+                        ("se3_S", se3_S), ("se3_theta", se3_theta)):
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                # a converted copy would not be the tensor the rasterizer call is given later
+                raise _rt.GsrError("GaussianForwardBatch: %s must be a contiguous float32 tensor" % name)
         self.tensors = tuple(_c(t) for t in (means3D, opacities, shs, scales, rotations))
         means_c, opac_c, sh_c, scales_c, rots_c = self.tensors
         if sh_c is None or sh_c.dim() != 3 or int(sh_c.shape[1]) != 16 or sh_c.data_ptr() & 31:
