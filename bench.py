@@ -872,6 +872,10 @@ def main():
                    "name": args.config,
                    "P": args.P, "width": args.W, "height": args.H, "views_per_gpu_per_step": args.views, "streams": args.streams,
                    "sync_free_forward": bool(args.sync_free) if args.impl == "ours" else False,
+                   # the views of a step share the parameters: their per-Gaussian work (preprocess; the chain rule behind the
+                   # blend backward) runs once per step for all views.  --batched-forward 0 --batched-backward 0: once per view
+                   "view_batched": ({"forward_preprocess": bool(args.batched_forward), "gaussian_backward": bool(args.batched_backward)}
+                                    if args.impl == "ours" else None),
                    "parallelism": "view-parallel x%d, per-Gaussian grad all-reduce (NCCL)" % world if world > 1 else "single GPU",
                    "l2": "inputs (264 MB params+twists, 85 MB geometry state, 190 MB keys) exceed the 126 MB L2 every view"},
         "clocks": clocks,
