@@ -174,7 +174,8 @@ def step_ours(leaves, cams, bg, grad, args):
     # the per-Gaussian half of the backward runs once for all views of the step (--batched-backward 0: once per view)
     batch = None
     overlap = False
-    if getattr(args, "batched_backward", 1):
+    many = len(cams) > 1                  # one view per step: nothing to share, the per-view kernels are the faster ones
+    if getattr(args, "batched_backward", 1) and many:
         # N > 1: the batched kernel runs over 4 ranges of Gaussians and each range's all-reduce starts as soon as the range
         # is enqueued (NCCL's stream), so only the last range's collective is exposed
         world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,7 +189,7 @@ def step_ours(leaves, cams, bg, grad, args):
     settings = [synthetic.raster_settings(cam, bg, sh_degree=3) for cam in cams]
     # the per-Gaussian half of the forward once for all views of the step (--batched-forward 0: once per view)
     fwd = None
-    if getattr(args, "batched_forward", 1):
+    if getattr(args, "batched_forward", 1) and many:
         from diff_gaussian_rasterization import GaussianForwardBatch
         extra = {} if no_deform else dict(se3_S=leaves["S"], se3_theta=leaves["theta"], body_id=args.body_id)
         fwd = GaussianForwardBatch(settings, means3D=leaves["means3D"], opacities=leaves["opacities"], shs=leaves["shs"],
@@ -874,7 +875,8 @@ def main():
                    "sync_free_forward": bool(args.sync_free) if args.impl == "ours" else False,
                    # the views of a step share the parameters: their per-Gaussian work (preprocess; the chain rule behind the
                    # blend backward) runs once per step for all views.  --batched-forward 0 --batched-backward 0: once per view
-                   "view_batched": ({"forward_preprocess": bool(args.batched_forward), "gaussian_backward": bool(args.batched_backward)}
+                   "view_batched": ({"forward_preprocess": bool(args.batched_forward) and args.views > 1,
+                                     "gaussian_backward": bool(args.batched_backward) and args.views > 1}
                                     if args.impl == "ours" else None),
                    "parallelism": "view-parallel x%d, per-Gaussian grad all-reduce (NCCL)" % world if world > 1 else "single GPU",
                    "l2": "inputs (264 MB params+twists, 85 MB geometry state, 190 MB keys) exceed the 126 MB L2 every view"},

@@ -122,6 +122,22 @@ def test_no_cpu_fallback():
         distCUDA2(torch.zeros(8, 3))
     with pytest.raises(rt.GsrError, match="no CPU fallback"):
         rigid_body.exp_se3(torch.zeros(2, 6), torch.ones(2))
+    with pytest.raises(rt.GsrError, match="no CPU fallback"):       # the view-batched preprocess has no CPU path either
+        dgr.GaussianForwardBatch([_settings()], means3D=m, opacities=torch.zeros(4, 1), shs=torch.zeros(4, 16, 3),
+                                 scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+
+
+def test_view_batch_objects_host_logic():
+    """GaussianBackwardBatch: dict-like target set, flush of an empty batch is a no-op, chunk count sanitised."""
+    t = {"means3D": torch.zeros(4, 3)}
+    b = dgr.GaussianBackwardBatch(t, chunks=0)
+    assert len(b) == 0 and b.chunks == 1 and dict(b.items()) == t and b.viewspace_grads == []
+    b.flush()                                                        # nothing pending: must not touch the library
+    assert len(b) == 0
+    # the batched entry points are part of the C ABI the header declares
+    for name in ("gsr_backward_blend", "gsr_backward_batched_fill_slots", "gsr_backward_gaussians_batched",
+                 "gsr_forward_batched_fill_slots", "gsr_forward_preprocess_batched", "gsr_read_num_rendered", "gsr_depth_order"):
+        assert name in rt.EXPORTED_SYMBOLS
 
 
 def test_product_does_not_import_the_oracle():
