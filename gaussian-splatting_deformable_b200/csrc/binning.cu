@@ -63,7 +63,7 @@ int gsr_launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* d
 // Binning order.  The reference sorts R (tile | depth) 64-bit keys (45 significant
 // bits -> 6 digit passes over 12-byte pairs).  All duplicates of one Gaussian share
 // the depth digits, so the same permutation is obtained much cheaper:
-//   1. stable-sort the P Gaussians by depth bits once (4 passes over 8-byte pairs;
+//   1. order the P Gaussians by (depth bits, index) once (depth_sort.cu;
 //      Gaussians that emit nothing carry key 0xffffffff and sink to the end),
 //   2. emit the duplicates walking the Gaussians in that order,
 //   3. stable-sort the duplicates by TILE ID only (tile_bits <= 16 -> 2 passes over

@@ -5,7 +5,7 @@
 // identifyTileRanges) - and produces the identical point_list / ranges - but never
 // materialises or sorts the R (tile, Gaussian) duplicates:
 //
-//   the P Gaussians are already in depth order (4-pass onesweep on 8-byte pairs), so the
+//   the P Gaussians are already in depth order (depth_sort.cu), so the
 //   reference's final order is "for every tile, the Gaussians that cover it, in depth
 //   order" = a STABLE partition of the duplicate stream by tile id.  A stable partition
 //   is a counting sort:

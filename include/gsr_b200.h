@@ -129,7 +129,7 @@ int gsr_forward_preprocess(const gsr_view* view, int P, int M,
                            int32_t* radii, void* geom_ws, size_t geom_bytes,
                            uint32_t* host_num_rendered, int debug_dump_cov3D, void* stream);
 
-/* Stage 2: depth-order the Gaussians (onesweep), then one stable counting sort of their tile duplicates into the
+/* Stage 2: depth-order the Gaussians (two-level bucket sort, csrc/depth_sort.cu), then one stable counting sort of their tile duplicates into the
  * per-tile lists (= the reference's sorted point_list and ranges; radix fallback: duplicate + onesweep by tile id +
  * tile ranges), then blend.  out_color[3,H,W].  materialize_keys != 0 also
  * writes the reference-format sorted 64-bit keys (tile << 32 | depth bits) for parity checks. */
