@@ -628,6 +628,27 @@ def main():
     views_total = args.views * world
     value = args.P * views_total / (ms_per_step * 1e-3)
 
+    # N > 1: the step's one collective, timed on its own (ranks aligned by a barrier first): it is not overlapped with the
+    # views, so this is its exposed time per step; what the step loses beyond it is rank skew (different cameras per rank)
+    collective = None
+    if world > 1 and args.impl == "ours":
+        fb = flat_buffer(leaves)
+        for _ in range(2):
+            fb.all_reduce()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            fb.all_reduce()
+        c1.record()
+        torch.cuda.synchronize()
+        cms = torch.tensor([c0.elapsed_time(c1) / 5.0], device=dev)
+        torch.distributed.all_reduce(cms, op=torch.distributed.ReduceOp.MAX)
+        nbytes = fb.flat.numel() * 4
+        collective = {"op": "all-reduce (NCCL) of the flat fp32 gradient buffer, once per step, after the views",
+                      "bytes": nbytes, "ms": round(float(cms.item()), 4), "exposed_ms_per_step": round(float(cms.item()), 4),
+                      "bus_GBps": round(nbytes * 2.0 * (world - 1) / world / (float(cms.item()) * 1e-3) / 1e9, 1)}
+
     # ---------------- breakdown: the rasterizer alone (no deformation), and for the reference arm its torch SE3 graph ----
     # north_star's target is ">= 2x the reference CUDA rasterizer's fwd+bwd throughput": both arms print
     # `rasterizer_only_ms_per_view` for the same un-deformed scene, so the ratio can be read off the two driver records.
@@ -886,6 +907,8 @@ def main():
                             "NVLink (every byte crosses PCIe once per node)" % world) if sharded else "every rank copies all parameters from its pinned host buffer"},
         "gpu_launches": launches if args.impl == "ours" else 0,
     }
+    if collective is not None:
+        out["collective"] = collective
     if train is not None:
         out["train_step"] = train
     out["breakdown"] = breakdown
