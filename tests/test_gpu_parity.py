@@ -563,6 +563,71 @@ def test_batched_forward_preprocess_is_bit_identical(mode, sync_free):
         assert rel_to_max(ga[k], gb[k]) <= 1e-5, (k, rel_to_max(ga[k], gb[k]))
 
 
+def test_view_batched_step_at_full_size_c2():
+    """BASELINE configs[1] / [4] size (1 M Gaussians, 1920x1080, several cameras per step): the view-batched step
+    (GaussianForwardBatch + GaussianBackwardBatch, sync-free forward, 4 streams - what bench.py times).
+    (1) per-Gaussian twists: images bit-identical to the per-view calls, accumulated gradients within the gradient bar;
+    (2) un-deformed scene: accumulated gradients within the gradient bar of the REFERENCE rasterizer's, summed over the views
+    (measured: batched vs reference 1.6e-5 of max on the rotations, where two runs of the reference differ by 2.5e-5)."""
+    import synthetic
+    import view_parallel as vp
+    import diff_gaussian_rasterization as dgr
+    from _gpu_util import assert_grad_close, make_view_settings
+    from diff_gaussian_rasterization import GaussianRasterizer, GaussianBackwardBatch, GaussianForwardBatch
+    P, W, H, V = 1000000, 1920, 1080, 4
+    sc, _, _ = make_view_settings(P, W, H)
+    S, th = synthetic.make_twists(P, device="cuda")
+    grad = synthetic.make_image_grad(W, H, device="cuda")
+    bg = torch.zeros(3, device="cuda")
+    settings = [synthetic.raster_settings(synthetic.make_camera(k, 64, W, H, device="cuda"), bg, sh_degree=3) for k in range(V)]
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+
+    def run(batched, deform):
+        lv = {k: sc[k].clone().requires_grad_(True) for k in names}
+        extra = {}
+        if deform:
+            lv["se3_S"], lv["se3_theta"] = S.clone().requires_grad_(True), th.clone().requires_grad_(True)
+            extra = dict(se3_S=lv["se3_S"], se3_theta=lv["se3_theta"])
+        vp.FlatGradBuffer(list(lv.values()))
+        sinks = {k: v.grad for k, v in lv.items()}
+        fwd = GaussianForwardBatch(settings, **lv) if batched else None
+        batch = GaussianBackwardBatch(sinks) if batched else None
+        images = [None] * V
+
+        def render_view(k):
+            m2 = torch.zeros(P, 3, device="cuda", requires_grad=True)
+            c, _ = GaussianRasterizer(settings[k])(means3D=lv["means3D"], means2D=m2, opacities=lv["opacities"], shs=lv["shs"],
+                                                   scales=lv["scales"], rotations=lv["rotations"], **extra,
+                                                   accumulate_grads=batch if batched else sinks,
+                                                   prepared=fwd.prepared(k) if batched else None)
+            images[k] = c.detach()
+            c.backward(grad)
+            return c.detach().sum()
+        vp.render_views(render_view, range(V), num_streams=4 if batched else 1, batch=batch)
+        torch.cuda.synchronize()
+        return images, {k: v.grad.clone() for k, v in lv.items()}
+    dgr.set_sync_free(True)
+    try:
+        run(False, True)                         # measures num_rendered per configuration for the sync-free path
+        (ia, ga), (ib, gb) = run(True, True), run(False, True)
+        _, gc = run(True, False)
+        dgr.check_sync_free()
+    finally:
+        dgr.set_sync_free(False)
+    for k in range(V):
+        assert torch.equal(ia[k], ib[k]), ("image", k)
+    for k in ga:
+        assert_grad_close(ga[k], gb[k], "batched step vs per-view, C2 x %d views: %s" % (V, k))
+    rd = _ref()
+    tot = None
+    for k in range(V):
+        f = rd.forward(settings[k], sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+        g = rd.backward(settings[k], f, grad, sc["means3D"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+        tot = {n: g[n].double() for n in names} if tot is None else {n: tot[n] + g[n].double() for n in names}
+    for n in names:
+        assert_grad_close(gc[n], tot[n].float().reshape(gc[n].shape), "batched step vs reference sum, C2 x %d views: %s" % (V, n))
+
+
 def test_packed_expf_is_cudas_expf_on_every_float():
     """The blend kernels evaluate expf on packed FP32x2 values (csrc/f32x2.cuh) with CUDA's own algorithm restated;
     it must be bit-identical to expf (what forward.cu:342 / backward.cu:472 compile to) on the whole range
