@@ -57,8 +57,8 @@ def test_workspace_sizes_and_layouts():
     bl = rt.binning_layout(R, W, H)
     assert len(set(bl.values())) == 4
     # 2 tile-id arrays + 2 value arrays + onesweep state + reference-format keys: 24..32 B per duplicate
-    # + the counting sort's chunk x tile count matrix (768 x 8160 x 4 B at 1080p), independent of R
-    matrix = 768 * 8160 * 4
+    # + the counting sort's chunk x tile count matrix (512 x 8160 x 4 B at 1080p), independent of R
+    matrix = 512 * 8160 * 4
     assert 24 * R <= lib.gsr_binning_bytes(R, W, H) - matrix <= 32 * R
     assert lib.gsr_binning_bytes(0, W, H) < matrix + (1 << 20)
     assert lib.gsr_grad_bytes(P) >= 48 * P
