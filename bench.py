@@ -39,7 +39,9 @@ sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_deformable_b200"))
 
 PARAM_KEYS = ("means3D", "scales", "rotations", "opacities", "shs")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` at the default workload (profiles/)
-NCU_TRAFFIC = {"preprocess_bwd": 581.1e6, "preprocess_fwd": 233.9e6, "blend_bwd": 110.1e6, "blend_fwd": 54.0e6}   # profiles/r02_ncu_full_metrics.csv
+NCU_TRAFFIC = {"preprocess_bwd": 581.1e6, "preprocess_fwd": 233.9e6, "blend_bwd": 110.1e6, "blend_fwd": 54.0e6,   # profiles/r02_ncu_full_metrics.csv
+               # per launch = per 8-view step (profiles/r03_ncu_batched_kernels_metrics.csv)
+               "preprocess_bwd_batched": 1484.9e6, "preprocess_fwd_batched": 753.9e6}
 
 
 # ---------------------------------------------------------------------------
