@@ -68,16 +68,21 @@ __device__ __forceinline__ f32x2 power2_exact(float dx, float s1, float s2, f32x
 // ---------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------
-template <int NP, int MINB, bool TMUL, bool STRAIGHT>
-__global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdArgs a) {
+// WPC = warps per CTA: 4 / NP (a CTA = a tile) or 1 (a CTA = one 8x8 region, NP == 1: a finished region gives its
+// registers back at once instead of holding them until the tile's slowest region is done).
+template <int NP, int MINB, bool TMUL, bool STRAIGHT, int WPC = 4 / NP>
+__global__ void __launch_bounds__(32 * WPC, MINB) blend_fwd_v2_kernel(BlendFwdArgs a) {
     constexpr int NW = 4 / NP;                       // warps (regions) per tile
-    __shared__ float4 s_q0[NW][32];                  // x, y, conic.x, -conic.y
-    __shared__ float4 s_q1[NW][32];                  // conic.z, opacity, cut, (list position + 1) as bits
-    __shared__ float4 s_q2[NW][32];                  // r, g, b, -
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.y * a.grid_x + blockIdx.x;
-    const int X0 = blockIdx.x * GSR_TILE + ((NP == 1) ? ((warp & 1) << 3) : (warp << 3));
-    const int Y0 = blockIdx.y * GSR_TILE + ((NP == 1) ? ((warp >> 1) << 3) : 0);
+    __shared__ float4 s_q0[WPC][32];                 // x, y, conic.x, -conic.y
+    __shared__ float4 s_q1[WPC][32];                 // conic.z, opacity, cut, (list position + 1) as bits
+    __shared__ float4 s_q2[WPC][32];                 // r, g, b, -
+    const int lane = threadIdx.x & 31;
+    const int warp = (WPC == 1) ? (int)((blockIdx.x & 1) | ((blockIdx.y & 1) << 1)) : (int)(threadIdx.x >> 5);   // region of the tile
+    const int sw = (WPC == 1) ? 0 : warp;
+    const int tbx = (WPC == 1) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tby = (WPC == 1) ? (int)(blockIdx.y >> 1) : (int)blockIdx.y;
+    const int tile = tby * a.grid_x + tbx;
+    const int X0 = tbx * GSR_TILE + ((NP == 1) ? ((warp & 1) << 3) : (warp << 3));
+    const int Y0 = tby * GSR_TILE + ((NP == 1) ? ((warp >> 1) << 3) : 0);
     if (X0 >= a.W || Y0 >= a.H) return;             // region outside the image: warps are independent
     const int px = X0 + (lane & 7);
     const float pxf = (float)px;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(128 / NP, MINB) blend_fwd_v2_kernel(BlendFwdAr
     }
     const uint2 range = a.ranges[tile];
     const int todo = (int)(range.y - range.x);
-    float4* const q0s = s_q0[warp]; float4* const q1s = s_q1[warp]; float4* const q2s = s_q2[warp];
+    float4* const q0s = s_q0[sw]; float4* const q1s = s_q1[sw]; float4* const q2s = s_q2[sw];
     // region masks: word (batch, region) of this tile at NW * (range.x / 32 + tile + batch) + region
     uint32_t* const mask_out = a.region_masks ? a.region_masks + (size_t)NW * ((size_t)(range.x >> 5) + (size_t)tile) + warp : nullptr;
 
@@ -653,6 +658,12 @@ int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
     static const int tmul = env_int_v2("GSR_FWD_TMUL", 0);   // T *= (1 - w) instead of a select: measured 1 % slower
     static const int straight = env_int_v2("GSR_FWD_STRAIGHT", 1);
     static const int minb = env_int_v2("GSR_FWD_MINB", 7);   // 72 regs: 7 CTAs/SM
+    // one 8x8 region per CTA by default: 0.350 vs 0.356 ms at C2 (the same variant of the backward is 3 % SLOWER)
+    static const int wpc = env_int_v2("GSR_FWD_WPC", 1);
+    if (np != 2 && wpc == 1 && straight && !tmul) {
+        const dim3 rgrid(2 * a.grid_x, 2 * a.grid_y, 1);
+        blend_fwd_v2_kernel<1, 28, false, true, 1><<<rgrid, 32, 0, stream>>>(a);
+    } else
     if (np == 2) blend_fwd_v2_kernel<2, 0, false, false><<<grid, 64, 0, stream>>>(a);
     else if (straight && tmul) blend_fwd_v2_kernel<1, 0, true, true><<<grid, 128, 0, stream>>>(a);
     else if (straight && minb == 7) blend_fwd_v2_kernel<1, 7, false, true><<<grid, 128, 0, stream>>>(a);

@@ -185,6 +185,8 @@ VARIANTS = [
     {"GSR_BLEND_FWD_V": "1", "GSR_BLEND_BWD_V": "1", "GSR_FWD_PPT": "1", "GSR_BWD_PPT": "2"},
     {"GSR_SWEEP_COUNT_V": "1", "GSR_SWEEP_SCATTER_V": "1"},               # striped sweep kernels (also the >51200-tile path)
     {"GSR_FWD_NP": "2", "GSR_BWD_NP": "2"},
+    {"GSR_FWD_WPC": "4"},                                                  # blend forward with a CTA per tile (4 regions) instead of per region
+    {"GSR_SCATTER_WARPS": "5", "GSR_SWEEP_CHUNKS": "768"},                # other groupings of the counting sort
     {"GSR_FWD_STRAIGHT": "0", "GSR_BWD_STRAIGHT": "0", "GSR_BWD_SMEM_RED": "0"},
 ]
 
