@@ -230,3 +230,42 @@ def test_lr_schedule_matches_the_reference_function():
             assert abs(f(s) - want) <= 1e-12 * max(1.0, abs(want)) + 1e-18, (name, s)
     assert list(inspect.signature(fused_adam.get_expon_lr_func).parameters) == [
         "lr_init", "lr_final", "lr_delay_steps", "lr_delay_mult", "max_steps"]
+
+
+def test_batched_slot_packing_is_host_only_and_validates():
+    """gsr_forward/backward_batched_fill_slots are pure host functions (no GPU needed): sizes, argument checks and the
+    frozen conventions they enforce (one scale_modifier / sh_degree per batch, no prefiltered / debug views)."""
+    import ctypes
+    lib = rt.load()
+    P, n = 1000, 3
+    views = [rt.make_view(_settings()) for _ in range(n)]
+    nb_f, nb_b = lib.gsr_forward_batched_slots_bytes(n), lib.gsr_backward_batched_slots_bytes(n)
+    assert nb_f > 0 and nb_b > 0 and nb_f % n == 0 and nb_b % n == 0
+    assert lib.gsr_forward_batched_slots_bytes(0) == 0 and lib.gsr_forward_batched_slots_bytes(2 * n) == 2 * nb_f
+    host = (ctypes.c_uint8 * max(nb_f, nb_b))()
+    fake = 0x10000                                       # never dereferenced: the functions only do pointer arithmetic
+    fa = (rt.gsr_view_fwd * n)()
+    ba = (rt.gsr_view_grads * n)()
+    for j in range(n):
+        fa[j].view = ctypes.pointer(views[j]); fa[j].radii = fake; fa[j].geom_ws = fake
+        ba[j].view = ctypes.pointer(views[j]); ba[j].radii = fake; ba[j].geom_ws = fake; ba[j].grad_ws = fake; ba[j].dL_dmeans2D = fake
+    assert lib.gsr_forward_batched_fill_slots(n, fa, P, 16, host, nb_f) == 0
+    assert lib.gsr_backward_batched_fill_slots(n, ba, P, 16, host, nb_b) == 0
+    assert any(host[i] for i in range(nb_b))             # something was written
+    assert lib.gsr_forward_batched_fill_slots(n, fa, P, 16, host, nb_f - 1) != 0        # buffer too small
+    assert b"too small" in lib.gsr_last_error_string()
+    assert lib.gsr_backward_batched_fill_slots(n, ba, P, 16, host, nb_b - 1) != 0
+    fa[1].geom_ws = None
+    assert lib.gsr_forward_batched_fill_slots(n, fa, P, 16, host, nb_f) != 0            # NULL workspace
+    fa[1].geom_ws = fake
+    views[2].scale_modifier = 2.0
+    assert lib.gsr_forward_batched_fill_slots(n, fa, P, 16, host, nb_f) != 0            # mixed scale_modifier
+    assert b"scale_modifier" in lib.gsr_last_error_string()
+    assert lib.gsr_backward_batched_fill_slots(n, ba, P, 16, host, nb_b) != 0
+    views[2].scale_modifier = views[0].scale_modifier
+    views[0].prefiltered = 1
+    assert lib.gsr_forward_batched_fill_slots(n, fa, P, 16, host, nb_f) != 0            # prefiltered views take the per-view path
+    views[0].prefiltered = 0
+    assert lib.gsr_forward_batched_fill_slots(n, fa, P, 16, host, nb_f) == 0
+    # depth-sort workspace query grows with P and is part of the geometry workspace
+    assert lib.gsr_depth_order_ws_bytes(1000) < lib.gsr_depth_order_ws_bytes(1000000) < lib.gsr_geom_bytes(1000000)
