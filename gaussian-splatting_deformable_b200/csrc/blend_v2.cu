@@ -77,9 +77,11 @@ __global__ void __launch_bounds__(32 * WPC, MINB) blend_fwd_v2_kernel(BlendFwdAr
     __shared__ float4 s_q1[WPC][32];                 // conic.z, opacity, cut, (list position + 1) as bits
     __shared__ float4 s_q2[WPC][32];                 // r, g, b, -
     const int lane = threadIdx.x & 31;
-    const int warp = (WPC == 1) ? (int)((blockIdx.x & 1) | ((blockIdx.y & 1) << 1)) : (int)(threadIdx.x >> 5);   // region of the tile
+    // WPC == 1: 1-D grid, block = 4 tile + region, so the four regions of a tile are dispatched together and share L2 / L1
+    const int warp = (WPC == 1) ? (int)(blockIdx.x & 3) : (int)(threadIdx.x >> 5);   // region of the tile
     const int sw = (WPC == 1) ? 0 : warp;
-    const int tbx = (WPC == 1) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tby = (WPC == 1) ? (int)(blockIdx.y >> 1) : (int)blockIdx.y;
+    const int tile1 = (int)(blockIdx.x >> 2);
+    const int tbx = (WPC == 1) ? tile1 % a.grid_x : (int)blockIdx.x, tby = (WPC == 1) ? tile1 / a.grid_x : (int)blockIdx.y;
     const int tile = tby * a.grid_x + tbx;
     const int X0 = tbx * GSR_TILE + ((NP == 1) ? ((warp & 1) << 3) : (warp << 3));
     const int Y0 = tby * GSR_TILE + ((NP == 1) ? ((warp >> 1) << 3) : 0);
@@ -275,6 +277,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // per blended (region, Gaussian)).
 constexpr int RED_E = 4, RED_STRIDE = 36;             // entries per flush; padded row (ncu: bank conflicts on 1.6 % of the kernel's shared wavefronts)
 
+// (A CTA per region, as in the forward, measured 3-4 % SLOWER here: 0.609 vs 0.585 ms.)
 template <int NP, int MINB, bool SMEM_RED, bool STRAIGHT, bool MASKS = false>
 __global__ void __launch_bounds__(128 / NP, MINB) blend_bwd_v2_kernel(BlendBwdArgs a) {
     constexpr int NW = 4 / NP;
@@ -658,10 +661,11 @@ int gsr_launch_blend_fwd_v2(const BlendFwdArgs& a, cudaStream_t stream) {
     static const int tmul = env_int_v2("GSR_FWD_TMUL", 0);   // T *= (1 - w) instead of a select: measured 1 % slower
     static const int straight = env_int_v2("GSR_FWD_STRAIGHT", 1);
     static const int minb = env_int_v2("GSR_FWD_MINB", 7);   // 72 regs: 7 CTAs/SM
-    // one 8x8 region per CTA by default: 0.350 vs 0.356 ms at C2 (the same variant of the backward is 3 % SLOWER)
+    // one 8x8 region per CTA by default, regions of a tile adjacent in a 1-D grid: 0.343 vs 0.354 ms per tile CTA at C2
+    // (2-D region grid: 0.349; the same variant of the backward is 3-4 % SLOWER)
     static const int wpc = env_int_v2("GSR_FWD_WPC", 1);
     if (np != 2 && wpc == 1 && straight && !tmul) {
-        const dim3 rgrid(2 * a.grid_x, 2 * a.grid_y, 1);
+        const dim3 rgrid(4u * (unsigned)a.grid_x * (unsigned)a.grid_y, 1, 1);
         blend_fwd_v2_kernel<1, 28, false, true, 1><<<rgrid, 32, 0, stream>>>(a);
     } else
     if (np == 2) blend_fwd_v2_kernel<2, 0, false, false><<<grid, 64, 0, stream>>>(a);
