@@ -716,9 +716,7 @@ int gsr_backward(const gsr_view* view, int P, int M, uint32_t R, const float* me
         return gsr_set_error_msg(-1, "backward: gradient buffer for a precomputed input is NULL");
     if (shs && !dL_dsh) return gsr_set_error_msg(-1, "backward: dL_dsh required when shs given");
     const GeomLayout L = geom_layout(P);
-    const ImageLayout IL = image_layout(v.W, v.H);
     const char* gw = reinterpret_cast<const char*>(geom_ws);
-    const char* iw = reinterpret_cast<const char*>(image_ws);
     float4* grad_recs = reinterpret_cast<float4*>(grad_ws);
     if (int rc = backward_blend_impl(view, v, P, R, geom_ws, binning_ws, image_ws, grad_recs, dL_dout_color, stream)) return rc;
     PreprocessBwdArgs a{};

@@ -25,7 +25,6 @@ __device__ __constant__ float bSH_C3[7] = {-0.5900435899266435f, 2.8906114426405
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 operator*(float s, V3 v) { return {s * v.x, s * v.y, s * v.z}; }
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 // d(v/|v|)/dv applied to dv  (auxiliary.h:107-117)
@@ -39,9 +38,6 @@ __device__ __forceinline__ V3 dnormvdv(V3 v, V3 dv) {
     return o;
 }
 
-__device__ __forceinline__ void store_sh(float* dst, int k, V3 g) {
-    dst[3 * k] = g.x; dst[3 * k + 1] = g.y; dst[3 * k + 2] = g.z;
-}
 
 // Output of one value: plain store, or (accumulate mode) a fire-and-forget RED so that
 // no load of the running gradient sits in the thread's dependency chain.
